@@ -1,0 +1,309 @@
+/*
+ * niagara_cull.h — C ABI of the B200-native visibility path for zeux/niagara.
+ *
+ * This library replaces the Vulkan compute dispatches of niagara's GPU-driven visibility path
+ * (reference call sites, all in src/niagara.cpp):
+ *
+ *   cull lambda      niagara.cpp:1530-1574   drawcull.comp (+ tasksubmit.comp)    -> nvc_drawcull
+ *   render lambda    niagara.cpp:1582-1610   clustercull.comp + clustersubmit.comp -> nvc_clustercull
+ *   pyramid lambda   niagara.cpp:1703-1733   depthreduce.comp, one dispatch / mip  -> nvc_depth_pyramid
+ *   task-shader path niagara.cpp:1666-1679   meshlet.task.glsl (payload variant)   -> nvc_taskcull
+ *
+ * with hand-written sm_100a CUDA kernels.  The buffer contract (struct layouts, counters, padding,
+ * overflow behaviour) is the reference's, bit for bit, so the outputs can be consumed by the existing
+ * indirect-draw path (vkCmdDrawIndexedIndirectCount / vkCmdDrawMeshTasksIndirectEXT) unchanged.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types in signatures: streams are passed as void* (a cudaStream_t),
+ *     device buffers as plain pointers to the structs below.
+ *   - every pass call only ENQUEUES work on `stream`; no allocation, no synchronisation, safe to capture
+ *     into a CUDA graph.  A context is not re-entrant (the reference's frame loop is single threaded).
+ *   - return value: 0 = NVC_OK, negative = NvcStatus error.  Capacity overflow (TASK_WGLIMIT /
+ *     CLUSTER_LIMIT) is NOT an error: it is the reference's defined drop-and-clamp behaviour.
+ *   - all struct layouts below are asserted (size/offset) against src/shaders/mesh.h + src/scene.h.
+ */
+#ifndef NIAGARA_CULL_H
+#define NIAGARA_CULL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NVC_API __declspec(dllexport)
+#else
+#define NVC_API __attribute__((visibility("default")))
+#endif
+
+/* ---- limits: src/config.h:1-28 ------------------------------------------------------------ */
+#define NVC_TASK_WGSIZE 64u           /* config.h:2  meshlets per task command / cluster-cull group  */
+#define NVC_TASK_WGLIMIT (1u << 22)   /* config.h:25 max task commands                               */
+#define NVC_CLUSTER_LIMIT (1u << 24)  /* config.h:28 max visible cluster indices                     */
+#define NVC_CLUSTER_TILE 16u          /* config.h:22 X dimension of the 16 x Y x 16 mesh dispatch    */
+#define NVC_MAX_DISPATCH_GROUPS 65535u /* tasksubmit.comp.glsl:36, clustersubmit.comp.glsl:37       */
+#define NVC_MAX_LODS 8u               /* mesh.h:77   Mesh::lods[8]                                   */
+#define NVC_MAX_HIZ_LEVELS 16u        /* sampler maxLod 16 (resources.cpp:306)                       */
+
+/* ---- data layouts: src/shaders/mesh.h:11-123 == src/scene.h:10-93 == src/niagara.cpp:227-260 ---- */
+
+/* mesh.h:11-24 / scene.h:10-23 — 24 B, 8-byte aligned.  Cull reads bytes 0..11 only. */
+typedef struct NvcMeshlet
+{
+	uint16_t center[3]; /* IEEE binary16 */
+	uint16_t radius;    /* IEEE binary16 */
+	int8_t cone_axis[3];
+	int8_t cone_cutoff;
+	uint32_t dataOffset;
+	uint32_t baseVertex;
+	uint8_t vertexCount;
+	uint8_t triangleCount;
+	uint8_t shortRefs;
+	uint8_t padding;
+} NvcMeshlet;
+
+/* mesh.h:53-60 / scene.h:68-75 — 20 B */
+typedef struct NvcMeshLod
+{
+	uint32_t indexOffset;
+	uint32_t indexCount;
+	uint32_t meshletOffset;
+	uint32_t meshletCount;
+	float error;
+} NvcMeshLod;
+
+/* mesh.h:62-78 / scene.h:77-93 — 208 B, 16-byte aligned */
+typedef struct NvcMesh
+{
+	float center[3];
+	float radius;
+	uint32_t vertexOffset;
+	uint32_t vertexCount;
+	uint32_t ommIndexData;
+	uint32_t ommIndexBase;
+	uint32_t lodCount;
+	uint32_t lodRT;
+	uint32_t padding[2];
+	NvcMeshLod lods[NVC_MAX_LODS];
+} NvcMesh;
+
+/* mesh.h:92-102 / scene.h:39-49 — 48 B, 16-byte aligned; orientation stored x,y,z,w */
+typedef struct NvcMeshDraw
+{
+	float position[3];
+	float scale;
+	float orientation[4];
+	uint32_t meshIndex;
+	uint32_t meshletVisibilityOffset;
+	uint32_t postPass;
+	uint32_t materialIndex;
+} NvcMeshDraw;
+
+/* mesh.h:104-114 / niagara.cpp:227-231 — 24 B: drawId + VkDrawIndexedIndirectCommand */
+typedef struct NvcMeshDrawCommand
+{
+	uint32_t drawId;
+	uint32_t indexCount;
+	uint32_t instanceCount;
+	uint32_t firstIndex;
+	uint32_t vertexOffset;
+	uint32_t firstInstance;
+} NvcMeshDrawCommand;
+
+/* mesh.h:116-123 / niagara.cpp:233-240 — 20 B */
+typedef struct NvcMeshTaskCommand
+{
+	uint32_t drawId;
+	uint32_t taskOffset;
+	uint32_t taskCount;
+	uint32_t lateDrawVisibility;
+	uint32_t meshletVisibilityOffset;
+} NvcMeshTaskCommand;
+
+/* mesh.h:26-44 / niagara.cpp:242-260 — 144 B (alignas 16), passed verbatim (the reference's push constants) */
+typedef struct NvcCullData
+{
+	float view[16]; /* column-major mat4 */
+	float P00, P11, znear, zfar;
+	float frustum[4];
+	float lodTarget;
+	float pyramidWidth, pyramidHeight;
+	uint32_t drawCount;
+	int32_t cullingEnabled;
+	int32_t lodEnabled;
+	int32_t occlusionEnabled;
+	int32_t clusterOcclusionEnabled;
+	int32_t clusterBackfaceEnabled;
+	uint32_t postPass;
+	uint32_t pad_[2];
+} NvcCullData;
+
+/* mesh.h:125-128 — task-shader payload (meshlet.task.glsl:47) */
+typedef struct NvcMeshTaskPayload
+{
+	uint32_t clusterIndices[NVC_TASK_WGSIZE];
+} NvcMeshTaskPayload;
+
+/* Depth pyramid ("depthPyramid" image, niagara.cpp:1339-1350): R32F, width x height = previousPow2 of the
+ * depth target, full mip chain.  In place of a VkImage: one linear device allocation, level l stored
+ * row-major and tightly packed at texels + level_offset[l], size max(1,width>>l) x max(1,height>>l). */
+typedef struct NvcHiZ
+{
+	float* texels; /* device pointer */
+	uint32_t width, height, levels;
+	uint32_t level_offset[NVC_MAX_HIZ_LEVELS]; /* in texels */
+	uint32_t total_texels;
+} NvcHiZ;
+
+typedef struct NvcLimits
+{
+	uint32_t task_wglimit;  /* default NVC_TASK_WGLIMIT  */
+	uint32_t cluster_limit; /* default NVC_CLUSTER_LIMIT */
+} NvcLimits;
+
+typedef enum NvcStatus
+{
+	NVC_OK = 0,
+	NVC_ERROR_INVALID_ARGUMENT = -1,
+	NVC_ERROR_CUDA = -2,
+	NVC_ERROR_NO_DEVICE = -3,
+	NVC_ERROR_OUT_OF_MEMORY = -4,
+	NVC_ERROR_NCCL = -5
+} NvcStatus;
+
+typedef struct NvcContext NvcContext;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Replaces pipeline/program creation for the cull path (niagara.cpp:652-762).  `limits` may be NULL. */
+NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx);
+NVC_API void nvc_destroy(NvcContext* ctx);
+NVC_API const char* nvc_status_string(int status);
+/* last CUDA error text recorded by this context (for NVC_ERROR_CUDA) */
+NVC_API const char* nvc_last_error(const NvcContext* ctx);
+NVC_API const char* nvc_version(void);
+
+/* ---- pyramid layout (host only): niagara.cpp:439-447 previousPow2, resources.cpp:280-292 getImageMipLevels,
+ *      niagara.cpp:1339-1342 ------------------------------------------------------------------------- */
+NVC_API uint32_t nvc_previous_pow2(uint32_t v);
+NVC_API uint32_t nvc_image_mip_levels(uint32_t width, uint32_t height);
+/* Fills width/height/levels/level_offset/total_texels for a depth target of depth_width x depth_height;
+ * leaves `texels` NULL (caller allocates total_texels * 4 bytes on the device). */
+NVC_API int nvc_hiz_layout(uint32_t depth_width, uint32_t depth_height, NvcHiZ* out);
+
+/* ---- passes ---------------------------------------------------------------------------------- */
+
+/* drawcull.comp.glsl:54-156 for all four (LATE, TASK) specialisations; when task != 0 the
+ * tasksubmit.comp.glsl:27-47 epilogue (group counts + zero padding to x64) is fused into the same launch.
+ *   draws            MeshDraw[cull->drawCount]                      (db)
+ *   meshes           Mesh[]                                         (mb)
+ *   draw_visibility  uint32[drawCount], read; written when late     (dvb)
+ *   commands         task ? MeshTaskCommand[task_wglimit] : MeshDrawCommand[drawCount]   (dcb)
+ *   command_count4   uint32[4] {commandCount, groupCountX, groupCountY, groupCountZ}      (dccb)
+ *                    fully written by the call (the host-side vkCmdFillBuffer reset of niagara.cpp:1541 is
+ *                    folded in); for task == 0 only [0] is meaningful, [1..3] are set to 0.
+ *   hiz              depth pyramid; required when late && cull->occlusionEnabled == 1, else may be NULL */
+NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late, int task,
+    const NvcMeshDraw* draws, const NvcMesh* meshes, uint32_t* draw_visibility,
+    void* commands, uint32_t* command_count4, const NvcHiZ* hiz);
+
+/* clustercull.comp.glsl:56-149 (LATE = 0/1) with the clustersubmit.comp.glsl:25-45 epilogue fused.
+ * Processes commandId < command_count4[1] * 64 exactly as the reference's indirect dispatch (X,64,1) does.
+ *   task_commands       MeshTaskCommand[] written by nvc_drawcull(task=1)   (dcb)
+ *   command_count4      uint32[4] written by nvc_drawcull(task=1)           (dccb)
+ *   meshlets            Meshlet[]                                            (mlb)
+ *   meshlet_visibility  bit array, read; atomically updated when late        (mvb)
+ *   cluster_indices     uint32[cluster_limit rounded up to 256]              (cib)
+ *   cluster_count4      uint32[4] {clusterCount, 16, Y, 16}, fully written   (ccb) */
+NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late,
+    const NvcMeshTaskCommand* task_commands, const uint32_t* command_count4,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
+    uint32_t* cluster_indices, uint32_t* cluster_count4, const NvcHiZ* hiz);
+
+/* meshlet.task.glsl:53-149 (task-shader submission mode, niagara.cpp:1666-1679): same per-meshlet test as
+ * nvc_clustercull, but the survivors of command c are compacted into payloads[c].clusterIndices[0..n) and
+ * n is written to emit_counts[c] (the EmitMeshTasksEXT(n,1,1) argument).  Order inside a payload is
+ * ascending lane (the reference's shared-memory atomic makes it arbitrary). */
+NVC_API int nvc_taskcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late,
+    const NvcMeshTaskCommand* task_commands, const uint32_t* command_count4,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
+    NvcMeshTaskPayload* payloads, uint32_t* emit_counts, const NvcHiZ* hiz);
+
+/* depthreduce.comp.glsl:14-22 + the per-mip loop of niagara.cpp:1703-1733, as ONE launch.
+ *   depth  float[depth_height][depth_width], reverse-Z (the D32 depthTarget)
+ *   hiz    layout from nvc_hiz_layout(depth_width, depth_height) with `texels` set */
+NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
+    uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz);
+
+/* ---- host-side helpers mirroring the reference's host code (pure CPU, no context needed) ---------- */
+
+/* niagara.cpp:449-481 PCG32 + rand01/rand32 and the random scene of niagara.cpp:969-998.
+ * Fills draws[draw_count] exactly as the reference does (rng state = 0x42, inc = PCG32 default). */
+NVC_API void nvc_host_random_draws(NvcMeshDraw* draws, uint32_t draw_count, uint32_t mesh_count, float scene_radius);
+
+/* niagara.cpp:1002-1020: meshletVisibilityOffset = exclusive prefix sum over draws of max-over-LODs
+ * meshletCount; returns the total bit count; *post_pass_mask gets OR(1 << postPass) (may be NULL). */
+NVC_API uint32_t nvc_host_visibility_offsets(NvcMeshDraw* draws, uint32_t draw_count, const NvcMesh* meshes, uint32_t* post_pass_mask);
+
+typedef struct NvcCamera
+{
+	float position[3];
+	float orientation[4]; /* x,y,z,w */
+	float fovY;
+	float znear;
+} NvcCamera;
+
+typedef struct NvcCullOptions
+{
+	float draw_distance; /* zfar, niagara.cpp:1000 (200) */
+	int32_t culling, lod, occlusion, cluster_occlusion, mesh_shading; /* runtime toggles niagara.cpp:31-44 */
+	int32_t debug_lod_step;
+} NvcCullOptions;
+
+/* niagara.cpp:424-432 + 1487-1516: view, infinite reverse-Z projection, frustum planes, lodTarget, pyramid size.
+ * Leaves clusterBackfaceEnabled = 0 and postPass = 0 exactly like `cullData` at niagara.cpp:1499-1516;
+ * the per-pass copies (niagara.cpp:1547-1550, 1595-1596) are the caller's job, see nvc_host_pass_data. */
+NVC_API void nvc_host_cull_data(const NvcCamera* camera, uint32_t screen_width, uint32_t screen_height,
+    uint32_t draw_count, const NvcCullOptions* options, NvcCullData* out, float* out_projection16 /* may be NULL */);
+
+/* passData of the cull lambda (niagara.cpp:1547-1550): clusterBackfaceEnabled = (postPass == 0), postPass set. */
+NVC_API void nvc_host_pass_data(const NvcCullData* frame, int for_drawcull, uint32_t post_pass, NvcCullData* out);
+
+/* ---- multi-GPU: exchange of the per-rank visible slabs (new in this implementation; the reference is single-GPU) */
+
+/* Bootstraps an NCCL communicator owned by the context.  unique_id is the 128-byte ncclUniqueId produced by
+ * nvc_nccl_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed broadcast). */
+NVC_API int nvc_nccl_unique_id(void* out_unique_id128);
+NVC_API int nvc_nccl_init(NvcContext* ctx, const void* unique_id128, int rank, int world_size);
+/* Gathers every rank's {count, slab[0..slab_capacity)} into gathered_counts[world] and
+ * gathered[world][slab_capacity] on every rank (one ncclAllGather each), after globalising nothing: ids inside
+ * the slabs are rank-local; rank r's base draw id is the caller's partition offset. */
+NVC_API int nvc_allgather_visible(NvcContext* ctx, void* stream, const void* local_slab, size_t slab_bytes,
+    const uint32_t* local_count4, void* gathered_slabs, uint32_t* gathered_count4);
+
+#ifdef __cplusplus
+} /* extern "C" */
+
+static_assert(sizeof(NvcMeshlet) == 24, "Meshlet must match src/shaders/mesh.h:11-24");
+static_assert(sizeof(NvcMeshLod) == 20, "MeshLod must match src/shaders/mesh.h:53-60");
+static_assert(sizeof(NvcMesh) == 208, "Mesh must match src/shaders/mesh.h:62-78");
+static_assert(sizeof(NvcMeshDraw) == 48, "MeshDraw must match src/shaders/mesh.h:92-102");
+static_assert(sizeof(NvcMeshDrawCommand) == 24, "MeshDrawCommand must match src/shaders/mesh.h:104-114");
+static_assert(sizeof(NvcMeshTaskCommand) == 20, "MeshTaskCommand must match src/shaders/mesh.h:116-123");
+static_assert(sizeof(NvcCullData) == 144, "CullData must match src/niagara.cpp:242-260 (alignas 16)");
+static_assert(offsetof(NvcMesh, lods) == 48, "Mesh::lods offset");
+static_assert(offsetof(NvcMesh, lodCount) == 32, "Mesh::lodCount offset");
+static_assert(offsetof(NvcMeshDraw, meshIndex) == 32, "MeshDraw::meshIndex offset");
+static_assert(offsetof(NvcMeshlet, cone_axis) == 8, "Meshlet::cone_axis offset");
+static_assert(offsetof(NvcMeshlet, dataOffset) == 12, "Meshlet::dataOffset offset");
+static_assert(offsetof(NvcCullData, P00) == 64, "CullData::P00 offset");
+static_assert(offsetof(NvcCullData, frustum) == 80, "CullData::frustum offset");
+static_assert(offsetof(NvcCullData, lodTarget) == 96, "CullData::lodTarget offset");
+static_assert(offsetof(NvcCullData, drawCount) == 108, "CullData::drawCount offset");
+static_assert(offsetof(NvcCullData, clusterBackfaceEnabled) == 128, "CullData::clusterBackfaceEnabled offset");
+static_assert(offsetof(NvcCullData, postPass) == 132, "CullData::postPass offset");
+#endif
+
+#endif /* NIAGARA_CULL_H */

@@ -1,0 +1,237 @@
+// nvc_api.cu — the C ABI declared in include/niagara_cull.h (context, argument validation, launches).
+#include "nvc_internal.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace
+{
+
+int cuda_fail(NvcContext* ctx, cudaError_t e, const char* what)
+{
+	if (ctx)
+		ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+	return NVC_ERROR_CUDA;
+}
+
+bool fill_hiz(const NvcHiZ* in, nvc::HiZDesc& out)
+{
+	memset(&out, 0, sizeof(out));
+	if (!in)
+		return false;
+	if (!in->texels || in->levels == 0 || in->levels > NVC_MAX_HIZ_LEVELS || in->width == 0 || in->height == 0)
+		return false;
+	out.texels = in->texels;
+	out.width = in->width;
+	out.height = in->height;
+	out.levels = in->levels;
+	memcpy(out.level_offset, in->level_offset, sizeof(out.level_offset));
+	return true;
+}
+
+} // namespace
+
+extern "C"
+{
+
+NVC_API const char* nvc_version(void)
+{
+	return "niagara_b200 0.1 (sm_100a)";
+}
+
+NVC_API const char* nvc_status_string(int status)
+{
+	switch (status)
+	{
+	case NVC_OK:
+		return "ok";
+	case NVC_ERROR_INVALID_ARGUMENT:
+		return "invalid argument";
+	case NVC_ERROR_CUDA:
+		return "CUDA error";
+	case NVC_ERROR_NO_DEVICE:
+		return "no CUDA device";
+	case NVC_ERROR_OUT_OF_MEMORY:
+		return "out of memory";
+	case NVC_ERROR_NCCL:
+		return "NCCL error";
+	default:
+		return "unknown status";
+	}
+}
+
+NVC_API const char* nvc_last_error(const NvcContext* ctx)
+{
+	return ctx ? ctx->last_error.c_str() : "";
+}
+
+NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx)
+{
+	if (!out_ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	*out_ctx = nullptr;
+
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+		return NVC_ERROR_NO_DEVICE; // no CPU fallback: the product path needs a GPU
+	if (device < 0 || device >= count)
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	NvcContext* ctx = new NvcContext();
+	ctx->device = device;
+	if (limits)
+	{
+		if (limits->task_wglimit == 0 || limits->cluster_limit == 0 || limits->cluster_limit > (1u << 24) || limits->task_wglimit > (1u << 24))
+		{
+			delete ctx;
+			return NVC_ERROR_INVALID_ARGUMENT; // cluster index packs a 24-bit command id
+		}
+		ctx->limits = *limits;
+	}
+
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess)
+		e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&ctx->scratch, sizeof(nvc::Scratch));
+	if (e == cudaSuccess)
+		e = cudaMemset(ctx->scratch, 0, sizeof(nvc::Scratch));
+	if (e == cudaSuccess)
+		e = nvc::clustercull_occupancy(&ctx->cluster_blocks_early, &ctx->cluster_blocks_late);
+	if (e == cudaSuccess)
+		e = cudaDeviceSynchronize();
+	if (e != cudaSuccess)
+	{
+		fprintf(stderr, "nvc_create: %s\n", cudaGetErrorString(e));
+		if (ctx->scratch)
+			cudaFree(ctx->scratch);
+		delete ctx;
+		return e == cudaErrorMemoryAllocation ? NVC_ERROR_OUT_OF_MEMORY : NVC_ERROR_CUDA;
+	}
+	if (ctx->cluster_blocks_early < 1)
+		ctx->cluster_blocks_early = 1;
+	if (ctx->cluster_blocks_late < 1)
+		ctx->cluster_blocks_late = 1;
+
+	*out_ctx = ctx;
+	return NVC_OK;
+}
+
+NVC_API void nvc_destroy(NvcContext* ctx)
+{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	nvc::nccl_destroy(ctx);
+	if (ctx->scratch)
+		cudaFree(ctx->scratch);
+	delete ctx;
+}
+
+NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late, int task,
+    const NvcMeshDraw* draws, const NvcMesh* meshes, uint32_t* draw_visibility,
+    void* commands, uint32_t* command_count4, const NvcHiZ* hiz)
+{
+	if (!ctx || !cull || !commands || !command_count4)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (cull->drawCount && (!draws || !meshes || !draw_visibility))
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	nvc::DrawCullParams p;
+	memset(&p, 0, sizeof(p));
+	p.cull = *cull;
+	p.draws = draws;
+	p.meshes = meshes;
+	p.draw_visibility = draw_visibility;
+	p.commands = commands;
+	p.command_count4 = command_count4;
+	p.scratch = ctx->scratch;
+	p.task_wglimit = ctx->limits.task_wglimit;
+	bool need_hiz = late && cull->occlusionEnabled == 1;
+	if (!fill_hiz(hiz, p.hiz) && need_hiz)
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_drawcull");
+}
+
+static int fill_cluster_params(NvcContext* ctx, const NvcCullData* cull, int late, const NvcMeshTaskCommand* task_commands,
+    const uint32_t* command_count4, const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
+    const NvcHiZ* hiz, nvc::ClusterParams& p)
+{
+	if (!ctx || !cull || !task_commands || !command_count4 || !draws || !meshlets)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (cull->clusterOcclusionEnabled == 1 && !meshlet_visibility)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	memset(&p, 0, sizeof(p));
+	p.cull = *cull;
+	p.task_commands = task_commands;
+	p.command_count4 = command_count4;
+	p.draws = draws;
+	p.meshlets = meshlets;
+	p.meshlet_visibility = meshlet_visibility;
+	p.scratch = ctx->scratch;
+	p.cluster_limit = ctx->limits.cluster_limit;
+	bool need_hiz = late && cull->clusterOcclusionEnabled == 1;
+	if (!fill_hiz(hiz, p.hiz) && need_hiz)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	return NVC_OK;
+}
+
+NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late,
+    const NvcMeshTaskCommand* task_commands, const uint32_t* command_count4,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
+    uint32_t* cluster_indices, uint32_t* cluster_count4, const NvcHiZ* hiz)
+{
+	if (!cluster_indices || !cluster_count4)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	nvc::ClusterParams p;
+	int s = fill_cluster_params(ctx, cull, late, task_commands, command_count4, draws, meshlets, meshlet_visibility, hiz, p);
+	if (s != NVC_OK)
+		return s;
+	p.cluster_indices = cluster_indices;
+	p.cluster_count4 = cluster_count4;
+
+	uint32_t blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_blocks_late : ctx->cluster_blocks_early);
+	cudaError_t e = nvc::launch_clustercull(p, late != 0, blocks, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_clustercull");
+}
+
+NVC_API int nvc_taskcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late,
+    const NvcMeshTaskCommand* task_commands, const uint32_t* command_count4,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
+    NvcMeshTaskPayload* payloads, uint32_t* emit_counts, const NvcHiZ* hiz)
+{
+	if (!payloads || !emit_counts)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	nvc::ClusterParams p;
+	int s = fill_cluster_params(ctx, cull, late, task_commands, command_count4, draws, meshlets, meshlet_visibility, hiz, p);
+	if (s != NVC_OK)
+		return s;
+	uint32_t blocks = uint32_t(ctx->sm_count) * 4u;
+	cudaError_t e = nvc::launch_taskcull(p, late != 0, payloads, emit_counts, blocks, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_taskcull");
+}
+
+NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
+    uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz)
+{
+	if (!ctx || !depth || !hiz || depth_width == 0 || depth_height == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	nvc::PyramidParams p;
+	memset(&p, 0, sizeof(p));
+	if (!fill_hiz(hiz, p.hiz))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	// the pyramid must be the one the reference would allocate for this depth target (niagara.cpp:1339-1342)
+	if (hiz->width != nvc_previous_pow2(depth_width) || hiz->height != nvc_previous_pow2(depth_height) ||
+	    hiz->levels != nvc_image_mip_levels(hiz->width, hiz->height))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	p.depth = depth;
+	p.depth_width = depth_width;
+	p.depth_height = depth_height;
+	p.scratch = ctx->scratch;
+	cudaError_t e = nvc::launch_pyramid(p, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_depth_pyramid");
+}
+
+} // extern "C"

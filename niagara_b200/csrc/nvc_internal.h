@@ -1,0 +1,100 @@
+// nvc_internal.h — types shared between the C ABI (nvc_api.cu) and the kernels (nvc_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/niagara_cull.h"
+
+namespace nvc
+{
+struct Scratch;
+}
+
+struct NvcContext
+{
+	int device = 0;
+	int sm_count = 0;
+	int cluster_blocks_early = 0, cluster_blocks_late = 0;
+	NvcLimits limits = { NVC_TASK_WGLIMIT, NVC_CLUSTER_LIMIT };
+	nvc::Scratch* scratch = nullptr;
+	std::string last_error;
+	void* nccl_comm = nullptr; // ncclComm_t, owned (nvc_nccl.cpp)
+	int nccl_rank = 0, nccl_world = 1;
+};
+
+namespace nvc
+{
+void nccl_destroy(NvcContext* ctx); // nvc_nccl.cpp
+
+// Device-side counters owned by the context.  Each pass's last-block epilogue leaves them zeroed, which replaces
+// the reference's vkCmdFillBuffer resets (niagara.cpp:1541,1586) and keeps every pass a single launch.
+// Hot atomics live on separate 128-byte lines.
+struct alignas(128) Scratch
+{
+	uint32_t draw_counter;
+	uint32_t pad0[31];
+	uint32_t draw_done;
+	uint32_t pad1[31];
+	uint32_t cluster_counter;
+	uint32_t pad2[31];
+	uint32_t cluster_done;
+	uint32_t pad3[31];
+	uint32_t cluster_batch;
+	uint32_t pad4[31];
+	uint32_t pyramid_done;
+	uint32_t pad5[31];
+};
+
+struct HiZDesc
+{
+	float* texels;
+	uint32_t width, height, levels;
+	uint32_t level_offset[NVC_MAX_HIZ_LEVELS];
+};
+
+struct DrawCullParams
+{
+	NvcCullData cull;
+	const NvcMeshDraw* draws;
+	const NvcMesh* meshes;
+	uint32_t* draw_visibility;
+	void* commands;
+	uint32_t* command_count4;
+	Scratch* scratch;
+	HiZDesc hiz;
+	uint32_t task_wglimit;
+};
+
+struct ClusterParams
+{
+	NvcCullData cull;
+	const NvcMeshTaskCommand* task_commands;
+	const uint32_t* command_count4;
+	const NvcMeshDraw* draws;
+	const NvcMeshlet* meshlets;
+	uint32_t* meshlet_visibility;
+	uint32_t* cluster_indices;
+	uint32_t* cluster_count4;
+	Scratch* scratch;
+	HiZDesc hiz;
+	uint32_t cluster_limit;
+};
+
+struct PyramidParams
+{
+	const float* depth;
+	uint32_t depth_width, depth_height;
+	HiZDesc hiz;
+	Scratch* scratch;
+};
+
+cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream);
+cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream);
+cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream);
+cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream);
+cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late);
+
+} // namespace nvc

@@ -1,0 +1,787 @@
+// nvc_kernels.cu — sm_100a kernels of the visibility path.
+//
+//   drawcull_kernel<LATE,TASK>   drawcull.comp.glsl:54-156  (+ tasksubmit.comp.glsl:27-47 as last-block epilogue)
+//   clustercull_kernel<LATE>     clustercull.comp.glsl:56-149 (+ clustersubmit.comp.glsl:25-45 as last-block epilogue)
+//   taskcull_kernel<LATE>        meshlet.task.glsl:53-149
+//   pyramid_kernel<EXACT>        depthreduce.comp.glsl:14-22 x all mips (niagara.cpp:1703-1733) in one launch
+//
+// Everything here is HBM/L2/ALU work on plain CUDA cores — there is no dense contraction, so no tensor cores.
+// Compiled with -fmad=false; see nvc_math.cuh for the arithmetic contract.
+#include "nvc_internal.h"
+#include "nvc_math.cuh"
+
+#include <cuda_runtime.h>
+
+namespace nvc
+{
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t lane_id()
+{
+	return threadIdx.x & 31u;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+__device__ __forceinline__ uint32_t lanemask_le()
+{
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+	return m;
+}
+
+// streaming 128-bit read-only load (each MeshDraw byte is touched once per pass)
+__device__ __forceinline__ float4 ldg_f4(const void* p)
+{
+	return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ uint4 ldg_u4(const void* p)
+{
+	return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+struct HiZLoad
+{
+	const float* base;
+	__device__ __forceinline__ float operator()(uint32_t idx) const { return __ldg(base + idx); }
+};
+
+// drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123
+__device__ __forceinline__ bool occlusion_visible(const NvcCullData& cd, const HiZDesc& hiz, f3 center, float radius)
+{
+	float4 aabb;
+	if (!project_sphere(center, radius, cd.znear, cd.P00, cd.P11, aabb))
+		return true;
+	int level = occlusion_mip(aabb, cd.pyramidWidth, cd.pyramidHeight, int(hiz.levels) - 1);
+	uint32_t w = max(1u, hiz.width >> level), h = max(1u, hiz.height >> level);
+	float u = __fmul_rn(__fadd_rn(aabb.x, aabb.z), 0.5f);
+	float v = __fmul_rn(__fadd_rn(aabb.y, aabb.w), 0.5f);
+	HiZLoad load = { hiz.texels + hiz.level_offset[level] };
+	float depth = sample_min(load, w, h, u, v);
+	float depthSphere = __fdiv_rn(cd.znear, __fsub_rn(center.z, radius));
+	return depthSphere > depth;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// drawcull
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kDrawBlock = 256;
+
+template <bool LATE, bool TASK>
+__global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
+{
+	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
+	__shared__ uint32_t s_block_base;
+	__shared__ uint32_t s_is_last;
+
+	const NvcCullData& cd = p.cull;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31u, warp = tid >> 5;
+	const uint32_t di = blockIdx.x * kDrawBlock + tid;
+
+	bool emit = false;
+	uint32_t units = 0; // commands this thread appends: taskGroups (TASK) or 1
+	uint32_t dv = 0;
+	uint32_t meshIndex = 0, lodIndex = 0, mvOffset = 0;
+
+	if (di < cd.drawCount)
+	{
+		const char* dp = reinterpret_cast<const char*>(p.draws + di);
+		float4 d0 = ldg_f4(dp);      // position.xyz, scale
+		float4 d1 = ldg_f4(dp + 16); // orientation
+		uint4 d2 = ldg_u4(dp + 32);  // meshIndex, meshletVisibilityOffset, postPass, materialIndex
+		meshIndex = d2.x;
+		mvOffset = d2.y;
+
+		bool reached = d2.z == cd.postPass; // :63
+		if (reached)
+		{
+			dv = p.draw_visibility[di];
+			if (!LATE && dv == 0) // :67
+				reached = false;
+		}
+
+		if (reached)
+		{
+			const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
+			float4 m0 = ldg_f4(mp); // center.xyz, radius
+
+			f3 mc = { m0.x, m0.y, m0.z };
+			f3 rc = rotate_quat(mc, d1);
+			f3 center = { __fadd_rn(__fmul_rn(rc.x, d0.w), d0.x), __fadd_rn(__fmul_rn(rc.y, d0.w), d0.y), __fadd_rn(__fmul_rn(rc.z, d0.w), d0.z) };
+			center = transform_point(cd.view, center);
+			float radius = __fmul_rn(m0.w, d0.w);
+
+			bool visible = frustum_visible(cd, center, radius);
+			visible = visible || cd.cullingEnabled == 0; // :85
+
+			if (LATE && visible && cd.occlusionEnabled == 1) // :87
+				visible = occlusion_visible(cd, p.hiz, center, radius);
+
+			// :108  (TASK_CULL == 1, config.h:8)
+			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv == 0 || cd.postPass != 0))
+			{
+				if (cd.lodEnabled == 1) // :112-120
+				{
+					float d = __fsub_rn(length3(center), radius);
+					float distance = d > 0.f ? d : 0.f;
+					float threshold = __fdiv_rn(__fmul_rn(distance, cd.lodTarget), d0.w);
+					uint32_t lodCount = __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
+					lodCount = min(lodCount, NVC_MAX_LODS);
+					for (uint32_t i = 1; i < lodCount; ++i)
+						if (__ldg(reinterpret_cast<const float*>(mp + 48 + i * 20 + 16)) < threshold)
+							lodIndex = i;
+				}
+				emit = true;
+				if (TASK)
+				{
+					uint32_t meshletCount = __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 12));
+					units = (meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
+				}
+				else
+					units = 1;
+			}
+
+			if (LATE)
+				p.draw_visibility[di] = visible ? 1u : 0u; // :154-155
+		}
+	}
+
+	// ---- block-wide exclusive scan of `units`, ONE global atomicAdd per block (the GLSL does one per thread) ----
+	uint32_t incl = units;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= uint32_t(o))
+			incl += n;
+	}
+	if (lane == 31)
+		s_warp_total[warp] = incl;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t t = lane < kDrawBlock / 32 ? s_warp_total[lane] : 0;
+		uint32_t ti = t;
+#pragma unroll
+		for (int o = 1; o < kDrawBlock / 32; o <<= 1)
+		{
+			uint32_t n = __shfl_up_sync(0xffffffffu, ti, o);
+			if (lane >= uint32_t(o))
+				ti += n;
+		}
+		if (lane < kDrawBlock / 32)
+			s_warp_total[lane] = ti - t; // exclusive warp offsets
+		uint32_t total = __shfl_sync(0xffffffffu, ti, kDrawBlock / 32 - 1);
+		if (lane == 0)
+			s_block_base = total ? atomicAdd(&p.scratch->draw_counter, total) : 0u;
+	}
+	__syncthreads();
+
+	if (emit)
+	{
+		uint32_t dci = s_block_base + s_warp_total[warp] + (incl - units);
+		const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
+		const uint32_t* lp = reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20);
+		if (TASK)
+		{
+			// :129 drop on overflow; the counter has already advanced
+			if (uint64_t(dci) + units <= p.task_wglimit)
+			{
+				uint32_t meshletOffset = __ldg(lp + 2), meshletCount = __ldg(lp + 3);
+				NvcMeshTaskCommand* out = static_cast<NvcMeshTaskCommand*>(p.commands) + dci;
+				for (uint32_t i = 0; i < units; ++i)
+				{
+					out[i].drawId = di;
+					out[i].taskOffset = meshletOffset + i * NVC_TASK_WGSIZE;
+					out[i].taskCount = min(NVC_TASK_WGSIZE, meshletCount - i * NVC_TASK_WGSIZE);
+					out[i].lateDrawVisibility = dv;
+					out[i].meshletVisibilityOffset = mvOffset + i * NVC_TASK_WGSIZE;
+				}
+			}
+		}
+		else
+		{
+			NvcMeshDrawCommand* out = static_cast<NvcMeshDrawCommand*>(p.commands) + dci;
+			out->drawId = di;
+			out->indexCount = __ldg(lp + 1);
+			out->instanceCount = 1;
+			out->firstIndex = __ldg(lp + 0);
+			out->vertexOffset = __ldg(reinterpret_cast<const uint32_t*>(mp + 16));
+			out->firstInstance = 0;
+		}
+	}
+
+	// ---- last-block epilogue: tasksubmit.comp.glsl:27-47 (TASK) / publish the count (draw path) ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+		s_is_last = atomicAdd(&p.scratch->draw_done, 1u) == gridDim.x - 1;
+	__syncthreads();
+	if (!s_is_last)
+		return;
+	__threadfence();
+
+	uint32_t commandCount = *reinterpret_cast<volatile uint32_t*>(&p.scratch->draw_counter);
+	if (TASK)
+	{
+		uint32_t count = min(commandCount, p.task_wglimit);
+		if (tid == 0)
+		{
+			p.command_count4[0] = commandCount;
+			p.command_count4[1] = min((count + 63) / 64, NVC_MAX_DISPATCH_GROUPS);
+			p.command_count4[2] = 64;
+			p.command_count4[3] = 1;
+		}
+		uint32_t boundary = (count + 63) & ~63u;
+		if (tid < 64 && count + tid < boundary)
+		{
+			NvcMeshTaskCommand* out = static_cast<NvcMeshTaskCommand*>(p.commands) + count + tid;
+			out->drawId = 0;
+			out->taskOffset = 0;
+			out->taskCount = 0;
+			out->lateDrawVisibility = 0;
+			out->meshletVisibilityOffset = 0;
+		}
+	}
+	else if (tid == 0)
+	{
+		p.command_count4[0] = commandCount;
+		p.command_count4[1] = 0;
+		p.command_count4[2] = 0;
+		p.command_count4[3] = 0;
+	}
+	__syncthreads();
+	if (tid == 0)
+	{
+		// leave the scratch counters zeroed for the next pass: replaces vkCmdFillBuffer(dccb, 0, 4, 0) niagara.cpp:1541
+		p.scratch->draw_counter = 0;
+		p.scratch->draw_done = 0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-meshlet test shared by clustercull / taskcull
+// ------------------------------------------------------------------------------------------------------
+
+// clustercull.comp.glsl:72-124 for one valid lane.  Returns `visible`; `skip` by reference.
+template <bool LATE>
+__device__ __forceinline__ bool meshlet_test(const ClusterParams& p, uint32_t drawId, uint32_t lateDrawVisibility, uint32_t mi, uint32_t mvi, bool& skip)
+{
+	const NvcCullData& cd = p.cull;
+	skip = false;
+	bool visible = true;
+
+	const bool track = cd.clusterOcclusionEnabled == 1 && cd.postPass == 0; // :86
+	if (track)
+	{
+		// early: read-only this pass.  late: only this lane's own bit matters and nobody else changes it.
+		uint32_t word = LATE ? __ldcg(p.meshlet_visibility + (mvi >> 5)) : __ldg(p.meshlet_visibility + (mvi >> 5));
+		bool bit = (word >> (mvi & 31u)) & 1u;
+		if (!LATE && !bit)
+			return false; // :91-92 — nothing below has side effects in the early pass
+		if (LATE && lateDrawVisibility == 1 && bit)
+			skip = true; // :97-98
+	}
+
+	const char* dp = reinterpret_cast<const char*>(p.draws + drawId);
+	float4 d0 = ldg_f4(dp);      // position.xyz, scale
+	float4 d1 = ldg_f4(dp + 16); // orientation
+
+	const char* mp = reinterpret_cast<const char*>(p.meshlets + mi);
+	uint2 b0 = __ldg(reinterpret_cast<const uint2*>(mp));        // center[3], radius (4 x binary16)
+	uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8)); // cone_axis[3], cone_cutoff (4 x s8)
+
+	f3 lc = { half_bits_to_float(b0.x & 0xffffu), half_bits_to_float(b0.x >> 16), half_bits_to_float(b0.y & 0xffffu) };
+	f3 rc = rotate_quat(lc, d1);
+	f3 center = { __fadd_rn(__fmul_rn(rc.x, d0.w), d0.x), __fadd_rn(__fmul_rn(rc.y, d0.w), d0.y), __fadd_rn(__fmul_rn(rc.z, d0.w), d0.z) };
+	center = transform_point(cd.view, center);
+	float radius = __fmul_rn(half_bits_to_float(b0.y >> 16), d0.w);
+
+	// cheapest rejection first; the GLSL's `visible && ...` chain is a pure conjunction so the order is free
+	visible = frustum_visible(cd, center, radius); // :104-108
+	if (!visible)
+		return false;
+
+	if (cd.clusterBackfaceEnabled != 0) // :102
+	{
+		f3 la = { s8_div127(int(int8_t(b1 & 0xffu))), s8_div127(int(int8_t((b1 >> 8) & 0xffu))), s8_div127(int(int8_t((b1 >> 16) & 0xffu))) };
+		f3 axis = transform_vector(cd.view, rotate_quat(la, d1));
+		float cutoff = s8_div127(int(int8_t(b1 >> 24)));
+		// math.h:41-44 with camera_position = 0
+		bool backface = dot3(center, axis) >= __fadd_rn(__fmul_rn(cutoff, length3(center)), radius);
+		if (backface)
+			return false;
+	}
+
+	if (LATE && cd.clusterOcclusionEnabled == 1) // :110
+		visible = occlusion_visible(cd, p.hiz, center, radius);
+
+	return visible;
+}
+
+// clustercull.comp.glsl:126-131 for one 32-item chunk: lanes with consecutive bit indices inside one word form a run;
+// the run's head lane applies the whole run with at most two atomics (the GLSL issues one atomic per lane).
+__device__ __forceinline__ void update_visibility_bits(uint32_t* mvb, bool active, bool visible, uint32_t mvi)
+{
+	const uint32_t lane = lane_id();
+	uint32_t prev_mvi = __shfl_up_sync(0xffffffffu, mvi, 1);
+	uint32_t act = __ballot_sync(0xffffffffu, active);
+	bool prev_active = lane > 0 && ((act >> (lane - 1)) & 1u);
+	bool head = active && (!prev_active || mvi != prev_mvi + 1 || (mvi & 31u) == 0);
+	uint32_t heads = __ballot_sync(0xffffffffu, head);
+	uint32_t vis = __ballot_sync(0xffffffffu, active && visible);
+	if (!head)
+		return;
+
+	// run = [lane, next head or first inactive lane)
+	uint32_t stop = (heads | ~act) & ~lanemask_le();
+	uint32_t end = stop ? uint32_t(__ffs(int(stop)) - 1) : 32u;
+	uint32_t len = end - lane; // 1..32
+	uint32_t runmask = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+	uint32_t shift = mvi & 31u;
+	uint32_t all = runmask << shift; // the run never crosses a word boundary ((mvi & 31) == 0 starts a new run)
+	uint32_t set = ((vis >> lane) & runmask) << shift;
+	uint32_t* word = mvb + (mvi >> 5);
+	if (all == 0xffffffffu)
+		*word = set; // all 32 bits of the word belong to this run: no other thread touches it this pass
+	else
+	{
+		if (set)
+			atomicOr(word, set);
+		uint32_t clr = all & ~set;
+		if (clr)
+			atomicAnd(word, ~clr);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// clustercull
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kClusterBlock = 256;
+constexpr int kClusterWarps = kClusterBlock / 32;
+constexpr int kStage = 256; // staged cluster indices per warp before one global atomicAdd + coalesced write-out
+
+__device__ __forceinline__ void flush_stage(const ClusterParams& p, uint32_t* stage, uint32_t& nst)
+{
+	const uint32_t lane = lane_id();
+	__syncwarp();
+	uint32_t base = 0;
+	if (lane == 0)
+		base = atomicAdd(&p.scratch->cluster_counter, nst); // :135, aggregated
+	base = __shfl_sync(0xffffffffu, base, 0);
+	for (uint32_t i = lane; i < nst; i += 32)
+	{
+		uint32_t index = base + i;
+		if (index < p.cluster_limit) // :137
+			p.cluster_indices[index] = stage[i];
+	}
+	__syncwarp();
+	nst = 0;
+}
+
+template <bool LATE>
+__global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const ClusterParams p)
+{
+	__shared__ uint32_t s_stage[kClusterWarps][kStage];
+	__shared__ uint32_t s_is_last;
+
+	const NvcCullData& cd = p.cull;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31u, warp = tid >> 5;
+	uint32_t* stage = s_stage[warp];
+	uint32_t nst = 0;
+
+	// the reference dispatches (X,64,1) groups from dccb+4 (niagara.cpp:1599): commandId < X * 64
+	const uint32_t ncmd = p.command_count4[1] * 64u;
+	const uint32_t nbatch = (ncmd + 31u) / 32u;
+	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
+
+	for (;;)
+	{
+		// dynamic batch of 32 consecutive task commands per warp
+		uint32_t batch = 0;
+		if (lane == 0)
+			batch = atomicAdd(&p.scratch->cluster_batch, 1u);
+		batch = __shfl_sync(0xffffffffu, batch, 0);
+		if (batch >= nbatch)
+			break;
+
+		const uint32_t cid = batch * 32u + lane;
+		uint32_t c_draw = 0, c_task = 0, c_count = 0, c_late = 0, c_mvo = 0;
+		if (cid < ncmd)
+		{
+			const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + cid);
+			c_draw = __ldg(cp + 0);
+			c_task = __ldg(cp + 1);
+			c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
+			c_late = __ldg(cp + 3);
+			c_mvo = __ldg(cp + 4);
+		}
+
+		// flatten (command, mgi) pairs: inclusive scan of taskCount over the batch
+		uint32_t incl = c_count;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= uint32_t(o))
+				incl += n;
+		}
+		const uint32_t excl = incl - c_count;
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		// per-command values with the exclusive offset folded in, so an item only needs `item + rel`
+		const uint32_t rel_task = c_task - excl;
+		const uint32_t rel_mvo = c_mvo - excl;
+		const uint32_t nz = __ballot_sync(0xffffffffu, c_count != 0);
+		const bool nz_prefix = (nz & (nz + 1u)) == 0; // non-empty commands form a prefix (always, except stale slots)
+
+		for (uint32_t base = 0; base < total; base += 32)
+		{
+			const uint32_t item = base + lane;
+			const bool active = item < total;
+
+			// which command does my item belong to?
+			uint32_t j;
+			if (nz_prefix)
+			{
+				// head bits: commands that START inside this chunk (bit 0 excluded: that command is `first`)
+				uint32_t rel = excl - base;
+				uint32_t hbit = (c_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
+				uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
+				uint32_t first = __popc(__ballot_sync(0xffffffffu, c_count != 0 && incl <= base));
+				j = first + __popc(heads & lanemask_le());
+			}
+			else
+			{
+				// generic: binary search for the smallest j with incl[j] > item
+				j = 0;
+#pragma unroll
+				for (int s = 16; s >= 1; s >>= 1)
+				{
+					uint32_t v = __shfl_sync(0xffffffffu, incl, (j + s - 1) & 31u);
+					if (v <= item)
+						j += s;
+				}
+			}
+			j &= 31u;
+
+			const uint32_t drawId = __shfl_sync(0xffffffffu, c_draw, j);
+			const uint32_t lateVis = __shfl_sync(0xffffffffu, c_late, j);
+			const uint32_t mi = __shfl_sync(0xffffffffu, rel_task, j) + item;
+			const uint32_t mvi = __shfl_sync(0xffffffffu, rel_mvo, j) + item;
+			const uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j);
+
+			bool skip = false;
+			bool visible = false;
+			if (active)
+				visible = meshlet_test<LATE>(p, drawId, lateVis, mi, mvi, skip);
+
+			if (track_late) // :126-131
+				update_visibility_bits(p.meshlet_visibility, active, visible, mvi);
+
+			const bool out = visible && !skip; // :133
+			const uint32_t omask = __ballot_sync(0xffffffffu, out);
+			const uint32_t n = __popc(omask);
+			if (n)
+			{
+				if (nst + n > kStage)
+					flush_stage(p, stage, nst);
+				if (out)
+					stage[nst + __popc(omask & lanemask_lt())] = (batch * 32u + j) | (mgi << 24); // :138
+				nst += n;
+			}
+		}
+	}
+	if (nst)
+		flush_stage(p, stage, nst);
+
+	// ---- last-block epilogue: clustersubmit.comp.glsl:25-45 ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+		s_is_last = atomicAdd(&p.scratch->cluster_done, 1u) == gridDim.x - 1;
+	__syncthreads();
+	if (!s_is_last)
+		return;
+	__threadfence();
+
+	uint32_t clusterCount = *reinterpret_cast<volatile uint32_t*>(&p.scratch->cluster_counter);
+	uint32_t count = min(clusterCount, p.cluster_limit);
+	if (tid == 0)
+	{
+		p.cluster_count4[0] = clusterCount;
+		p.cluster_count4[1] = NVC_CLUSTER_TILE;
+		p.cluster_count4[2] = min((count + 255) / 256, NVC_MAX_DISPATCH_GROUPS);
+		p.cluster_count4[3] = 256 / NVC_CLUSTER_TILE;
+	}
+	uint32_t boundary = (count + 255) & ~255u;
+	if (count + tid < boundary) // blockDim == 256 == the reference's local_size_x
+		p.cluster_indices[count + tid] = ~0u;
+	__syncthreads();
+	if (tid == 0)
+	{
+		p.scratch->cluster_counter = 0; // replaces vkCmdFillBuffer(ccb, 0, 4, 0) niagara.cpp:1586
+		p.scratch->cluster_done = 0;
+		p.scratch->cluster_batch = 0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// taskcull: meshlet.task.glsl:53-149 — one warp per command (two 32-lane halves), payload compaction per command
+// ------------------------------------------------------------------------------------------------------
+
+template <bool LATE>
+__global__ void __launch_bounds__(kClusterBlock) taskcull_kernel(const ClusterParams p, NvcMeshTaskPayload* payloads, uint32_t* emit_counts)
+{
+	const NvcCullData& cd = p.cull;
+	const uint32_t lane = lane_id();
+	const uint32_t ncmd = p.command_count4[1] * 64u;
+	const uint32_t warps_total = gridDim.x * kClusterWarps;
+	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
+
+	for (uint32_t cid = blockIdx.x * kClusterWarps + (threadIdx.x >> 5); cid < ncmd; cid += warps_total)
+	{
+		const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + cid);
+		const uint32_t c_draw = __ldg(cp + 0), c_task = __ldg(cp + 1), c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE);
+		const uint32_t c_late = __ldg(cp + 3), c_mvo = __ldg(cp + 4);
+
+		uint32_t sharedCount = 0; // :71
+#pragma unroll 1
+		for (uint32_t half = 0; half < 2; ++half)
+		{
+			const uint32_t mgi = half * 32 + lane;
+			const bool active = mgi < c_count;
+			if (!__any_sync(0xffffffffu, active))
+				break;
+			bool skip = false, visible = false;
+			if (active)
+				visible = meshlet_test<LATE>(p, c_draw, c_late, c_task + mgi, c_mvo + mgi, skip);
+			if (track_late)
+				update_visibility_bits(p.meshlet_visibility, active, visible, c_mvo + mgi);
+			const bool out = visible && !skip;
+			const uint32_t omask = __ballot_sync(0xffffffffu, out);
+			if (out)
+				payloads[cid].clusterIndices[sharedCount + __popc(omask & lanemask_lt())] = cid | (mgi << 24); // :137-139
+			sharedCount += __popc(omask);
+		}
+		if (lane == 0)
+			emit_counts[cid] = sharedCount; // EmitMeshTasksEXT(sharedCount, 1, 1)  :143
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// depth pyramid: all mips in ONE launch.
+// Each CTA owns a 64x64 tile of mip 0 (128x128 depth texels when the ratio is exactly 2:1), reduces it through
+// mips 0..6 in shared memory, writing every level; the last CTA to finish (global ticket) reduces the remaining
+// small mips.  min() is exact and order independent, so the result is bit-identical to the reference's
+// level-by-level dispatch chain (niagara.cpp:1713-1728).
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kPyrBlock = 256;
+constexpr int kPyrTile = 64; // mip-0 texels per CTA edge
+constexpr int kPyrTileLevels = 7; // 64 -> 1
+
+struct DepthLoad
+{
+	const float* base;
+	__device__ __forceinline__ float operator()(uint32_t idx) const { return __ldg(base + idx); }
+};
+
+// dst(x, y) = min of src[2x..2x+1][2y..2y+1] clamped to the source extent (exact 2:1 MIN-sampler footprint)
+__device__ __forceinline__ float reduce2x2(const float* src, uint32_t sw, uint32_t sh, uint32_t spitch, uint32_t x, uint32_t y)
+{
+	uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1);
+	uint32_t y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+	return fminf(fminf(src[y0 * spitch + x0], src[y0 * spitch + x1]), fminf(src[y1 * spitch + x0], src[y1 * spitch + x1]));
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams p)
+{
+	__shared__ float s_a[kPyrTile * kPyrTile];             // level 0 tile, later levels 2, 4, 6
+	__shared__ float s_b[(kPyrTile / 2) * (kPyrTile / 2)]; // levels 1, 3, 5
+	__shared__ uint32_t s_is_last;
+
+	const HiZDesc& hz = p.hiz;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t tile_x = blockIdx.x * kPyrTile, tile_y = blockIdx.y * kPyrTile;
+
+	// ---- mip 0 from the depth target: depthreduce.comp.glsl:19 with imageSize = (hz.width, hz.height) ----
+	{
+		const uint32_t lw = hz.width, lh = hz.height;
+		float* dst = hz.texels + hz.level_offset[0];
+		for (uint32_t i = tid; i < kPyrTile * kPyrTile; i += kPyrBlock)
+		{
+			uint32_t lx = i % kPyrTile, ly = i / kPyrTile;
+			uint32_t x = tile_x + lx, y = tile_y + ly;
+			float v = 0.f;
+			if (x < lw && y < lh)
+			{
+				if (EXACT)
+				{
+					// depth is exactly (2*lw) x (2*lh): footprint is the 2x2 block
+					const float2* r0 = reinterpret_cast<const float2*>(p.depth + size_t(2 * y) * p.depth_width + 2 * x);
+					const float2* r1 = reinterpret_cast<const float2*>(p.depth + size_t(2 * y + 1) * p.depth_width + 2 * x);
+					float2 a = __ldg(r0), b = __ldg(r1);
+					v = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
+				}
+				else
+				{
+					float u = __fdiv_rn(__fadd_rn(float(x), 0.5f), float(lw));
+					float w = __fdiv_rn(__fadd_rn(float(y), 0.5f), float(lh));
+					DepthLoad load = { p.depth };
+					v = sample_min(load, p.depth_width, p.depth_height, u, w);
+				}
+				dst[size_t(y) * lw + x] = v;
+			}
+			s_a[i] = v;
+		}
+	}
+	__syncthreads();
+
+	// ---- mips 1..6 of this tile in shared memory ----
+	float* src = s_a;
+	float* out = s_b;
+	uint32_t src_pitch = kPyrTile;
+	for (uint32_t l = 1; l < kPyrTileLevels && l < hz.levels; ++l)
+	{
+		const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
+		const uint32_t pw = max(1u, hz.width >> (l - 1)), ph = max(1u, hz.height >> (l - 1)); // previous level size
+		const uint32_t edge = kPyrTile >> l;                                                       // tile edge at this level
+		const uint32_t ox = tile_x >> l, oy = tile_y >> l;                                         // tile origin at this level
+		const uint32_t pox = tile_x >> (l - 1), poy = tile_y >> (l - 1);
+		// valid extent of the previous level inside this tile
+		const uint32_t sw = min(kPyrTile >> (l - 1), pw > pox ? pw - pox : 0u), sh = min(kPyrTile >> (l - 1), ph > poy ? ph - poy : 0u);
+		float* dst = hz.texels + hz.level_offset[l];
+		for (uint32_t i = tid; i < edge * edge; i += kPyrBlock)
+		{
+			uint32_t lx = i % edge, ly = i / edge;
+			uint32_t x = ox + lx, y = oy + ly;
+			float v = 0.f;
+			if (x < lw && y < lh && sw && sh)
+			{
+				v = reduce2x2(src, sw, sh, src_pitch, lx, ly);
+				dst[size_t(y) * lw + x] = v;
+			}
+			out[ly * edge + lx] = v;
+		}
+		__syncthreads();
+		float* t = src;
+		src = out;
+		out = t;
+		src_pitch = edge;
+	}
+
+	if (hz.levels <= kPyrTileLevels && gridDim.x * gridDim.y == 1)
+		return; // single tile covered every level
+
+	// ---- remaining mips by the last CTA to finish ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+		s_is_last = atomicAdd(&p.scratch->pyramid_done, 1u) == gridDim.x * gridDim.y - 1;
+	__syncthreads();
+	if (!s_is_last)
+		return;
+	__threadfence();
+
+	// first level not completed by the tiles: a level is complete iff l < kPyrTileLevels; but tiles whose extent
+	// degenerates (non-square pyramids) still wrote every texel of those levels, so start at kPyrTileLevels.
+	for (uint32_t l = kPyrTileLevels; l < hz.levels; ++l)
+	{
+		const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
+		const uint32_t pw = max(1u, hz.width >> (l - 1)), ph = max(1u, hz.height >> (l - 1));
+		const float* prev = hz.texels + hz.level_offset[l - 1];
+		float* dst = hz.texels + hz.level_offset[l];
+		for (uint32_t i = tid; i < lw * lh; i += kPyrBlock)
+		{
+			uint32_t x = i % lw, y = i / lw;
+			uint32_t x0 = min(2 * x, pw - 1), x1 = min(2 * x + 1, pw - 1);
+			uint32_t y0 = min(2 * y, ph - 1), y1 = min(2 * y + 1, ph - 1);
+			// written by other CTAs / earlier iterations of this loop: bypass L1
+			float v = fminf(fminf(__ldcg(prev + y0 * pw + x0), __ldcg(prev + y0 * pw + x1)), fminf(__ldcg(prev + y1 * pw + x0), __ldcg(prev + y1 * pw + x1)));
+			dst[i] = v;
+		}
+		__threadfence_block();
+		__syncthreads();
+	}
+	if (tid == 0)
+		p.scratch->pyramid_done = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------
+
+cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
+{
+	uint32_t blocks = (p.cull.drawCount + kDrawBlock - 1) / kDrawBlock;
+	if (blocks == 0)
+		blocks = 1;
+	if (late)
+	{
+		if (task)
+			drawcull_kernel<true, true><<<blocks, kDrawBlock, 0, stream>>>(p);
+		else
+			drawcull_kernel<true, false><<<blocks, kDrawBlock, 0, stream>>>(p);
+	}
+	else
+	{
+		if (task)
+			drawcull_kernel<false, true><<<blocks, kDrawBlock, 0, stream>>>(p);
+		else
+			drawcull_kernel<false, false><<<blocks, kDrawBlock, 0, stream>>>(p);
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream)
+{
+	if (late)
+		clustercull_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p);
+	else
+		clustercull_kernel<false><<<blocks, kClusterBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream)
+{
+	if (late)
+		taskcull_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p, payloads, emit_counts);
+	else
+		taskcull_kernel<false><<<blocks, kClusterBlock, 0, stream>>>(p, payloads, emit_counts);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream)
+{
+	dim3 grid((p.hiz.width + kPyrTile - 1) / kPyrTile, (p.hiz.height + kPyrTile - 1) / kPyrTile);
+	bool exact = p.depth_width == 2 * p.hiz.width && p.depth_height == 2 * p.hiz.height;
+	if (exact)
+		pyramid_kernel<true><<<grid, kPyrBlock, 0, stream>>>(p);
+	else
+		pyramid_kernel<false><<<grid, kPyrBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
+{
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_kernel<false>, kClusterBlock, 0);
+	if (e != cudaSuccess)
+		return e;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_kernel<true>, kClusterBlock, 0);
+}
+
+} // namespace nvc

@@ -1,0 +1,167 @@
+"""VisibilityPath — the host-side mirror of the reference's hot-path call sites (src/niagara.cpp):
+
+    cull(late, post_pass)             niagara.cpp:1530-1574   cull lambda   (drawcull [+ tasksubmit])
+    render_clusters(late, post_pass)  niagara.cpp:1582-1610   cluster block of the render lambda (clustercull + clustersubmit)
+    pyramid(depth)                    niagara.cpp:1703-1733   pyramid lambda (depthreduce per mip)
+    frame(...)                        niagara.cpp:1765-1788   pass order: early cull/render, pyramid, late cull/render[, post]
+
+Buffers carry the reference's names (db, mb, mlb, dvb, mvb, dcb, dccb, cib, ccb, depthPyramid; niagara.cpp:1027-1090).
+PyTorch is only used to own device memory and streams; every pass goes through the C ABI (libniagara_cull.so)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import layout
+from .lib import check, load_library
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class VisibilityPath:
+    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True):
+        """meshes / meshlets / draws: structured numpy arrays (layout.MESH_DTYPE / MESHLET_DTYPE / MESHDRAW_DTYPE) or
+        already-resident torch uint8 tensors.  draws must already carry meshletVisibilityOffset
+        (host.visibility_offsets)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("VisibilityPath needs a CUDA device; there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        self.mesh_shading = bool(mesh_shading)
+        torch.cuda.set_device(self.device)
+
+        limits = layout.Limits(task_wglimit, cluster_limit)
+        ctx = ctypes.c_void_p()
+        check(self.lib.nvc_create(self.device.index or 0, ctypes.byref(limits), ctypes.byref(ctx)), None, "nvc_create")
+        self.ctx = ctx
+        self.task_wglimit = int(task_wglimit)
+        self.cluster_limit = int(cluster_limit)
+
+        self.draw_count = int(len(draws)) if not isinstance(draws, torch.Tensor) else draws.numel() // layout.MESHDRAW_DTYPE.itemsize
+        self.mb = self._upload(meshes)
+        self.mlb = self._upload(meshlets)
+        self.db = self._upload(draws)
+
+        # niagara.cpp:1062-1090
+        self.dvb = torch.zeros(max(1, self.draw_count), dtype=torch.int32, device=self.device)
+        cmd_bytes = max(_round_up(self.task_wglimit, 64) * layout.MESHTASKCOMMAND_DTYPE.itemsize, self.draw_count * layout.MESHDRAWCOMMAND_DTYPE.itemsize)
+        self.dcb = torch.zeros(cmd_bytes, dtype=torch.uint8, device=self.device)
+        self.dccb = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.cib = torch.zeros(_round_up(self.cluster_limit, 256), dtype=torch.int32, device=self.device)
+        self.ccb = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.mvb = None  # sized by set_visibility_bits()
+
+        self.depth_width, self.depth_height = int(depth_width), int(depth_height)
+        self.hiz = layout.HiZ()
+        check(self.lib.nvc_hiz_layout(self.depth_width, self.depth_height, ctypes.byref(self.hiz)), self.ctx, "nvc_hiz_layout")
+        self.depthPyramid = torch.zeros(self.hiz.total_texels, dtype=torch.float32, device=self.device)
+        self.hiz.texels = self.depthPyramid.data_ptr()
+
+    # -- buffers ------------------------------------------------------------------------------------------
+    def _upload(self, arr):
+        if isinstance(arr, torch.Tensor):
+            return arr.to(self.device)
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        return torch.from_numpy(raw.copy()).to(self.device)
+
+    def set_visibility_bits(self, meshlet_visibility_count):
+        """mvb: (count + 31) / 32 words, zeroed on the first frame (niagara.cpp:1020,1081,1460-1468)."""
+        words = max(1, (int(meshlet_visibility_count) + 31) // 32)
+        self.mvb = torch.zeros(words, dtype=torch.int32, device=self.device)
+
+    def update_draws(self, draws):
+        """The reference rewrites the host-visible `db` when animating (niagara.cpp:1362-1411)."""
+        raw = torch.from_numpy(np.ascontiguousarray(draws).view(np.uint8).reshape(-1))
+        self.db.copy_(raw, non_blocking=True)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.nvc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- passes -------------------------------------------------------------------------------------------
+    def cull(self, cull_data, late, post_pass=0, task=None):
+        """cull lambda, niagara.cpp:1530-1574.  task defaults to meshSubmit (mesh shading on)."""
+        task = self.mesh_shading if task is None else task
+        pass_data = layout.CullData()
+        self.lib.nvc_host_pass_data(ctypes.byref(cull_data), 1, post_pass, ctypes.byref(pass_data))
+        check(
+            self.lib.nvc_drawcull(self.ctx, self._stream(), ctypes.byref(pass_data), int(late), int(task), _ptr(self.db), _ptr(self.mb), _ptr(self.dvb), _ptr(self.dcb), _ptr(self.dccb), ctypes.byref(self.hiz)),
+            self.ctx,
+            "nvc_drawcull",
+        )
+
+    def render_clusters(self, cull_data, late, post_pass=0, cluster_backface=None):
+        """clusterSubmit block of the render lambda, niagara.cpp:1582-1610.  cluster_backface=None keeps the
+        reference's wiring (flag stays 0 for this pass); True/False overrides it."""
+        pass_data = layout.CullData()
+        self.lib.nvc_host_pass_data(ctypes.byref(cull_data), 0, post_pass, ctypes.byref(pass_data))
+        if cluster_backface is not None:
+            pass_data.clusterBackfaceEnabled = int(cluster_backface)
+        check(
+            self.lib.nvc_clustercull(self.ctx, self._stream(), ctypes.byref(pass_data), int(late), _ptr(self.dcb), _ptr(self.dccb), _ptr(self.db), _ptr(self.mlb), _ptr(self.mvb), _ptr(self.cib), _ptr(self.ccb), ctypes.byref(self.hiz)),
+            self.ctx,
+            "nvc_clustercull",
+        )
+
+    def task_shading(self, cull_data, late, payloads, emit_counts, post_pass=0, cluster_backface=None):
+        """taskShadingEnabled path, niagara.cpp:1666-1679 (meshlet.task.glsl)."""
+        pass_data = layout.CullData()
+        self.lib.nvc_host_pass_data(ctypes.byref(cull_data), 0, post_pass, ctypes.byref(pass_data))
+        if cluster_backface is not None:
+            pass_data.clusterBackfaceEnabled = int(cluster_backface)
+        check(
+            self.lib.nvc_taskcull(self.ctx, self._stream(), ctypes.byref(pass_data), int(late), _ptr(self.dcb), _ptr(self.dccb), _ptr(self.db), _ptr(self.mlb), _ptr(self.mvb), _ptr(payloads), _ptr(emit_counts), ctypes.byref(self.hiz)),
+            self.ctx,
+            "nvc_taskcull",
+        )
+
+    def pyramid(self, depth):
+        """pyramid lambda, niagara.cpp:1703-1733.  depth: float32 device tensor [depth_height, depth_width]."""
+        assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.numel() == self.depth_width * self.depth_height
+        check(self.lib.nvc_depth_pyramid(self.ctx, self._stream(), _ptr(depth), self.depth_width, self.depth_height, ctypes.byref(self.hiz)), self.ctx, "nvc_depth_pyramid")
+
+    def frame(self, cull_data, depth, post_passes=False, cluster_backface=None):
+        """One frame of the hot path in the reference's order (niagara.cpp:1765-1788).  `depth` stands in for the
+        depth target the early render would have produced."""
+        self.cull(cull_data, late=False)
+        if self.mesh_shading:
+            self.render_clusters(cull_data, late=False, cluster_backface=cluster_backface)
+        self.pyramid(depth)
+        self.cull(cull_data, late=True)
+        if self.mesh_shading:
+            self.render_clusters(cull_data, late=True, cluster_backface=cluster_backface)
+        if post_passes:
+            self.cull(cull_data, late=True, post_pass=1)
+            if self.mesh_shading:
+                self.render_clusters(cull_data, late=True, post_pass=1, cluster_backface=cluster_backface)
+
+    # -- readback helpers (tests / e2e) -----------------------------------------------------------------------
+    def read_counts(self):
+        return self.dccb.cpu().numpy().astype(np.uint32), self.ccb.cpu().numpy().astype(np.uint32)
+
+    def read_task_commands(self, count):
+        n = int(count) * layout.MESHTASKCOMMAND_DTYPE.itemsize
+        return self.dcb[:n].cpu().numpy().view(layout.MESHTASKCOMMAND_DTYPE)
+
+    def read_draw_commands(self, count):
+        n = int(count) * layout.MESHDRAWCOMMAND_DTYPE.itemsize
+        return self.dcb[:n].cpu().numpy().view(layout.MESHDRAWCOMMAND_DTYPE)
+
+    def read_cluster_indices(self, count):
+        return self.cib[: int(count)].cpu().numpy().astype(np.uint32)
