@@ -1,0 +1,247 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bar: bit-exact — identical visible sets, lod selection, counters, padding, dvb / mvb words, every pyramid texel.
+Only ORDER inside dcb / cib may differ (atomics), exactly as in the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from niagara_b200 import host, layout, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    return torch
+
+
+def _paths(s, **kw):
+    from niagara_b200.path import VisibilityPath
+
+    torch = _torch()
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, **kw)
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8, **kw)
+    g.set_visibility_bits(s.visibility_bits)
+    o.set_visibility_bits(s.visibility_bits)
+    depth = torch.from_numpy(s.depth).cuda()
+    return g, o, depth
+
+
+def _compare_draw_pass(g, o, task, what):
+    torch = _torch()
+    torch.cuda.synchronize()
+    gd, _ = g.read_counts()
+    od, _ = o.read_counts()
+    assert np.array_equal(gd, od), (what, gd, od)
+    if task:
+        n = int(gd[1]) * 64  # includes the zero padding written by the tasksubmit epilogue
+        assert np.array_equal(oracle_lib.sorted_commands(g.read_task_commands(n)), oracle_lib.sorted_commands(o.read_task_commands(n))), what
+    else:
+        n = int(gd[0])
+        assert np.array_equal(oracle_lib.sorted_commands(g.read_draw_commands(n)), oracle_lib.sorted_commands(o.read_draw_commands(n))), what
+    assert np.array_equal(g.dvb.cpu().numpy().astype(np.uint32)[: len(o.dvb)], o.dvb), what
+
+
+def _compare_cluster_pass(g, o, what):
+    torch = _torch()
+    torch.cuda.synchronize()
+    gd, gc = g.read_counts()
+    od, oc = o.read_counts()
+    assert np.array_equal(gc, oc), (what, gc, oc)
+    n = int(gc[0])
+    gt, ot = g.read_task_commands(int(gd[1]) * 64), o.read_task_commands(int(od[1]) * 64)
+    assert np.array_equal(oracle_lib.cluster_pairs(g.read_cluster_indices(n), gt), oracle_lib.cluster_pairs(o.read_cluster_indices(n), ot)), what
+    pad = (n + 255) // 256 * 256
+    assert (g.read_cluster_indices(pad)[n:] == 0xFFFFFFFF).all(), what
+    assert np.array_equal(g.mvb.cpu().numpy().astype(np.uint32), o.mvb), what
+
+
+def _compare_pyramid(g, o, what):
+    _torch().cuda.synchronize()
+    assert np.array_equal(g.depthPyramid.cpu().numpy().view(np.uint32), o.pyramid_texels.view(np.uint32)), what
+
+
+def _run_frames(s, frames=2, cameras=None, toggles=None, cluster_backface=True, **kw):
+    g, o, depth = _paths(s, **kw)
+    for f in range(frames):
+        if cameras:
+            s.camera = cameras[f % len(cameras)]
+        cd = s.cull_data(**(toggles or {}))
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+                o.pyramid(s.depth)
+                _compare_pyramid(g, o, ("pyramid", f))
+            g.cull(cd, late)
+            o.cull(cd, late)
+            _compare_draw_pass(g, o, g.mesh_shading, ("cull", f, late))
+            if g.mesh_shading:
+                g.render_clusters(cd, late, cluster_backface=cluster_backface)
+                o.render_clusters(cd, late, cluster_backface=cluster_backface)
+                _compare_cluster_pass(g, o, ("clusters", f, late))
+    return g, o
+
+
+def test_kitten_4096_two_phase(golden_dir):
+    """BASELINE configs[0] geometry (kitten.obj cooked by the reference's scene.cpp), 4096 instanced draws."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten.nvcg"), 4096)
+    g, o = _run_frames(s, frames=3)
+    assert o.read_counts()[0][0] > 0
+
+
+@pytest.mark.parametrize(
+    "toggles",
+    [dict(lod=False), dict(culling=False), dict(occlusion=False), dict(cluster_occlusion=False), dict(debug_lod_step=3)],
+)
+def test_toggles(golden_dir, toggles):
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 20000, screen=(1280, 720))
+    _run_frames(s, frames=2, toggles=toggles)
+
+
+@pytest.mark.parametrize("backface", [False, True, None])
+def test_cluster_backface_flag(golden_dir, backface):
+    """clusterBackfaceEnabled 0 / 1 / reference wiring (never set for the cluster pass)."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 15000, screen=(1024, 768))
+    _run_frames(s, frames=2, cluster_backface=backface)
+
+
+def test_moving_camera_multi_frame(golden_dir):
+    """Early/late interplay: the camera moves and turns every frame so draws and meshlets change visibility state."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 60000, screen=(1920, 1080))
+    cams = [
+        host.make_camera((0, 0, 0)),
+        host.make_camera((30, -10, 20), host.quat_from_axis_angle((0, 1, 0), 0.4)),
+        host.make_camera((60, 5, -40), host.quat_from_axis_angle((0.2, 1, 0.1), 1.3)),
+        host.make_camera((-20, 40, 10), host.quat_from_axis_angle((1, 0.3, 0), -0.7)),
+    ]
+    _run_frames(s, frames=5, cameras=cams)
+
+
+def test_draw_path_without_mesh_shading(golden_dir):
+    """TASK = 0 variants: MeshDrawCommand output for vkCmdDrawIndexedIndirectCount (niagara.cpp:1680-1694)."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 50000, screen=(1024, 768))
+    _run_frames(s, frames=3, toggles=dict(mesh_shading=False, cluster_occlusion=False), mesh_shading=False)
+
+
+def test_post_pass_draws(golden_dir):
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 8000)
+    s.draws["postPass"][::3] = 1
+    g, o, depth = _paths(s)
+    cd = s.cull_data()
+    for f in range(2):
+        g.frame(cd, depth, post_passes=True, cluster_backface=True)
+        o.frame(cd, s.depth, post_passes=True, cluster_backface=True)
+        _compare_draw_pass(g, o, True, ("post", f))
+        _compare_cluster_pass(g, o, ("post", f))
+
+
+def test_empty_and_tiny_inputs(golden_dir):
+    meshes, meshlets, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten.nvcg"))
+    for n in (0, 1, 31, 33, 257):
+        s = scenes.reference_random_scene(meshes, meshlets, max(n, 1), screen=(64, 48))
+        s.draws["position"][:] = (0, 0, -20)  # in front of the default camera (view z = -world z)
+        s.draws = s.draws[:n] if n else s.draws[:1]
+        g, o, depth = _paths(s)
+        cd = s.cull_data()
+        if n == 0:
+            cd.drawCount = 0
+        for f in range(2):
+            g.frame(cd, depth, cluster_backface=True)
+            o.frame(cd, s.depth, cluster_backface=True)
+            _compare_draw_pass(g, o, True, ("tiny", n, f))
+            _compare_cluster_pass(g, o, ("tiny", n, f))
+
+
+@pytest.mark.parametrize("size", [(64, 64), (128, 128), (100, 60), (1920, 1080), (4096, 4096), (2048, 256), (30, 17), (3, 2), (1, 1), (4096, 600)])
+def test_pyramid_sizes(size):
+    torch = _torch()
+    from niagara_b200.path import VisibilityPath
+
+    w, h = size
+    rng = np.random.default_rng(w + 7 * h)
+    depth = rng.random((h, w), dtype=np.float32)
+    dummy = (np.zeros(1, layout.MESH_DTYPE), np.zeros(1, layout.MESHLET_DTYPE), np.zeros(1, layout.MESHDRAW_DTYPE))
+    g = VisibilityPath(*dummy, w, h, task_wglimit=64, cluster_limit=256)
+    o = oracle_lib.OraclePath(*dummy, w, h, threads=8)
+    for rep in range(2):  # second run checks that the ticket counter was left reset
+        g.depthPyramid.zero_()
+        g.pyramid(torch.from_numpy(depth).cuda())
+        o.pyramid(depth)
+        _compare_pyramid(g, o, size)
+
+
+def test_overflow_limits(golden_dir):
+    """TASK_WGLIMIT / CLUSTER_LIMIT overflow (drawcull.comp.glsl:129, clustercull.comp.glsl:137, the submit clamps):
+    counters keep counting, writes are dropped, dispatch sizes clamp.  WHICH draws are dropped depends on atomic
+    order, so compare counters, clamps, padding and that everything written is a subset of the unlimited result."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten.nvcg"), 30000, screen=(800, 600))
+    s.draws["position"][:, 2] = -np.abs(s.draws["position"][:, 2]) * 0.3 - 5
+    s.draws["position"][:, :2] *= 0.05
+    cd = s.cull_data()
+    full_g, full_o = _run_frames(s, frames=1)
+    fd, fc = full_o.read_counts()
+    assert fd[0] > 1000 and fc[0] > 5000
+    wg, cl = 640, 2048
+    g, o, depth = _paths(s, task_wglimit=wg, cluster_limit=cl)
+    g.dcb.zero_()
+    for late in (False, True):
+        g.pyramid(depth)
+        o.pyramid(s.depth)
+        g.cull(cd, late)
+        o.cull(cd, late)
+        _torch().cuda.synchronize()
+        gd, _ = g.read_counts()
+        od, _ = o.read_counts()
+        assert np.array_equal(gd, od)  # count unclamped, X clamped identically
+        g.render_clusters(cd, late, cluster_backface=True)
+        _torch().cuda.synchronize()
+        _, gc = g.read_counts()
+        if late:
+            assert gd[0] == fd[0] and gd[0] > wg and gd[1] == wg // 64
+            written = g.read_task_commands(wg)
+            live = written[written["taskCount"] > 0]
+            allowed = set(map(tuple, full_o.read_task_commands(int(fd[0])).tolist()))
+            assert all(tuple(c) in allowed for c in live.tolist())
+            assert gc[0] > cl and gc[2] == cl // 256 and gc[1] == 16 and gc[3] == 16
+
+
+def test_taskcull_payloads(golden_dir):
+    """meshlet.task.glsl path: per-command payload + emit count."""
+    torch = _torch()
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 12000)
+    g, o, depth = _paths(s)
+    cd = s.cull_data()
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+                o.pyramid(s.depth)
+            g.cull(cd, late)
+            o.cull(cd, late)
+            torch.cuda.synchronize()
+            n = int(o.read_counts()[0][1]) * 64
+            gp = torch.zeros((max(n, 1), 64), dtype=torch.int32, device="cuda")
+            ge = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+            op = np.zeros((max(n, 1), 64), dtype=np.uint32)
+            oe = np.zeros(max(n, 1), dtype=np.uint32)
+            g.task_shading(cd, late, gp, ge, cluster_backface=True)
+            o.task_shading(cd, late, op, oe, cluster_backface=True)
+            torch.cuda.synchronize()
+            # commands are in a different order on the two sides: key by command contents
+            gt, ot = g.read_task_commands(n), o.read_task_commands(n)
+            gp, ge = gp.cpu().numpy().astype(np.uint32), ge.cpu().numpy().astype(np.uint32)
+
+            def table(cmds, payloads, counts):
+                out = {}
+                for i in range(n):
+                    if cmds["taskCount"][i]:
+                        out[tuple(cmds[i].tolist())] = tuple(int(v) >> 24 for v in payloads[i][: counts[i]])
+                        assert all((int(v) & 0xFFFFFF) == i for v in payloads[i][: counts[i]])
+                return out
+
+            assert table(gt, gp, ge) == table(ot, op, oe)
+            assert np.array_equal(g.mvb.cpu().numpy().astype(np.uint32), o.mvb)
