@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the visibility hot path on B200 (metric of BASELINE.json: meshlets culled/sec, with draws
+culled/sec and the HBM-roofline fraction of the dominant kernel alongside).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement (oracle/, multi-threaded) on the host cores
+
+A "step" is one frame of the hot path in the reference's order (niagara.cpp:1765-1788) over the C4 workload of
+BASELINE.json (configs[3]: 10M synthetic meshlets / 1M draws): early drawcull+tasksubmit, early
+clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit = 5 launches.
+`value` counts the meshlet instances the two cluster passes TEST per second (lanes with mgi < taskCount), inputs
+resident in HBM.  `e2e` is the same frame driven from HOST buffers: per step H2D of the MeshDraw array, the prior-frame
+depth and D2H of the counters plus the visible command / cluster-index slabs.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C4", "C2"])
+    ap.add_argument("--draws", type=int, default=1_000_000)
+    ap.add_argument("--meshlets-per-draw", type=int, default=10)
+    ap.add_argument("--depth", type=int, default=4096)
+    ap.add_argument("--cpu-sample-draws", type=int, default=100_000, help="draws in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the NCCL allgather of the visible command slabs")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene(args, rank):
+    """Synthetic scene of the workload; cached under /tmp so that several bench invocations in one session (bench,
+    ncu launch list, ncu full capture) do not regenerate 0.5 GB of inputs each."""
+    import pickle
+
+    from niagara_b200 import scenes
+
+    key = "%s_%d_%d_%d_%d" % (args.workload, args.draws, args.meshlets_per_draw, args.depth, rank)
+    cache = os.path.join(tempfile.gettempdir(), "nvc_scene_%s.pkl" % key)
+    if os.path.exists(cache):
+        try:
+            return pickle.load(open(cache, "rb"))
+        except Exception:
+            pass
+    if args.workload == "C4":
+        scene = scenes.config4_scene(args.draws, args.meshlets_per_draw, screen=(args.depth, args.depth), seed=21 + 100 * rank)
+    else:
+        scene = scenes.config2_scene(args.draws, screen=(args.depth, args.depth), seed=11 + 100 * rank)
+    try:
+        tmp = cache + ".%d" % os.getpid()
+        pickle.dump(scene, open(tmp, "wb"), protocol=4)
+        os.replace(tmp, cache)
+    except Exception:
+        pass
+    return scene
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(args, scene, threads):
+    """The CPU restatement (oracle/, `kind: port` — the reference has no CPU cull path) on a bounded sample:
+    the first `cpu_sample_draws` draws of the same scene, one steady-state frame, all host threads."""
+    import oracle_lib
+
+    n = min(args.cpu_sample_draws, len(scene.draws))
+    draws = scene.draws[:n].copy()
+    from niagara_b200 import host
+
+    bits, _ = host.visibility_offsets(draws, scene.meshes)
+    cd = host.cull_data(scene.camera, scene.screen[0], scene.screen[1], n)
+    o = oracle_lib.OraclePath(scene.meshes, scene.meshlets, draws, *scene.screen, threads=threads, cmd_capacity=max(64, (n * 2 + 63) // 64 * 64))
+    o.set_visibility_bits(bits)
+    o.frame(cd, scene.depth, cluster_backface=True)  # warm-up frame: establishes dvb / mvb
+    tested = 0
+    t0 = time.perf_counter()
+    # identical pass order; count the meshlets the two cluster passes test
+    o.cull(cd, late=False)
+    tested += int(o.read_task_commands(int(o.dccb[1]) * 64)["taskCount"].sum())
+    o.render_clusters(cd, late=False, cluster_backface=True)
+    o.pyramid(scene.depth)
+    o.cull(cd, late=True)
+    tested += int(o.read_task_commands(int(o.dccb[1]) * 64)["taskCount"].sum())
+    o.render_clusters(cd, late=True, cluster_backface=True)
+    dt = time.perf_counter() - t0
+    return {
+        "value": tested / dt,
+        "unit": "meshlets/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": "one steady-state frame over the first %d draws (%d meshlet tests, %dx%d depth pyramid) of the same scene, %.2f s" % (n, tested, scene.screen[0], scene.screen[1], dt),
+        "draws_per_s": 2 * n / dt,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement timed on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+
+    threads = oracle_lib.load().orc_hardware_threads() or os.cpu_count() or 1
+    # bounded sample per step so that steps + warmup end within a few minutes
+    args.cpu_sample_draws = min(args.cpu_sample_draws, args.draws)
+    sample_args = argparse.Namespace(**vars(args))
+    sample_args.draws = args.cpu_sample_draws
+    scene = build_scene(sample_args, 0)
+    res = None
+    t_steps = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(sample_args, scene, threads)
+        if i >= args.warmup:
+            t_steps.append(r)
+        res = r
+    value = float(np.mean([r["value"] for r in t_steps]))
+    tested = value  # per second
+    line = {
+        "impl": "reference",
+        "metric": "meshlets culled/sec",
+        "value": value,
+        "unit": "meshlets/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean([float(r["sample"].split(",")[-1].split()[0]) for r in t_steps])),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C4 sample: %d draws x %d meshlets, %dx%d depth; CPU restatement of the GLSL (the reference has no CPU cull path)" % (sample_args.draws, args.meshlets_per_draw, args.depth, args.depth)},
+        "cpu_baseline": {"value": value, "unit": "meshlets/s", "cores": threads, "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "meshlets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "draws_per_s": float(np.mean([r["draws_per_s"] for r in t_steps])),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from niagara_b200 import layout
+    from niagara_b200.lib import check
+    from niagara_b200.path import VisibilityPath
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peak_gbs, peak_src = load_peaks()
+    scene = build_scene(args, rank)
+    D = len(scene.draws)
+    cd = scene.cull_data()
+    path = VisibilityPath(scene.meshes, scene.meshlets, scene.draws, *scene.screen, device=dev)
+    path.set_visibility_bits(scene.visibility_bits)
+    depth_host = torch.from_numpy(scene.depth).pin_memory()
+    draws_host = torch.from_numpy(scene.draws.view(np.uint8).reshape(-1)).pin_memory()
+    depth = depth_host.to(dev)
+    lib = path.lib
+
+    # ---- multi-GPU: one NCCL allgather of the per-rank visible command slabs + counts ----
+    gather = world > 1 and not args.no_gather
+    slab_cmds = (D * max(1, (args.meshlets_per_draw + 63) // 64) + 63) // 64 * 64 if args.workload == "C4" else 0
+    if gather and slab_cmds:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            check(lib.nvc_nccl_unique_id(buf), path.ctx, "nvc_nccl_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        uid_host = (ctypes.c_ubyte * 128)(*uid.cpu().tolist())
+        check(lib.nvc_nccl_init(path.ctx, uid_host, rank, world), path.ctx, "nvc_nccl_init")
+        slab_bytes = slab_cmds * layout.MESHTASKCOMMAND_DTYPE.itemsize
+        gathered = torch.zeros(world * slab_bytes, dtype=torch.uint8, device=dev)
+        gathered_counts = torch.zeros(world * 4, dtype=torch.int32, device=dev)
+        comm_stream = torch.cuda.Stream(dev)
+    else:
+        gather = False
+
+    names = ["drawcull_early", "clustercull_early", "pyramid", "drawcull_late", "clustercull_late"]
+
+    def frame(events=None):
+        def mark(i):
+            if events is not None:
+                events[i].record()
+
+        mark(0)
+        path.cull(cd, late=False)
+        mark(1)
+        path.render_clusters(cd, late=False, cluster_backface=True)
+        mark(2)
+        path.pyramid(depth)
+        mark(3)
+        path.cull(cd, late=True)
+        mark(4)
+        if gather:
+            # the late command slab is final once drawcull(late) is done: gather it on a side stream while the
+            # late cluster pass runs
+            done = torch.cuda.Event()
+            done.record()
+            comm_stream.wait_event(done)
+            check(
+                lib.nvc_allgather_visible(path.ctx, ctypes.c_void_p(comm_stream.cuda_stream), ctypes.c_void_p(path.dcb.data_ptr()), slab_bytes, ctypes.c_void_p(path.dccb.data_ptr()), ctypes.c_void_p(gathered.data_ptr()), ctypes.c_void_p(gathered_counts.data_ptr())),
+                path.ctx,
+                "nvc_allgather_visible",
+            )
+        path.render_clusters(cd, late=True, cluster_backface=True)
+        mark(5)
+        if gather:
+            torch.cuda.current_stream().wait_stream(comm_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up: establishes the steady two-phase state (dvb / mvb) and warms caches / clocks ----
+    for _ in range(max(3, args.warmup)):
+        frame()
+    torch.cuda.synchronize()
+
+    # probe one frame for the per-pass work counts (static scene: identical every step)
+    early_reached = int((path.dvb != 0).sum().item())
+    path.cull(cd, late=False)
+    torch.cuda.synchronize()
+    dccb_e = path.dccb.cpu().numpy().astype(np.uint32)
+    tested_early = int(path.read_task_commands(int(dccb_e[1]) * 64)["taskCount"].sum())
+    path.render_clusters(cd, late=False, cluster_backface=True)
+    path.pyramid(depth)
+    path.cull(cd, late=True)
+    torch.cuda.synchronize()
+    dccb_l = path.dccb.cpu().numpy().astype(np.uint32)
+    cmds_late = path.read_task_commands(int(dccb_l[1]) * 64)
+    tested_late = int(cmds_late["taskCount"].sum())
+    visible_draws_late = int(np.unique(cmds_late["drawId"][cmds_late["taskCount"] > 0]).size)
+    path.render_clusters(cd, late=True, cluster_backface=True)
+    torch.cuda.synchronize()
+    ccb_l = path.ccb.cpu().numpy().astype(np.uint32)
+    tested_per_step = tested_early + tested_late
+    draws_per_step = early_reached + D
+
+    # ---- timed region: device-resident inputs ----
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    sync_all()
+    start.record()
+    for k in range(K):
+        frame(ev[k])
+    stop.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = start.elapsed_time(stop)
+    pass_ms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(5)] for k in range(K)])
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    counts = torch.tensor([tested_per_step, draws_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    tested_all, draws_all = float(counts[0].item()), float(counts[1].item())
+
+    # ---- end-to-end: host buffers in, results out, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        count_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        cmd_host = torch.zeros(path.dcb.numel() if path.dcb.numel() < (1 << 26) else (1 << 26), dtype=torch.uint8).pin_memory()
+        cib_host = torch.zeros(min(path.cib.numel(), 1 << 24), dtype=torch.int32).pin_memory()
+        h2d = d2h = 0
+
+        def e2e_frame():
+            nonlocal h2d, d2h
+            path.db.copy_(draws_host, non_blocking=True)  # MeshDraw[] (the reference's db is host-visible and rewritten when animating)
+            depth.copy_(depth_host, non_blocking=True)    # prior-frame depth target stand-in
+            h2d = draws_host.numel() + depth_host.numel() * 4 + 144
+            frame()
+            count_host[:4].copy_(path.dccb, non_blocking=True)
+            count_host[4:].copy_(path.ccb, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            ncmd = min(int(count_host[0].item()), path.task_wglimit)
+            ncl = min(int(count_host[4].item()), path.cluster_limit)
+            nb = ncmd * 20
+            cmd_host[:nb].copy_(path.dcb[:nb], non_blocking=True)
+            cib_host[:ncl].copy_(path.cib[:ncl], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            d2h = 32 + nb + ncl * 4
+
+        for _ in range(2):
+            e2e_frame()
+        sync_all()
+        t0 = time.perf_counter()
+        start.record()
+        for _ in range(K):
+            e2e_frame()
+        stop.record()
+        sync_all()
+        e_ms = start.elapsed_time(stop)
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": tested_all * K / (float(te.item()) * 1e-3),
+            "unit": "meshlets/s",
+            "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": float(te.item()) / K,
+            "what": "per step: H2D MeshDraw[] + depth target from pinned host memory, the 5-launch frame, D2H counters then the visible MeshTaskCommand and cluster-index slabs",
+        }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (clustercull LATE): algorithmic bytes per SURVEY §8(d) ----
+        M, C, v = tested_late, int(dccb_l[0]), int(ccb_l[0])
+        alg_bytes = M * 24 + C * 20 + visible_draws_late * 48 + 2 * (M / 8.0) + 4 * v
+        k_ms = float(pass_ms[:, 4].mean())
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        share = pass_ms.mean(axis=0) / pass_ms.mean(axis=0).sum()
+        line = {
+            "metric": "meshlets culled/sec",
+            "value": tested_all * K / (max_ms * 1e-3),
+            "unit": "meshlets/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": max(3, args.warmup),
+            "ms_per_step": max_ms / K,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": "%s: %s; per GPU" % (scene.name, scene.note),
+                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit (5 launches)%s" % ("; + NCCL allgather of the late MeshTaskCommand slabs+counts overlapped with the late cluster pass" if gather else ""),
+                "counting": "value = meshlet instances TESTED by the two cluster passes per second (early %d + late %d per step per GPU); draws_per_s likewise (early %d + late %d)" % (tested_early, tested_late, early_reached, D),
+                "l2": "inputs larger than L2 (Meshlet[] %d MB + MeshDraw[] %d MB + Mesh[] %d MB + depth %d MB per step vs 126 MB L2), no flush" % (scene.meshlets.nbytes >> 20, scene.draws.nbytes >> 20, scene.meshes.nbytes >> 20, scene.depth.nbytes >> 20),
+                "cluster_backface": 1,
+                "parallelism": "draw-sharded x%d" % world,
+            },
+            "draws_per_s": draws_all * K / (max_ms * 1e-3),
+            "passes_ms": {n: float(pass_ms[:, i].mean()) for i, n in enumerate(names)},
+            "passes_share": {n: float(share[i]) for i, n in enumerate(names)},
+            "visible": {"late_commands": C, "late_visible_draws": visible_draws_late, "late_emitted_clusters": v, "early_commands": int(dccb_e[0])},
+            "roofline": {
+                "kernel": "clustercull_kernel<LATE=1> (+clustersubmit epilogue)",
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak_gbs,
+                "peak_source": peak_src,
+                "unit": "GB/s",
+                "frac": achieved / peak_gbs,
+                "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": k_ms,
+                "meshlets_per_s_kernel": M / (k_ms * 1e-3),
+            },
+            "clocks": clocks,
+            "gpu_launches": 5 * K,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world >= 1:
+            import oracle_lib
+
+            threads = oracle_lib.load().orc_hardware_threads() or os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_baseline(args, scene, threads)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,16 @@ class Scene:
     def cull_data(self, **toggles):
         return host.cull_data(self.camera, self.screen[0], self.screen[1], len(self.draws), **toggles)
 
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        c = self.camera
+        st["camera"] = (tuple(c.position), tuple(c.orientation), float(c.fovY), float(c.znear))
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.camera = host.make_camera(*st["camera"])
+
 
 def reference_random_scene(meshes, meshlets, draw_count, screen=(1024, 768), depth_seed=4, occluders=60, name="reference-random"):
     """C1/C2 recipe: the reference's own PCG32 scene (niagara.cpp:969-998) over a given geometry table, default camera."""
