@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--draws", type=int, default=1_000_000)
     ap.add_argument("--meshlets-per-draw", type=int, default=10)
     ap.add_argument("--depth", type=int, default=4096)
-    ap.add_argument("--cpu-sample-draws", type=int, default=100_000, help="draws in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-draws", type=int, default=1_000_000, help="draws in the bounded CPU-baseline sample (default: the whole C4 scene, one frame ~ 10-60 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the NCCL allgather of the visible command slabs")

@@ -1,0 +1,97 @@
+"""Run under torchrun with >= 2 GPUs: sharded CUDA path + nvc_allgather_visible (NCCL over NVLink) must reproduce the
+single-rank oracle result.  Used by tests/test_gpu_multi.py and directly:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import oracle_lib
+    from niagara_b200 import layout, scenes, shard
+    from niagara_b200.lib import check
+    from niagara_b200.path import VisibilityPath
+
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+
+    s = scenes.instanced_scene(os.path.join(ROOT, "tests", "golden", "kitten_pirate.nvcg"), 40003, screen=(1280, 720))
+    local, base, bit_base, bits = shard.shard_draws(s.draws, s.meshes, rank, world)
+    # every rank uses the same (largest) capacity: ncclAllGather needs equal slab sizes
+    cap = max(shard.slab_capacity(e - b, s.meshes) for b, e in shard.partition(len(s.draws), world))
+    cd = s.cull_data()
+    cd.drawCount = len(local)
+    g = VisibilityPath(s.meshes, s.meshlets, local, *s.screen, device=dev)
+    g.set_visibility_bits(bits)
+    depth = torch.from_numpy(s.depth).to(dev)
+    lib = g.lib
+
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf = (ctypes.c_ubyte * 128)()
+        check(lib.nvc_nccl_unique_id(buf), g.ctx, "nvc_nccl_unique_id")
+        uid = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(uid, 0)
+    check(lib.nvc_nccl_init(g.ctx, (ctypes.c_ubyte * 128)(*uid.cpu().tolist()), rank, world), g.ctx, "nvc_nccl_init")
+
+    slab_bytes = cap * 20
+    gathered = torch.zeros(world * slab_bytes, dtype=torch.uint8, device=dev)
+    gathered_counts = torch.zeros(world * 4, dtype=torch.int32, device=dev)
+    bases = [b for b, _ in shard.partition(len(s.draws), world)]
+    bit_bases = [int(s.draws["meshletVisibilityOffset"][b]) for b in bases]
+
+    if rank == 0:
+        o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8)
+        o.set_visibility_bits(s.visibility_bits)
+        cd_all = s.cull_data()
+
+    ok = True
+    for frame in range(2):
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+            g.cull(cd, late)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            check(lib.nvc_allgather_visible(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), slab_bytes, ctypes.c_void_p(g.dccb.data_ptr()), ctypes.c_void_p(gathered.data_ptr()), ctypes.c_void_p(gathered_counts.data_ptr())), g.ctx, "nvc_allgather_visible")
+            g.render_clusters(cd, late, cluster_backface=True)
+            torch.cuda.synchronize()
+            slabs = gathered.cpu().numpy().reshape(world, slab_bytes)
+            counts = gathered_counts.cpu().numpy().reshape(world, 4)
+            cmds = shard.globalise_task_commands(list(slabs), list(counts), bases, bit_bases)
+            if rank == 0:
+                if late:
+                    o.pyramid(s.depth)
+                o.cull(cd_all, late)
+                want = oracle_lib.sorted_commands(o.read_task_commands(int(o.dccb[0])))
+                o.render_clusters(cd_all, late, cluster_backface=True)
+                same = len(cmds) == len(want) and np.array_equal(oracle_lib.sorted_commands(cmds), want)
+                # rank-local cluster counts must add up to the single-rank count
+                ok = ok and same
+                if not same:
+                    print("MISMATCH frame", frame, "late", late, len(cmds), len(want))
+            total = torch.tensor([int(g.ccb[0].item())], dtype=torch.int64, device=dev)
+            dist.all_reduce(total)
+            if rank == 0 and int(total.item()) != int(o.ccb[0]):
+                ok = False
+                print("cluster count mismatch", int(total.item()), int(o.ccb[0]))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", "world", world)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
