@@ -89,6 +89,7 @@ struct PyramidParams
 	uint32_t depth_width, depth_height;
 	HiZDesc hiz;
 	Scratch* scratch;
+	uint32_t vector_ok; // set by launch_pyramid: bases aligned for 16-byte loads
 };
 
 cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream);

@@ -49,26 +49,46 @@ __device__ __forceinline__ uint4 ldg_u4(const void* p)
 	return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
+// The numeric per-pass constants the per-item math reads.  They stay in the kernel-parameter constant bank: ptxas
+// re-materialises them as uniform loads (LDCU) inside the persistent loop; pinning them in registers was tried and is
+// not expressible at the PTX level (ptxas sees through register copies), see DESIGN.md "things that did not help".
+typedef NvcCullData ClusterConsts;
+
+// Tuning knobs (A/B measured on B200, profiles/r1_variants.md): software prefetch of the next chunk's loads did not pay
+// (the extra registers cost more occupancy than the overlap wins); capping registers at 40 so that 6 CTAs (48 warps)
+// are resident per SM did.
+#ifndef NVC_PREFETCH
+#define NVC_PREFETCH 0
+#endif
+#ifndef NVC_CLUSTER_MIN_BLOCKS
+#define NVC_CLUSTER_MIN_BLOCKS 6
+#endif
+#ifndef NVC_PYRAMID_MIN_BLOCKS
+#define NVC_PYRAMID_MIN_BLOCKS 7
+#endif
+
 struct HiZLoad
 {
-	const float* base;
-	__device__ __forceinline__ float operator()(uint32_t idx) const { return __ldg(base + idx); }
+	const float* texels; // uniform base; the level offset is folded into the 32-bit index
+	uint32_t offset;
+	__device__ __forceinline__ float operator()(uint32_t idx) const { return __ldg(texels + (offset + idx)); }
 };
 
-// drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123
-__device__ __forceinline__ bool occlusion_visible(const NvcCullData& cd, const HiZDesc& hiz, f3 center, float radius)
+// drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123.  Straight-line: every lane computes, the
+// "sphere crosses the near plane -> stays visible" case is a select at the end.
+template <typename CD>
+__device__ __forceinline__ bool occlusion_visible(const CD& cd, const HiZDesc& hiz, f3 center, float radius)
 {
 	float4 aabb;
-	if (!project_sphere(center, radius, cd.znear, cd.P00, cd.P11, aabb))
-		return true;
+	bool ok = project_sphere(center, radius, cd.znear, cd.P00, cd.P11, aabb);
 	int level = occlusion_mip(aabb, cd.pyramidWidth, cd.pyramidHeight, int(hiz.levels) - 1);
 	uint32_t w = max(1u, hiz.width >> level), h = max(1u, hiz.height >> level);
 	float u = __fmul_rn(__fadd_rn(aabb.x, aabb.z), 0.5f);
 	float v = __fmul_rn(__fadd_rn(aabb.y, aabb.w), 0.5f);
-	HiZLoad load = { hiz.texels + hiz.level_offset[level] };
+	HiZLoad load = { hiz.texels, hiz.level_offset[level] };
 	float depth = sample_min(load, w, h, u, v);
 	float depthSphere = __fdiv_rn(cd.znear, __fsub_rn(center.z, radius));
-	return depthSphere > depth;
+	return !ok || depthSphere > depth;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -76,13 +96,15 @@ __device__ __forceinline__ bool occlusion_visible(const NvcCullData& cd, const H
 // ------------------------------------------------------------------------------------------------------
 
 constexpr int kDrawBlock = 256;
+constexpr uint32_t kDrawStage = 512; // commands staged per block before the coalesced write-out
 
 template <bool LATE, bool TASK>
 __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
 {
 	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
-	__shared__ uint32_t s_block_base;
+	__shared__ uint32_t s_block_base, s_block_total;
 	__shared__ uint32_t s_is_last;
+	__shared__ uint32_t s_stage[kDrawStage * 6];
 
 	const NvcCullData& cd = p.cull;
 	const uint32_t tid = threadIdx.x;
@@ -184,42 +206,59 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			s_warp_total[lane] = ti - t; // exclusive warp offsets
 		uint32_t total = __shfl_sync(0xffffffffu, ti, kDrawBlock / 32 - 1);
 		if (lane == 0)
+		{
+			s_block_total = total;
 			s_block_base = total ? atomicAdd(&p.scratch->draw_counter, total) : 0u;
+		}
 	}
 	__syncthreads();
 
+	// ---- command write-out.  The block's commands are contiguous in dcb, so they are staged in shared memory and
+	// copied out with fully coalesced 4-byte stores (the GLSL stores 5-6 scattered words per thread).  Blocks that
+	// exceed the staging capacity or run into TASK_WGLIMIT take the direct per-thread path. ----
+	constexpr uint32_t kWords = TASK ? 5u : 6u;
+	const uint32_t block_total = s_block_total;
+	const uint32_t local = s_warp_total[warp] + (incl - units);
+	const bool staged = block_total <= kDrawStage && (!TASK || uint64_t(s_block_base) + block_total <= p.task_wglimit);
 	if (emit)
 	{
-		uint32_t dci = s_block_base + s_warp_total[warp] + (incl - units);
+		const uint32_t dci = s_block_base + local;
 		const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
 		const uint32_t* lp = reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20);
 		if (TASK)
 		{
 			// :129 drop on overflow; the counter has already advanced
-			if (uint64_t(dci) + units <= p.task_wglimit)
+			if (staged || uint64_t(dci) + units <= p.task_wglimit)
 			{
 				uint32_t meshletOffset = __ldg(lp + 2), meshletCount = __ldg(lp + 3);
-				NvcMeshTaskCommand* out = static_cast<NvcMeshTaskCommand*>(p.commands) + dci;
-				for (uint32_t i = 0; i < units; ++i)
+				uint32_t* out = staged ? s_stage + local * 5u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshTaskCommand*>(p.commands) + dci);
+				for (uint32_t i = 0; i < units; ++i, out += 5)
 				{
-					out[i].drawId = di;
-					out[i].taskOffset = meshletOffset + i * NVC_TASK_WGSIZE;
-					out[i].taskCount = min(NVC_TASK_WGSIZE, meshletCount - i * NVC_TASK_WGSIZE);
-					out[i].lateDrawVisibility = dv;
-					out[i].meshletVisibilityOffset = mvOffset + i * NVC_TASK_WGSIZE;
+					out[0] = di;                                                          // drawId
+					out[1] = meshletOffset + i * NVC_TASK_WGSIZE;                         // taskOffset
+					out[2] = min(NVC_TASK_WGSIZE, meshletCount - i * NVC_TASK_WGSIZE);    // taskCount
+					out[3] = dv;                                                          // lateDrawVisibility
+					out[4] = mvOffset + i * NVC_TASK_WGSIZE;                              // meshletVisibilityOffset
 				}
 			}
 		}
 		else
 		{
-			NvcMeshDrawCommand* out = static_cast<NvcMeshDrawCommand*>(p.commands) + dci;
-			out->drawId = di;
-			out->indexCount = __ldg(lp + 1);
-			out->instanceCount = 1;
-			out->firstIndex = __ldg(lp + 0);
-			out->vertexOffset = __ldg(reinterpret_cast<const uint32_t*>(mp + 16));
-			out->firstInstance = 0;
+			uint32_t* out = staged ? s_stage + local * 6u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshDrawCommand*>(p.commands) + dci);
+			out[0] = di;                                                       // drawId
+			out[1] = __ldg(lp + 1);                                            // indexCount
+			out[2] = 1;                                                        // instanceCount
+			out[3] = __ldg(lp + 0);                                            // firstIndex
+			out[4] = __ldg(reinterpret_cast<const uint32_t*>(mp + 16));        // vertexOffset
+			out[5] = 0;                                                        // firstInstance
 		}
+	}
+	if (staged && block_total)
+	{
+		__syncthreads();
+		uint32_t* out = reinterpret_cast<uint32_t*>(p.commands) + size_t(s_block_base) * kWords;
+		for (uint32_t i = tid; i < block_total * kWords; i += kDrawBlock)
+			out[i] = s_stage[i];
 	}
 
 	// ---- last-block epilogue: tasksubmit.comp.glsl:27-47 (TASK) / publish the count (draw path) ----
@@ -274,60 +313,112 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 // per-meshlet test shared by clustercull / taskcull
 // ------------------------------------------------------------------------------------------------------
 
-// clustercull.comp.glsl:72-124 for one valid lane.  Returns `visible`; `skip` by reference.
+// One lane's work item inside a chunk and the raw data its test needs.
+struct ItemRef
+{
+	uint32_t drawId, lateVis, mi, mvi, code; // code = commandId | (mgi << 24), the value appended on success
+	bool active;
+};
+
+struct ItemData
+{
+	float4 d0, d1;  // MeshDraw: position.xyz + scale, orientation
+	uint2 b0;       // Meshlet: center[3], radius (4 x binary16)
+	uint32_t b1;    // Meshlet: cone_axis[3], cone_cutoff (4 x s8)
+	uint32_t word;  // visibility word of this lane's bit (when the pass tracks bits)
+	bool have_geom; // d0/d1/b0/b1 were loaded
+};
+
+__device__ __forceinline__ void load_geometry(const ClusterParams& p, const ItemRef& r, ItemData& d)
+{
+	const char* dp = reinterpret_cast<const char*>(p.draws + r.drawId);
+	d.d0 = ldg_f4(dp);
+	d.d1 = ldg_f4(dp + 16);
+	const char* mp = reinterpret_cast<const char*>(p.meshlets + r.mi);
+	d.b0 = __ldg(reinterpret_cast<const uint2*>(mp));
+	d.b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8));
+}
+
+// Issues the loads of one chunk.  LATE: everything an active lane needs (bit word + geometry).  EARLY: only the bit
+// word when the pass tracks bits (the geometry of meshlets that were invisible last frame is never touched), else
+// the geometry.
 template <bool LATE>
-__device__ __forceinline__ bool meshlet_test(const ClusterParams& p, uint32_t drawId, uint32_t lateDrawVisibility, uint32_t mi, uint32_t mvi, bool& skip)
+__device__ __forceinline__ void meshlet_fetch(const ClusterParams& p, const ItemRef& r, ItemData& d)
 {
 	const NvcCullData& cd = p.cull;
-	skip = false;
-	bool visible = true;
-
 	const bool track = cd.clusterOcclusionEnabled == 1 && cd.postPass == 0; // :86
-	if (track)
+	d.d0 = make_float4(0.f, 0.f, 0.f, 1.f);
+	d.d1 = make_float4(0.f, 0.f, 0.f, 1.f);
+	d.b0 = make_uint2(0u, 0u);
+	d.b1 = 0;
+	d.word = 0;
+	d.have_geom = false;
+	if (r.active)
 	{
-		// early: read-only this pass.  late: only this lane's own bit matters and nobody else changes it.
-		uint32_t word = LATE ? __ldcg(p.meshlet_visibility + (mvi >> 5)) : __ldg(p.meshlet_visibility + (mvi >> 5));
-		bool bit = (word >> (mvi & 31u)) & 1u;
-		if (!LATE && !bit)
-			return false; // :91-92 — nothing below has side effects in the early pass
-		if (LATE && lateDrawVisibility == 1 && bit)
-			skip = true; // :97-98
+		if (track) // early: read-only this pass.  late: only this lane's own bit matters and nobody else changes it.
+			d.word = LATE ? __ldcg(p.meshlet_visibility + (r.mvi >> 5)) : __ldg(p.meshlet_visibility + (r.mvi >> 5));
+		if (LATE || !track)
+		{
+			load_geometry(p, r, d);
+			d.have_geom = true;
+		}
+	}
+}
+
+// clustercull.comp.glsl:72-124 for one 32-lane chunk.  Only warp-uniform branches: the GLSL's `visible && ...` chain
+// (a pure conjunction, free of side effects) is evaluated straight through, and the expensive occlusion stage runs
+// only when some lane is still alive.
+//   visible  the GLSL's `visible` after all tests
+//   skip     clustercull.comp.glsl:97-98
+//   oldbit   the lane's previous visibility bit (meaningful when clusterOcclusionEnabled == 1 && postPass == 0)
+template <bool LATE>
+__device__ __forceinline__ void meshlet_compute(const ClusterParams& p, const ClusterConsts& cc, const ItemRef& r, ItemData& d, bool& visible, bool& skip, bool& oldbit)
+{
+	const NvcCullData& cd = p.cull;
+	bool alive = r.active;
+	skip = false;
+	oldbit = false;
+
+	if (cd.clusterOcclusionEnabled == 1 && cd.postPass == 0) // :86
+	{
+		bool bit = (d.word >> (r.mvi & 31u)) & 1u;
+		oldbit = bit;
+		if (!LATE)
+			alive = alive && bit; // :91-92
+		else
+			skip = r.lateVis == 1 && bit; // :97-98
+	}
+	visible = false;
+	if (!LATE)
+	{
+		if (!__any_sync(0xffffffffu, alive))
+			return; // nothing in this chunk was visible last frame
+		if (alive && !d.have_geom)
+			load_geometry(p, r, d);
 	}
 
-	const char* dp = reinterpret_cast<const char*>(p.draws + drawId);
-	float4 d0 = ldg_f4(dp);      // position.xyz, scale
-	float4 d1 = ldg_f4(dp + 16); // orientation
+	f3 lc = { half_bits_to_float(d.b0.x & 0xffffu), half_bits_to_float(d.b0.x >> 16), half_bits_to_float(d.b0.y & 0xffffu) };
+	f3 rc = rotate_quat(lc, d.d1);
+	f3 center = { __fadd_rn(__fmul_rn(rc.x, d.d0.w), d.d0.x), __fadd_rn(__fmul_rn(rc.y, d.d0.w), d.d0.y), __fadd_rn(__fmul_rn(rc.z, d.d0.w), d.d0.z) };
+	center = transform_point(cc.view, center);
+	float radius = __fmul_rn(half_bits_to_float(d.b0.y >> 16), d.d0.w);
 
-	const char* mp = reinterpret_cast<const char*>(p.meshlets + mi);
-	uint2 b0 = __ldg(reinterpret_cast<const uint2*>(mp));        // center[3], radius (4 x binary16)
-	uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8)); // cone_axis[3], cone_cutoff (4 x s8)
-
-	f3 lc = { half_bits_to_float(b0.x & 0xffffu), half_bits_to_float(b0.x >> 16), half_bits_to_float(b0.y & 0xffffu) };
-	f3 rc = rotate_quat(lc, d1);
-	f3 center = { __fadd_rn(__fmul_rn(rc.x, d0.w), d0.x), __fadd_rn(__fmul_rn(rc.y, d0.w), d0.y), __fadd_rn(__fmul_rn(rc.z, d0.w), d0.z) };
-	center = transform_point(cd.view, center);
-	float radius = __fmul_rn(half_bits_to_float(b0.y >> 16), d0.w);
-
-	// cheapest rejection first; the GLSL's `visible && ...` chain is a pure conjunction so the order is free
-	visible = frustum_visible(cd, center, radius); // :104-108
-	if (!visible)
-		return false;
+	alive = alive && frustum_visible(cc, center, radius); // :104-108
 
 	if (cd.clusterBackfaceEnabled != 0) // :102
 	{
-		f3 la = { s8_div127(int(int8_t(b1 & 0xffu))), s8_div127(int(int8_t((b1 >> 8) & 0xffu))), s8_div127(int(int8_t((b1 >> 16) & 0xffu))) };
-		f3 axis = transform_vector(cd.view, rotate_quat(la, d1));
-		float cutoff = s8_div127(int(int8_t(b1 >> 24)));
+		f3 la = { s8_div127(int(int8_t(d.b1 & 0xffu))), s8_div127(int(int8_t((d.b1 >> 8) & 0xffu))), s8_div127(int(int8_t((d.b1 >> 16) & 0xffu))) };
+		f3 axis = transform_vector(cc.view, rotate_quat(la, d.d1));
+		float cutoff = s8_div127(int(int8_t(d.b1 >> 24)));
 		// math.h:41-44 with camera_position = 0
 		bool backface = dot3(center, axis) >= __fadd_rn(__fmul_rn(cutoff, length3(center)), radius);
-		if (backface)
-			return false;
+		alive = alive && !backface;
 	}
 
-	if (LATE && cd.clusterOcclusionEnabled == 1) // :110
-		visible = occlusion_visible(cd, p.hiz, center, radius);
+	if (LATE && cd.clusterOcclusionEnabled == 1 && __any_sync(0xffffffffu, alive)) // :110
+		alive = occlusion_visible(cc, p.hiz, center, radius) && alive;
 
-	return visible;
+	visible = alive;
 }
 
 // clustercull.comp.glsl:126-131 for one 32-item chunk: lanes with consecutive bit indices inside one word form a run;
@@ -392,12 +483,13 @@ __device__ __forceinline__ void flush_stage(const ClusterParams& p, uint32_t* st
 }
 
 template <bool LATE>
-__global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const ClusterParams p)
+__global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) clustercull_kernel(const ClusterParams p)
 {
 	__shared__ uint32_t s_stage[kClusterWarps][kStage];
 	__shared__ uint32_t s_is_last;
 
 	const NvcCullData& cd = p.cull;
+	const ClusterConsts& cc = cd;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	uint32_t* stage = s_stage[warp];
@@ -407,6 +499,7 @@ __global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const Cluste
 	const uint32_t ncmd = p.command_count4[1] * 64u;
 	const uint32_t nbatch = (ncmd + 31u) / 32u;
 	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
+	const bool bits_known = cd.postPass == 0; // meshlet_test read the previous bit (clustercull.comp.glsl:86)
 
 	for (;;)
 	{
@@ -447,12 +540,9 @@ __global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const Cluste
 		const uint32_t nz = __ballot_sync(0xffffffffu, c_count != 0);
 		const bool nz_prefix = (nz & (nz + 1u)) == 0; // non-empty commands form a prefix (always, except stale slots)
 
-		for (uint32_t base = 0; base < total; base += 32)
-		{
+		// item -> command mapping of the chunk starting at `base` (executed by all lanes)
+		auto map_chunk = [&](uint32_t base) -> ItemRef {
 			const uint32_t item = base + lane;
-			const bool active = item < total;
-
-			// which command does my item belong to?
 			uint32_t j;
 			if (nz_prefix)
 			{
@@ -476,20 +566,41 @@ __global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const Cluste
 				}
 			}
 			j &= 31u;
-
-			const uint32_t drawId = __shfl_sync(0xffffffffu, c_draw, j);
-			const uint32_t lateVis = __shfl_sync(0xffffffffu, c_late, j);
-			const uint32_t mi = __shfl_sync(0xffffffffu, rel_task, j) + item;
-			const uint32_t mvi = __shfl_sync(0xffffffffu, rel_mvo, j) + item;
+			ItemRef r;
+			r.active = item < total;
+			r.drawId = __shfl_sync(0xffffffffu, c_draw, j);
+			r.lateVis = __shfl_sync(0xffffffffu, c_late, j);
+			r.mi = __shfl_sync(0xffffffffu, rel_task, j) + item;
+			r.mvi = __shfl_sync(0xffffffffu, rel_mvo, j) + item;
 			const uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j);
+			r.code = (batch * 32u + j) | (mgi << 24); // :138
+			return r;
+		};
 
-			bool skip = false;
-			bool visible = false;
-			if (active)
-				visible = meshlet_test<LATE>(p, drawId, lateVis, mi, mvi, skip);
+		ItemRef cur = map_chunk(0);
+		ItemData cur_data;
+		if (total)
+			meshlet_fetch<LATE>(p, cur, cur_data);
 
-			if (track_late) // :126-131
-				update_visibility_bits(p.meshlet_visibility, active, visible, mvi);
+		for (uint32_t base = 0; base < total; base += 32)
+		{
+#if NVC_PREFETCH
+			// software pipeline: the next chunk's loads are in flight while this chunk is evaluated
+			ItemRef next = cur;
+			ItemData next_data = cur_data;
+			if (base + 32 < total)
+			{
+				next = map_chunk(base + 32);
+				meshlet_fetch<LATE>(p, next, next_data);
+			}
+#endif
+			bool skip, oldbit, visible;
+			meshlet_compute<LATE>(p, cc, cur, cur_data, visible, skip, oldbit);
+
+			// :126-131 — the GLSL rewrites every valid lane's bit; bits that already hold the new value need no
+			// traffic, so the whole chunk skips the update when no lane changes state (the steady-state case)
+			if (track_late && __any_sync(0xffffffffu, cur.active && (!bits_known || oldbit != visible)))
+				update_visibility_bits(p.meshlet_visibility, cur.active, visible, cur.mvi);
 
 			const bool out = visible && !skip; // :133
 			const uint32_t omask = __ballot_sync(0xffffffffu, out);
@@ -499,9 +610,19 @@ __global__ void __launch_bounds__(kClusterBlock) clustercull_kernel(const Cluste
 				if (nst + n > kStage)
 					flush_stage(p, stage, nst);
 				if (out)
-					stage[nst + __popc(omask & lanemask_lt())] = (batch * 32u + j) | (mgi << 24); // :138
+					stage[nst + __popc(omask & lanemask_lt())] = cur.code;
 				nst += n;
 			}
+#if NVC_PREFETCH
+			cur = next;
+			cur_data = next_data;
+#else
+			if (base + 32 < total)
+			{
+				cur = map_chunk(base + 32);
+				meshlet_fetch<LATE>(p, cur, cur_data);
+			}
+#endif
 		}
 	}
 	if (nst)
@@ -546,6 +667,7 @@ template <bool LATE>
 __global__ void __launch_bounds__(kClusterBlock) taskcull_kernel(const ClusterParams p, NvcMeshTaskPayload* payloads, uint32_t* emit_counts)
 {
 	const NvcCullData& cd = p.cull;
+	const ClusterConsts& cc = cd;
 	const uint32_t lane = lane_id();
 	const uint32_t ncmd = p.command_count4[1] * 64u;
 	const uint32_t warps_total = gridDim.x * kClusterWarps;
@@ -565,10 +687,18 @@ __global__ void __launch_bounds__(kClusterBlock) taskcull_kernel(const ClusterPa
 			const bool active = mgi < c_count;
 			if (!__any_sync(0xffffffffu, active))
 				break;
-			bool skip = false, visible = false;
-			if (active)
-				visible = meshlet_test<LATE>(p, c_draw, c_late, c_task + mgi, c_mvo + mgi, skip);
-			if (track_late)
+			bool skip, visible, oldbit;
+			ItemRef r;
+			r.active = active;
+			r.drawId = c_draw;
+			r.lateVis = c_late;
+			r.mi = c_task + mgi;
+			r.mvi = c_mvo + mgi;
+			r.code = cid | (mgi << 24);
+			ItemData d;
+			meshlet_fetch<LATE>(p, r, d);
+			meshlet_compute<LATE>(p, cc, r, d, visible, skip, oldbit);
+			if (track_late && __any_sync(0xffffffffu, active && (cd.postPass != 0 || oldbit != visible)))
 				update_visibility_bits(p.meshlet_visibility, active, visible, c_mvo + mgi);
 			const bool out = visible && !skip;
 			const uint32_t omask = __ballot_sync(0xffffffffu, out);
@@ -608,7 +738,8 @@ __device__ __forceinline__ float reduce2x2(const float* src, uint32_t sw, uint32
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams p)
+// 7 resident CTAs per SM = 1036 slots: the 1024 tiles of a 2048^2 pyramid (4096^2 depth target) run as ONE wave
+__global__ void __launch_bounds__(kPyrBlock, NVC_PYRAMID_MIN_BLOCKS) pyramid_kernel(const PyramidParams p)
 {
 	__shared__ float s_a[kPyrTile * kPyrTile];             // level 0 tile, later levels 2, 4, 6
 	__shared__ float s_b[(kPyrTile / 2) * (kPyrTile / 2)]; // levels 1, 3, 5
@@ -619,6 +750,73 @@ __global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams 
 	const uint32_t tile_x = blockIdx.x * kPyrTile, tile_y = blockIdx.y * kPyrTile;
 
 	// ---- mip 0 from the depth target: depthreduce.comp.glsl:19 with imageSize = (hz.width, hz.height) ----
+	const bool full_tile = tile_x + kPyrTile <= hz.width && tile_y + kPyrTile <= hz.height;
+	uint32_t first_smem_level = 1; // first mip still to be produced from the shared-memory tile
+	if (EXACT && full_tile && p.vector_ok && hz.levels > 3)
+	{
+		// Streaming fast path.  Warp w owns mip-0 rows 8w..8w+7 of the tile, lane l owns mip-0 columns 2l, 2l+1: the
+		// 128 x 128 depth texels of the tile arrive as 16 independent 16-byte loads per thread (all issued before the
+		// first use, 64 KB in flight per CTA).  Mips 0-3 are then reduced in registers: vertically inside the thread,
+		// horizontally with xor-shuffles ("wave recursion"), no shared memory and no barrier until mip 4.
+		const uint32_t warp = tid >> 5, lane = tid & 31u;
+		const uint32_t row0 = tile_y + 8 * warp;
+		const float* src_row = p.depth + size_t(2 * row0) * p.depth_width + 2 * tile_x + 4 * lane;
+		float4 a[8], b[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			a[j] = __ldcs(reinterpret_cast<const float4*>(src_row + size_t(2 * j) * p.depth_width));
+			b[j] = __ldcs(reinterpret_cast<const float4*>(src_row + size_t(2 * j + 1) * p.depth_width));
+		}
+		float2 v0[8];
+		{
+			float* dst = hz.texels + hz.level_offset[0] + size_t(row0) * hz.width + tile_x + 2 * lane;
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				v0[j].x = fminf(fminf(a[j].x, a[j].y), fminf(b[j].x, b[j].y));
+				v0[j].y = fminf(fminf(a[j].z, a[j].w), fminf(b[j].z, b[j].w));
+				*reinterpret_cast<float2*>(dst + size_t(j) * hz.width) = v0[j];
+			}
+		}
+		float v1[4]; // mip 1: rows 4w..4w+3 of the tile, column l
+		{
+			const uint32_t w1 = hz.width >> 1;
+			float* dst = hz.texels + hz.level_offset[1] + size_t((tile_y >> 1) + 4 * warp) * w1 + (tile_x >> 1) + lane;
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+			{
+				v1[j] = fminf(fminf(v0[2 * j].x, v0[2 * j].y), fminf(v0[2 * j + 1].x, v0[2 * j + 1].y));
+				dst[size_t(j) * w1] = v1[j];
+			}
+		}
+		float v2[2]; // mip 2: rows 2w..2w+1, column l/2 (valid in even lanes)
+		{
+			const uint32_t w2 = hz.width >> 2;
+			float* dst = hz.texels + hz.level_offset[2] + size_t((tile_y >> 2) + 2 * warp) * w2 + (tile_x >> 2) + (lane >> 1);
+#pragma unroll
+			for (int j = 0; j < 2; ++j)
+			{
+				float m = fminf(v1[2 * j], v1[2 * j + 1]);
+				v2[j] = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+				if ((lane & 1u) == 0)
+					dst[size_t(j) * w2] = v2[j];
+			}
+		}
+		{
+			// mip 3: row w, column l/4 (valid in lanes that are multiples of 4)
+			const uint32_t w3 = hz.width >> 3;
+			float m = fminf(v2[0], v2[1]);
+			m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+			if ((lane & 3u) == 0)
+			{
+				hz.texels[hz.level_offset[3] + size_t((tile_y >> 3) + warp) * w3 + (tile_x >> 3) + (lane >> 2)] = m;
+				s_b[warp * 8 + (lane >> 2)] = m; // 8 x 8 tile of mip 3 for the remaining levels
+			}
+		}
+		first_smem_level = 4;
+	}
+	else
 	{
 		const uint32_t lw = hz.width, lh = hz.height;
 		float* dst = hz.texels + hz.level_offset[0];
@@ -632,10 +830,9 @@ __global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams 
 				if (EXACT)
 				{
 					// depth is exactly (2*lw) x (2*lh): footprint is the 2x2 block
-					const float2* r0 = reinterpret_cast<const float2*>(p.depth + size_t(2 * y) * p.depth_width + 2 * x);
-					const float2* r1 = reinterpret_cast<const float2*>(p.depth + size_t(2 * y + 1) * p.depth_width + 2 * x);
-					float2 a = __ldg(r0), b = __ldg(r1);
-					v = fminf(fminf(a.x, a.y), fminf(b.x, b.y));
+					const float* r0 = p.depth + size_t(2 * y) * p.depth_width + 2 * x;
+					const float* r1 = r0 + p.depth_width;
+					v = fminf(fminf(__ldg(r0), __ldg(r0 + 1)), fminf(__ldg(r1), __ldg(r1 + 1)));
 				}
 				else
 				{
@@ -651,11 +848,11 @@ __global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams 
 	}
 	__syncthreads();
 
-	// ---- mips 1..6 of this tile in shared memory ----
-	float* src = s_a;
-	float* out = s_b;
-	uint32_t src_pitch = kPyrTile;
-	for (uint32_t l = 1; l < kPyrTileLevels && l < hz.levels; ++l)
+	// ---- remaining mips (up to 6) of this tile in shared memory ----
+	float* src = first_smem_level == 4 ? s_b : s_a;
+	float* out = first_smem_level == 4 ? s_a : s_b;
+	uint32_t src_pitch = kPyrTile >> (first_smem_level - 1);
+	for (uint32_t l = first_smem_level; l < kPyrTileLevels && l < hz.levels; ++l)
 	{
 		const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
 		const uint32_t pw = max(1u, hz.width >> (l - 1)), ph = max(1u, hz.height >> (l - 1)); // previous level size
@@ -697,12 +894,16 @@ __global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams 
 		return;
 	__threadfence();
 
-	// first level not completed by the tiles: a level is complete iff l < kPyrTileLevels; but tiles whose extent
-	// degenerates (non-square pyramids) still wrote every texel of those levels, so start at kPyrTileLevels.
-	for (uint32_t l = kPyrTileLevels; l < hz.levels; ++l)
+	// The tiles completed mips 0 .. kPyrTileLevels-1 (tiles whose extent degenerates on non-square pyramids still wrote
+	// every texel of those levels).  Reduce the rest here: from global memory while a level is too large for the
+	// 16 KB tile buffer, then entirely in shared memory (one global read phase instead of one per level).
+	uint32_t l = kPyrTileLevels;
+	for (; l < hz.levels; ++l)
 	{
-		const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
 		const uint32_t pw = max(1u, hz.width >> (l - 1)), ph = max(1u, hz.height >> (l - 1));
+		const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
+		if (pw * ph <= kPyrTile * kPyrTile && lw * lh <= (kPyrTile / 2) * (kPyrTile / 2))
+			break; // this level fits s_a and the next one fits s_b: finish in shared memory
 		const float* prev = hz.texels + hz.level_offset[l - 1];
 		float* dst = hz.texels + hz.level_offset[l];
 		for (uint32_t i = tid; i < lw * lh; i += kPyrBlock)
@@ -716,6 +917,33 @@ __global__ void __launch_bounds__(kPyrBlock) pyramid_kernel(const PyramidParams 
 		}
 		__threadfence_block();
 		__syncthreads();
+	}
+	if (l < hz.levels)
+	{
+		uint32_t pw = max(1u, hz.width >> (l - 1)), ph = max(1u, hz.height >> (l - 1));
+		const float* prev = hz.texels + hz.level_offset[l - 1];
+		float* cur = s_a;
+		float* nxt = s_b;
+		for (uint32_t i = tid; i < pw * ph; i += kPyrBlock)
+			cur[i] = __ldcg(prev + i); // written by other CTAs: bypass L1
+		__syncthreads();
+		for (; l < hz.levels; ++l)
+		{
+			const uint32_t lw = max(1u, hz.width >> l), lh = max(1u, hz.height >> l);
+			float* dst = hz.texels + hz.level_offset[l];
+			for (uint32_t i = tid; i < lw * lh; i += kPyrBlock)
+			{
+				float v = reduce2x2(cur, pw, ph, pw, i % lw, i / lw);
+				dst[i] = v;
+				nxt[i] = v; // fits: the first step writes <= 1024 texels into s_b, every later level at most halves
+			}
+			__syncthreads();
+			float* t = cur;
+			cur = nxt;
+			nxt = t;
+			pw = lw;
+			ph = lh;
+		}
 	}
 	if (tid == 0)
 		p.scratch->pyramid_done = 0;
@@ -769,10 +997,14 @@ cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream)
 {
 	dim3 grid((p.hiz.width + kPyrTile - 1) / kPyrTile, (p.hiz.height + kPyrTile - 1) / kPyrTile);
 	bool exact = p.depth_width == 2 * p.hiz.width && p.depth_height == 2 * p.hiz.height;
+	PyramidParams q = p;
+	// 16-byte loads of the depth rows / 8-byte stores of mip 0 need aligned bases (row pitches are multiples of 4 / 2
+	// texels whenever a full 64-texel tile exists)
+	q.vector_ok = (reinterpret_cast<uintptr_t>(p.depth) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.hiz.texels) & 7u) == 0 && (p.depth_width & 3u) == 0;
 	if (exact)
-		pyramid_kernel<true><<<grid, kPyrBlock, 0, stream>>>(p);
+		pyramid_kernel<true><<<grid, kPyrBlock, 0, stream>>>(q);
 	else
-		pyramid_kernel<false><<<grid, kPyrBlock, 0, stream>>>(p);
+		pyramid_kernel<false><<<grid, kPyrBlock, 0, stream>>>(q);
 	return cudaGetLastError();
 }
 

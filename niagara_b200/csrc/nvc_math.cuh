@@ -90,7 +90,8 @@ __device__ __forceinline__ float length3(f3 a)
 }
 
 // drawcull.comp.glsl:77-83 == clustercull.comp.glsl:104-108
-__device__ __forceinline__ bool frustum_visible(const NvcCullData& cd, f3 c, float radius)
+template <typename CD>
+__device__ __forceinline__ bool frustum_visible(const CD& cd, f3 c, float radius)
 {
 	bool visible = __fsub_rn(__fmul_rn(c.z, cd.frustum[1]), __fmul_rn(fabsf(c.x), cd.frustum[0])) > -radius;
 	visible = visible && __fsub_rn(__fmul_rn(c.z, cd.frustum[3]), __fmul_rn(fabsf(c.y), cd.frustum[2])) > -radius;
@@ -98,68 +99,52 @@ __device__ __forceinline__ bool frustum_visible(const NvcCullData& cd, f3 c, flo
 	return visible;
 }
 
-// src/shaders/math.h:1-22
+// src/shaders/math.h:1-22.  Branch-free: the aabb is always computed (garbage, possibly NaN, when the sphere crosses
+// the near plane) and the early `return false` becomes the returned flag, so that a warp runs one straight path.
 __device__ __forceinline__ bool project_sphere(f3 c, float r, float znear, float P00, float P11, float4& aabb)
 {
-	if (c.z < __fadd_rn(r, znear))
-		return false;
+	bool ok = !(c.z < __fadd_rn(r, znear));
 
 	float crx = __fmul_rn(c.x, r), cry = __fmul_rn(c.y, r), crz = __fmul_rn(c.z, r);
 	float czr2 = __fsub_rn(__fmul_rn(c.z, c.z), __fmul_rn(r, r));
 
 	float vx = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), czr2));
-	float minx = __fdiv_rn(__fsub_rn(__fmul_rn(vx, c.x), crz), __fadd_rn(__fmul_rn(vx, c.z), crx));
-	float maxx = __fdiv_rn(__fadd_rn(__fmul_rn(vx, c.x), crz), __fsub_rn(__fmul_rn(vx, c.z), crx));
+	float vxx = __fmul_rn(vx, c.x), vxz = __fmul_rn(vx, c.z);
+	float minx = __fdiv_rn(__fsub_rn(vxx, crz), __fadd_rn(vxz, crx));
+	float maxx = __fdiv_rn(__fadd_rn(vxx, crz), __fsub_rn(vxz, crx));
 
 	float vy = __fsqrt_rn(__fadd_rn(__fmul_rn(c.y, c.y), czr2));
-	float miny = __fdiv_rn(__fsub_rn(__fmul_rn(vy, c.y), crz), __fadd_rn(__fmul_rn(vy, c.z), cry));
-	float maxy = __fdiv_rn(__fadd_rn(__fmul_rn(vy, c.y), crz), __fsub_rn(__fmul_rn(vy, c.z), cry));
+	float vyy = __fmul_rn(vy, c.y), vyz = __fmul_rn(vy, c.z);
+	float miny = __fdiv_rn(__fsub_rn(vyy, crz), __fadd_rn(vyz, cry));
+	float maxy = __fdiv_rn(__fadd_rn(vyy, crz), __fsub_rn(vyz, cry));
 
 	aabb.x = __fadd_rn(__fmul_rn(__fmul_rn(minx, P00), 0.5f), 0.5f);
 	aabb.y = __fadd_rn(__fmul_rn(__fmul_rn(maxy, P11), -0.5f), 0.5f);
 	aabb.z = __fadd_rn(__fmul_rn(__fmul_rn(maxx, P00), 0.5f), 0.5f);
 	aabb.w = __fadd_rn(__fmul_rn(__fmul_rn(miny, P11), -0.5f), 0.5f);
-	return true;
+	return ok;
 }
 
-// smallest integer L with 2^L >= x for finite x > 0
-__device__ __forceinline__ int ceil_log2_exact(float x)
-{
-	uint32_t bits = __float_as_uint(x);
-	int e = int((bits >> 23) & 0xff);
-	uint32_t man = bits & 0x7fffffu;
-	if (e == 0)
-	{
-		int top = 31 - __clz(man);
-		bool pow2 = (man & (man - 1)) == 0;
-		return top - 149 + (pow2 ? 0 : 1);
-	}
-	return e - 127 + (man ? 1 : 0);
-}
-
-// src/shaders/math.h:24-39; returns an integer level already clamped to [0, max_level]
+// src/shaders/math.h:24-39; returns an integer level already clamped to [0, max_level].
+// level = ceil(log2(m)) with m = max(size.x * pw, size.y * ph), minus one if the finer mip still fits 2x2, max(., 0).
+// ceil(log2 m) <= 0 for every m <= 1 (and log2 of a non-positive / NaN m is -inf / NaN, max(level, 0) = 0), so
+// anything but m > 1 yields level 0; for m > 1 the float is normal and L = exponent + (mantissa != 0).
 __device__ __forceinline__ int occlusion_mip(float4 aabb, float pw, float ph, int max_level)
 {
 	float sizex = __fsub_rn(aabb.z, aabb.x);
 	float sizey = __fsub_rn(aabb.w, aabb.y);
-	float a = __fmul_rn(sizex, pw);
-	float b = __fmul_rn(sizey, ph);
-	float m = (a > b) ? a : b;
-	if (b != b && !(a != a))
-		m = a;
-
-	if (!(m > 0.f))
+	// GLSL max(x, y) = (x < y) ? y : x; fmaxf agrees for ordered operands and keeps the defined operand when exactly
+	// one is NaN (the oracle's rule)
+	float m = fmaxf(__fmul_rn(sizex, pw), __fmul_rn(sizey, ph));
+	if (!(m > 1.0f))
 		return 0;
-	if (m == __int_as_float(0x7f800000))
+	uint32_t bits = __float_as_uint(m);
+	if (bits == 0x7f800000u)
 		return max_level;
+	int L = int(bits >> 23) - 127 + ((bits & 0x7fffffu) ? 1 : 0); // 1..128
 
-	int L = ceil_log2_exact(m);
-	if (L <= 0)
-		return 0;
-
-	// exp2(1 - L): exact power of two; 1 - L is in [-127, 0] here (L <= 128), build it from the exponent bits,
-	// falling back to the subnormal 2^-127 when L == 128
-	float scale = (L <= 127) ? __uint_as_float(uint32_t(127 + 1 - L) << 23) : __uint_as_float(0x00400000u);
+	// exp2(1 - L): exact power of two built from exponent bits (subnormal 2^-127 when L == 128)
+	float scale = (L <= 127) ? __uint_as_float(uint32_t(128 - L) << 23) : __uint_as_float(0x00400000u);
 	float fmx = __fmul_rn(pw, scale);
 	float fmy = __fmul_rn(ph, scale);
 	float px = __fmul_rn(aabb.x, fmx);
@@ -178,35 +163,22 @@ struct Footprint
 	bool usex1, usey1;
 };
 
+// x = u * w - 0.5; texels floor(x) and floor(x) + 1, clamped to the edge; the second one only counts when its weight
+// fract(x) is non-zero.  Non-finite coordinates need no special case: a NaN clamps both indices to 0 and +-inf clamps
+// both to the same edge texel, so whether the second texel "counts" cannot change the minimum.
 __device__ __forceinline__ Footprint min_footprint(uint32_t w, uint32_t h, float u, float v)
 {
 	float x = __fsub_rn(__fmul_rn(u, (float)w), 0.5f);
 	float y = __fsub_rn(__fmul_rn(v, (float)h), 0.5f);
 	float fx0 = floorf(x), fy0 = floorf(y);
-	float fx = __fsub_rn(x, fx0), fy = __fsub_rn(y, fy0);
 	float wmax = (float)(w - 1), hmax = (float)(h - 1);
-	float fx1 = __fadd_rn(fx0, 1.f), fy1 = __fadd_rn(fy0, 1.f);
-	float cx0 = fx0 < 0.f ? 0.f : (fx0 > wmax ? wmax : fx0);
-	float cy0 = fy0 < 0.f ? 0.f : (fy0 > hmax ? hmax : fy0);
-	float cx1 = fx1 < 0.f ? 0.f : (fx1 > wmax ? wmax : fx1);
-	float cy1 = fy1 < 0.f ? 0.f : (fy1 > hmax ? hmax : fy1);
-	if (!(x == x))
-	{
-		cx0 = cx1 = 0.f;
-		fx = 0.f;
-	}
-	if (!(y == y))
-	{
-		cy0 = cy1 = 0.f;
-		fy = 0.f;
-	}
 	Footprint f;
-	f.x0 = (uint32_t)cx0;
-	f.x1 = (uint32_t)cx1;
-	f.y0 = (uint32_t)cy0;
-	f.y1 = (uint32_t)cy1;
-	f.usex1 = fx != 0.f;
-	f.usey1 = fy != 0.f;
+	f.x0 = (uint32_t)fminf(fmaxf(fx0, 0.f), wmax);
+	f.y0 = (uint32_t)fminf(fmaxf(fy0, 0.f), hmax);
+	f.x1 = (uint32_t)fminf(fmaxf(__fadd_rn(fx0, 1.f), 0.f), wmax);
+	f.y1 = (uint32_t)fminf(fmaxf(__fadd_rn(fy0, 1.f), 0.f), hmax);
+	f.usex1 = __fsub_rn(x, fx0) != 0.f;
+	f.usey1 = __fsub_rn(y, fy0) != 0.f;
 	return f;
 }
 
@@ -214,22 +186,18 @@ template <typename Load>
 __device__ __forceinline__ float sample_min(Load load, uint32_t w, uint32_t h, float u, float v)
 {
 	Footprint f = min_footprint(w, h, u, v);
-	// issue all four loads unconditionally (clamped addresses are always valid), select afterwards: keeps the
-	// loads independent and in flight together
-	float t00 = load(f.y0 * w + f.x0);
-	float t01 = load(f.y0 * w + f.x1);
-	float t10 = load(f.y1 * w + f.x0);
-	float t11 = load(f.y1 * w + f.x1);
-	float r = t00;
-	if (f.usex1)
-		r = fminf(r, t01);
-	if (f.usey1)
-	{
-		r = fminf(r, t10);
-		if (f.usex1)
-			r = fminf(r, t11);
-	}
-	return r;
+	// all four loads are issued unconditionally (clamped addresses are always valid) so they are in flight together;
+	// texels whose weight is zero are replaced by +inf before the min (VK_SAMPLER_REDUCTION_MODE_MIN ignores them)
+	const float inf = __int_as_float(0x7f800000);
+	uint32_t r0 = f.y0 * w, r1 = f.y1 * w;
+	float t00 = load(r0 + f.x0);
+	float t01 = load(r0 + f.x1);
+	float t10 = load(r1 + f.x0);
+	float t11 = load(r1 + f.x1);
+	t01 = f.usex1 ? t01 : inf;
+	t10 = f.usey1 ? t10 : inf;
+	t11 = (f.usex1 && f.usey1) ? t11 : inf;
+	return fminf(fminf(t00, t01), fminf(t10, t11));
 }
 
 } // namespace nvc

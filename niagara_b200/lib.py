@@ -59,7 +59,8 @@ SIGNATURES = [
 
 
 def library_path():
-    return _build.LIB_PATH
+    # NVC_LIB_PATH selects a tuning variant built with _build.build(defines=..., out=...); default = the product build
+    return os.environ.get("NVC_LIB_PATH") or _build.LIB_PATH
 
 
 def load_library():

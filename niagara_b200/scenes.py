@@ -10,23 +10,26 @@ from . import host, layout
 
 
 def _unit_vectors(rng, n):
-    v = rng.standard_normal((n, 3))
-    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v = rng.standard_normal((n, 3), dtype=np.float32)
+    v /= np.sqrt((v * v).sum(axis=1, keepdims=True))
     return v
 
 
-def synthetic_meshlets(count, seed=1):
+def synthetic_meshlets(count, seed=1, chunk=1 << 20):
     """Meshlet cull bounds with kitten-like statistics: center fp16 U(-0.5,0.5)^3, radius fp16 in
-    [0.02, 0.45] skewed to small values (mean ~0.1), s8 unit cone axis, s8 cutoff U(16,127) with ~6 % == 127."""
+    [0.02, 0.45] skewed to small values (mean ~0.1), s8 unit cone axis, s8 cutoff U(16,127) with ~6 % == 127.
+    Generated in chunks (float32 temporaries) so that 10M records do not need GBs of scratch."""
     rng = np.random.default_rng(seed)
     m = np.zeros(count, dtype=layout.MESHLET_DTYPE)
-    m["center"] = rng.uniform(-0.5, 0.5, (count, 3)).astype(np.float16).view(np.uint16)
-    m["radius"] = (0.02 + 0.43 * rng.random(count) ** 4).astype(np.float16).view(np.uint16)
-    axis = np.rint(_unit_vectors(rng, count) * 127.0).astype(np.int8)
-    m["cone_axis"] = axis
-    cutoff = rng.integers(16, 128, count)
-    cutoff[rng.random(count) < 0.06] = 127
-    m["cone_cutoff"] = cutoff.astype(np.int8)
+    for lo in range(0, count, chunk):
+        n = min(chunk, count - lo)
+        part = m[lo : lo + n]
+        part["center"] = (rng.random((n, 3), dtype=np.float32) - np.float32(0.5)).astype(np.float16).view(np.uint16)
+        part["radius"] = (np.float32(0.02) + np.float32(0.43) * rng.random(n, dtype=np.float32) ** 4).astype(np.float16).view(np.uint16)
+        part["cone_axis"] = np.rint(_unit_vectors(rng, n) * np.float32(127.0)).astype(np.int8)
+        cutoff = rng.integers(16, 128, n, dtype=np.int16)
+        cutoff[rng.random(n, dtype=np.float32) < 0.06] = 127
+        part["cone_cutoff"] = cutoff.astype(np.int8)
     m["vertexCount"] = 64
     m["triangleCount"] = 96
     m["dataOffset"] = (np.arange(count, dtype=np.uint64) * 40 % (1 << 32)).astype(np.uint32)
@@ -74,7 +77,7 @@ def frustum_draws(count, mesh_indices, fov_y=math.radians(70.0), aspect=1.0, zmi
     d["position"][:, 1] = (rng.uniform(-1, 1, count) * ty * z).astype(np.float32)
     d["position"][:, 2] = (-z).astype(np.float32)
     d["scale"] = ((rng.random(count) + 1.0) * 2.0).astype(np.float32)
-    axis = _unit_vectors(rng, count)
+    axis = _unit_vectors(rng, count).astype(np.float64)
     angle = np.radians(rng.random(count) * 90.0)
     d["orientation"][:, :3] = (axis * np.sin(angle * 0.5)[:, None]).astype(np.float32)
     d["orientation"][:, 3] = np.cos(angle * 0.5).astype(np.float32)

@@ -156,7 +156,7 @@ def test_empty_and_tiny_inputs(golden_dir):
             _compare_cluster_pass(g, o, ("tiny", n, f))
 
 
-@pytest.mark.parametrize("size", [(64, 64), (128, 128), (100, 60), (1920, 1080), (4096, 4096), (2048, 256), (30, 17), (3, 2), (1, 1), (4096, 600)])
+@pytest.mark.parametrize("size", [(64, 64), (128, 128), (100, 60), (1920, 1080), (4096, 4096), (2048, 256), (30, 17), (3, 2), (1, 1), (4096, 600), (16384, 4), (4, 16384), (8192, 130), (512, 512)])
 def test_pyramid_sizes(size):
     torch = _torch()
     from niagara_b200.path import VisibilityPath
@@ -172,6 +172,37 @@ def test_pyramid_sizes(size):
         g.pyramid(torch.from_numpy(depth).cuda())
         o.pyramid(depth)
         _compare_pyramid(g, o, size)
+
+
+def test_pyramid_unaligned_depth_pointer():
+    """the 16-byte-load fast path must not be taken for a depth pointer that is only 4-byte aligned"""
+    torch = _torch()
+    from niagara_b200.path import VisibilityPath
+
+    w = h = 256
+    rng = np.random.default_rng(3)
+    depth = rng.random((h, w), dtype=np.float32)
+    dummy = (np.zeros(1, layout.MESH_DTYPE), np.zeros(1, layout.MESHLET_DTYPE), np.zeros(1, layout.MESHDRAW_DTYPE))
+    g = VisibilityPath(*dummy, w, h, task_wglimit=64, cluster_limit=256)
+    o = oracle_lib.OraclePath(*dummy, w, h)
+    buf = torch.zeros(w * h + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(h, w)
+    view.copy_(torch.from_numpy(depth))
+    assert view.data_ptr() % 16 != 0
+    g.pyramid(view)
+    o.pyramid(depth)
+    _compare_pyramid(g, o, "unaligned")
+
+
+def test_big_meshes_many_groups_per_draw(golden_dir):
+    """draws with hundreds of meshlets (several task commands per draw, blocks that exceed the command staging
+    buffer take the direct write path)"""
+    meshes, nmeshlets = scenes.synthetic_meshes(40, 3, 700, seed=5)
+    meshlets = scenes.synthetic_meshlets(nmeshlets, seed=6)
+    s = scenes.reference_random_scene(meshes, meshlets, 30000, screen=(1024, 1024))
+    s.draws["position"][:, 2] = -np.abs(s.draws["position"][:, 2]) * 0.4 - 10
+    s.draws["position"][:, :2] *= 0.2
+    _run_frames(s, frames=2)
 
 
 def test_overflow_limits(golden_dir):
