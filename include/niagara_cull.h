@@ -185,6 +185,13 @@ NVC_API const char* nvc_status_string(int status);
 NVC_API const char* nvc_last_error(const NvcContext* ctx);
 NVC_API const char* nvc_version(void);
 
+/* Tuning: stage the coarse tail of the depth pyramid (top mips, at most `texels` texels, capped at 11264 = 44 KB) into
+ * shared memory once per CTA of the late cluster pass with one TMA bulk copy (cp.async.bulk, SASS UBLKCP); lookups
+ * whose whole warp samples a staged mip then read shared memory.  0 (default) disables it: on the measured workloads
+ * the shared-memory carve-out costs more L1 hit rate on the fine mips than the staged mips save.
+ * Results are identical either way.  Also settable with the environment variable NVC_HIZ_STAGE_TEXELS. */
+NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels);
+
 /* ---- pyramid layout (host only): niagara.cpp:439-447 previousPow2, resources.cpp:280-292 getImageMipLevels,
  *      niagara.cpp:1339-1342 ------------------------------------------------------------------------- */
 NVC_API uint32_t nvc_previous_pow2(uint32_t v);

@@ -2,6 +2,7 @@
 #include "nvc_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace
@@ -13,6 +14,40 @@ int cuda_fail(NvcContext* ctx, cudaError_t e, const char* what)
 		ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
 	return NVC_ERROR_CUDA;
 }
+
+// Picks the coarse tail of the pyramid that is staged into shared memory by TMA: the largest set of top mips whose
+// texels fit the budget, whose start is 16-byte aligned in the packed allocation and that holds at least one 16-byte unit.
+void choose_stage(nvc::HiZDesc& hz, uint32_t total_texels, uint32_t budget_texels)
+{
+	hz.stage_level = hz.levels;
+	hz.stage_texels = 0;
+	if (budget_texels == 0)
+		return;
+	for (uint32_t l = 0; l < hz.levels; ++l)
+	{
+		uint32_t tail = total_texels - hz.level_offset[l];
+		uintptr_t addr = reinterpret_cast<uintptr_t>(hz.texels + hz.level_offset[l]);
+		if (tail <= budget_texels && tail >= 4 && (addr & 15u) == 0)
+		{
+			hz.stage_level = l;
+			hz.stage_texels = tail;
+			return;
+		}
+	}
+}
+
+} // namespace
+
+namespace nvc
+{
+void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_texels)
+{
+	choose_stage(hz, total_texels, budget_texels);
+}
+} // namespace nvc
+
+namespace
+{
 
 bool fill_hiz(const NvcHiZ* in, nvc::HiZDesc& out)
 {
@@ -26,6 +61,8 @@ bool fill_hiz(const NvcHiZ* in, nvc::HiZDesc& out)
 	out.height = in->height;
 	out.levels = in->levels;
 	memcpy(out.level_offset, in->level_offset, sizeof(out.level_offset));
+	out.stage_level = in->levels; // staging is opted into per pass
+	out.stage_texels = 0;
 	return true;
 }
 
@@ -97,7 +134,13 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 	if (e == cudaSuccess)
 		e = cudaMemset(ctx->scratch, 0, sizeof(nvc::Scratch));
 	if (e == cudaSuccess)
-		e = nvc::clustercull_occupancy(&ctx->cluster_blocks_early, &ctx->cluster_blocks_late);
+	{
+		if (const char* env = getenv("NVC_HIZ_STAGE_TEXELS"))
+			ctx->hiz_stage_budget = uint32_t(strtoul(env, nullptr, 10));
+		if (ctx->hiz_stage_budget > 11264)
+			ctx->hiz_stage_budget = 11264; // 44 KB: stays under the 48 KB dynamic shared memory default
+		e = nvc::clustercull_occupancy(&ctx->cluster_blocks_early, &ctx->cluster_blocks_late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
+	}
 	if (e == cudaSuccess)
 		e = cudaDeviceSynchronize();
 	if (e != cudaSuccess)
@@ -112,6 +155,8 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		ctx->cluster_blocks_early = 1;
 	if (ctx->cluster_blocks_late < 1)
 		ctx->cluster_blocks_late = 1;
+	if (ctx->cluster_blocks_late_staged < 1)
+		ctx->cluster_blocks_late_staged = 1;
 
 	*out_ctx = ctx;
 	return NVC_OK;
@@ -126,6 +171,21 @@ NVC_API void nvc_destroy(NvcContext* ctx)
 	if (ctx->scratch)
 		cudaFree(ctx->scratch);
 	delete ctx;
+}
+
+NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels)
+{
+	if (!ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	ctx->hiz_stage_budget = texels > 11264 ? 11264 : texels; // 44 KB: stays under the 48 KB dynamic shared memory default
+	int early = 0, late = 0;
+	cudaError_t e = nvc::clustercull_occupancy(&early, &late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
+	if (e != cudaSuccess)
+		return cuda_fail(ctx, e, "nvc_set_hiz_staging");
+	if (ctx->cluster_blocks_late_staged < 1)
+		ctx->cluster_blocks_late_staged = 1;
+	return NVC_OK;
 }
 
 NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late, int task,
@@ -192,7 +252,13 @@ NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cu
 	p.cluster_indices = cluster_indices;
 	p.cluster_count4 = cluster_count4;
 
-	uint32_t blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_blocks_late : ctx->cluster_blocks_early);
+	bool staged = false;
+	if (late && cull->clusterOcclusionEnabled == 1 && hiz)
+	{
+		nvc::choose_stage_public(p.hiz, hiz->total_texels, ctx->hiz_stage_budget);
+		staged = p.hiz.stage_level < p.hiz.levels;
+	}
+	uint32_t blocks = uint32_t(ctx->sm_count) * uint32_t(late ? (staged ? ctx->cluster_blocks_late_staged : ctx->cluster_blocks_late) : ctx->cluster_blocks_early);
 	cudaError_t e = nvc::launch_clustercull(p, late != 0, blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_clustercull");
 }

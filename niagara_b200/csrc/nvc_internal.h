@@ -17,7 +17,8 @@ struct NvcContext
 {
 	int device = 0;
 	int sm_count = 0;
-	int cluster_blocks_early = 0, cluster_blocks_late = 0;
+	int cluster_blocks_early = 0, cluster_blocks_late = 0, cluster_blocks_late_staged = 0;
+	uint32_t hiz_stage_budget = 0; // texels (24 KB) of coarse Hi-Z mips staged per CTA; 0 = off (env NVC_HIZ_STAGE_TEXELS)
 	NvcLimits limits = { NVC_TASK_WGLIMIT, NVC_CLUSTER_LIMIT };
 	nvc::Scratch* scratch = nullptr;
 	std::string last_error;
@@ -53,6 +54,9 @@ struct HiZDesc
 	float* texels;
 	uint32_t width, height, levels;
 	uint32_t level_offset[NVC_MAX_HIZ_LEVELS];
+	// mips >= stage_level (the coarse tail of the packed pyramid, stage_texels texels) are staged into shared memory
+	// once per CTA with one TMA bulk copy; stage_level == levels disables staging
+	uint32_t stage_level, stage_texels;
 };
 
 struct DrawCullParams
@@ -96,6 +100,8 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaS
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream);
-cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late);
+cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late, int* blocks_per_sm_late_staged, uint32_t stage_bytes);
+uint32_t hiz_stage_bytes(const HiZDesc& hiz);
+void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_texels);
 
 } // namespace nvc

@@ -9,6 +9,7 @@
 // Compiled with -fmad=false; see nvc_math.cuh for the arithmetic contract.
 #include "nvc_internal.h"
 #include "nvc_math.cuh"
+#include "nvc_tma.cuh"
 
 #include <cuda_runtime.h>
 
@@ -74,21 +75,68 @@ struct HiZLoad
 	__device__ __forceinline__ float operator()(uint32_t idx) const { return __ldg(texels + (offset + idx)); }
 };
 
+// Loads from the shared-memory copy of the coarse mips (staged by TMA at kernel start); offset is relative to it
+struct HiZLoadShared
+{
+	const float* staged;
+	uint32_t offset;
+	__device__ __forceinline__ float operator()(uint32_t idx) const { return staged[offset + idx]; }
+};
+
 // drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123.  Straight-line: every lane computes, the
 // "sphere crosses the near plane -> stays visible" case is a select at the end.
-template <typename CD>
-__device__ __forceinline__ bool occlusion_visible(const CD& cd, const HiZDesc& hiz, f3 center, float radius)
+// STAGED: when every live lane of the warp samples a mip that was staged into shared memory the four texel fetches
+// are shared-memory loads; otherwise the warp takes the global (L1/L2) path.  The choice is warp-uniform, so the
+// common fine-mip case pays one vote and no per-load select.
+template <bool STAGED, typename CD>
+__device__ __forceinline__ bool occlusion_visible(const CD& cd, const HiZDesc& hiz, const float* staged, bool alive, f3 center, float radius)
 {
 	float4 aabb;
 	bool ok = project_sphere(center, radius, cd.znear, cd.P00, cd.P11, aabb);
 	int level = occlusion_mip(aabb, cd.pyramidWidth, cd.pyramidHeight, int(hiz.levels) - 1);
+	if (STAGED && !alive)
+		level = int(hiz.levels) - 1; // dead lanes compute on garbage: keep their (ignored) fetch inside the staged range
 	uint32_t w = max(1u, hiz.width >> level), h = max(1u, hiz.height >> level);
 	float u = __fmul_rn(__fadd_rn(aabb.x, aabb.z), 0.5f);
 	float v = __fmul_rn(__fadd_rn(aabb.y, aabb.w), 0.5f);
-	HiZLoad load = { hiz.texels, hiz.level_offset[level] };
-	float depth = sample_min(load, w, h, u, v);
+	float depth;
+	if (STAGED && __all_sync(0xffffffffu, uint32_t(level) >= hiz.stage_level))
+	{
+		HiZLoadShared load = { staged, hiz.level_offset[level] - hiz.level_offset[hiz.stage_level] };
+		depth = sample_min(load, w, h, u, v);
+	}
+	else
+	{
+		HiZLoad load = { hiz.texels, hiz.level_offset[level] };
+		depth = sample_min(load, w, h, u, v);
+	}
 	float depthSphere = __fdiv_rn(cd.znear, __fsub_rn(center.z, radius));
 	return !ok || depthSphere > depth;
+}
+
+// Stages the coarse tail of the pyramid (mips >= stage_level, contiguous in the packed layout) into shared memory:
+// one elected thread arms an mbarrier and issues ONE cp.async.bulk (TMA, UBLKCP); the <= 3 texels that do not fill a
+// 16-byte unit are copied by hand.  Every thread must call hiz_stage_wait() before reading `staged`.
+__device__ __forceinline__ void hiz_stage_begin(const HiZDesc& hiz, float* staged, uint64_t* bar)
+{
+	const uint32_t bulk_texels = hiz.stage_texels & ~3u;
+	if (threadIdx.x == 0)
+		mbar_init(bar, 1);
+	__syncthreads();
+	const float* src = hiz.texels + hiz.level_offset[hiz.stage_level];
+	if (threadIdx.x == 0)
+	{
+		mbar_arrive_expect_tx(bar, bulk_texels * 4u);
+		bulk_copy_g2s(staged, src, bulk_texels * 4u, bar);
+	}
+	if (threadIdx.x < hiz.stage_texels - bulk_texels)
+		staged[bulk_texels + threadIdx.x] = __ldg(src + bulk_texels + threadIdx.x);
+	__syncthreads();
+}
+
+__device__ __forceinline__ void hiz_stage_wait(uint64_t* bar)
+{
+	mbar_wait(bar, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -148,7 +196,7 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			visible = visible || cd.cullingEnabled == 0; // :85
 
 			if (LATE && visible && cd.occlusionEnabled == 1) // :87
-				visible = occlusion_visible(cd, p.hiz, center, radius);
+				visible = occlusion_visible<false>(cd, p.hiz, nullptr, true, center, radius);
 
 			// :108  (TASK_CULL == 1, config.h:8)
 			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv == 0 || cd.postPass != 0))
@@ -371,8 +419,8 @@ __device__ __forceinline__ void meshlet_fetch(const ClusterParams& p, const Item
 //   visible  the GLSL's `visible` after all tests
 //   skip     clustercull.comp.glsl:97-98
 //   oldbit   the lane's previous visibility bit (meaningful when clusterOcclusionEnabled == 1 && postPass == 0)
-template <bool LATE>
-__device__ __forceinline__ void meshlet_compute(const ClusterParams& p, const ClusterConsts& cc, const ItemRef& r, ItemData& d, bool& visible, bool& skip, bool& oldbit)
+template <bool LATE, bool STAGED>
+__device__ __forceinline__ void meshlet_compute(const ClusterParams& p, const ClusterConsts& cc, const float* staged, const ItemRef& r, ItemData& d, bool& visible, bool& skip, bool& oldbit)
 {
 	const NvcCullData& cd = p.cull;
 	bool alive = r.active;
@@ -416,7 +464,7 @@ __device__ __forceinline__ void meshlet_compute(const ClusterParams& p, const Cl
 	}
 
 	if (LATE && cd.clusterOcclusionEnabled == 1 && __any_sync(0xffffffffu, alive)) // :110
-		alive = occlusion_visible(cc, p.hiz, center, radius) && alive;
+		alive = occlusion_visible<STAGED>(cc, p.hiz, staged, alive, center, radius) && alive;
 
 	visible = alive;
 }
@@ -482,11 +530,17 @@ __device__ __forceinline__ void flush_stage(const ClusterParams& p, uint32_t* st
 	nst = 0;
 }
 
-template <bool LATE>
+template <bool LATE, bool STAGED>
 __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) clustercull_kernel(const ClusterParams p)
 {
 	__shared__ uint32_t s_stage[kClusterWarps][kStage];
 	__shared__ uint32_t s_is_last;
+	__shared__ __align__(8) uint64_t s_hiz_bar;
+	extern __shared__ __align__(16) float s_hiz[]; // coarse Hi-Z mips (STAGED only)
+
+	if (STAGED)
+		hiz_stage_begin(p.hiz, s_hiz, &s_hiz_bar); // the copy overlaps the first batch's command / geometry loads
+	bool hiz_ready = !STAGED;
 
 	const NvcCullData& cd = p.cull;
 	const ClusterConsts& cc = cd;
@@ -594,8 +648,13 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 				meshlet_fetch<LATE>(p, next, next_data);
 			}
 #endif
+			if (!hiz_ready)
+			{
+				hiz_stage_wait(&s_hiz_bar);
+				hiz_ready = true;
+			}
 			bool skip, oldbit, visible;
-			meshlet_compute<LATE>(p, cc, cur, cur_data, visible, skip, oldbit);
+			meshlet_compute<LATE, STAGED>(p, cc, s_hiz, cur, cur_data, visible, skip, oldbit);
 
 			// :126-131 — the GLSL rewrites every valid lane's bit; bits that already hold the new value need no
 			// traffic, so the whole chunk skips the update when no lane changes state (the steady-state case)
@@ -627,6 +686,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 	}
 	if (nst)
 		flush_stage(p, stage, nst);
+	if (!hiz_ready)
+		hiz_stage_wait(&s_hiz_bar); // never leave the CTA while the bulk copy may still be writing its shared memory
 
 	// ---- last-block epilogue: clustersubmit.comp.glsl:25-45 ----
 	__threadfence();
@@ -697,7 +758,7 @@ __global__ void __launch_bounds__(kClusterBlock) taskcull_kernel(const ClusterPa
 			r.code = cid | (mgi << 24);
 			ItemData d;
 			meshlet_fetch<LATE>(p, r, d);
-			meshlet_compute<LATE>(p, cc, r, d, visible, skip, oldbit);
+			meshlet_compute<LATE, false>(p, cc, nullptr, r, d, visible, skip, oldbit);
 			if (track_late && __any_sync(0xffffffffu, active && (cd.postPass != 0 || oldbit != visible)))
 				update_visibility_bits(p.meshlet_visibility, active, visible, c_mvo + mgi);
 			const bool out = visible && !skip;
@@ -975,12 +1036,20 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaS
 	return cudaGetLastError();
 }
 
+uint32_t hiz_stage_bytes(const HiZDesc& hiz)
+{
+	return hiz.stage_level < hiz.levels ? ((hiz.stage_texels * 4u + 15u) & ~15u) : 0u;
+}
+
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream)
 {
-	if (late)
-		clustercull_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p);
+	const uint32_t stage_bytes = late ? hiz_stage_bytes(p.hiz) : 0u;
+	if (late && stage_bytes)
+		clustercull_kernel<true, true><<<blocks, kClusterBlock, stage_bytes, stream>>>(p);
+	else if (late)
+		clustercull_kernel<true, false><<<blocks, kClusterBlock, 0, stream>>>(p);
 	else
-		clustercull_kernel<false><<<blocks, kClusterBlock, 0, stream>>>(p);
+		clustercull_kernel<false, false><<<blocks, kClusterBlock, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
@@ -1008,12 +1077,14 @@ cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream)
 	return cudaGetLastError();
 }
 
-cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
+cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late, int* blocks_per_sm_late_staged, uint32_t stage_bytes)
 {
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_kernel<false>, kClusterBlock, 0);
-	if (e != cudaSuccess)
-		return e;
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_kernel<true>, kClusterBlock, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_kernel<false, false>, kClusterBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_kernel<true, false>, kClusterBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late_staged, clustercull_kernel<true, true>, kClusterBlock, stage_bytes);
+	return e;
 }
 
 } // namespace nvc

@@ -25,7 +25,7 @@ def _round_up(v, m):
 
 
 class VisibilityPath:
-    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True):
+    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, hiz_stage_texels=None):
         """meshes / meshlets / draws: structured numpy arrays (layout.MESH_DTYPE / MESHLET_DTYPE / MESHDRAW_DTYPE) or
         already-resident torch uint8 tensors.  draws must already carry meshletVisibilityOffset
         (host.visibility_offsets)."""
@@ -40,6 +40,8 @@ class VisibilityPath:
         ctx = ctypes.c_void_p()
         check(self.lib.nvc_create(self.device.index or 0, ctypes.byref(limits), ctypes.byref(ctx)), None, "nvc_create")
         self.ctx = ctx
+        if hiz_stage_texels is not None:
+            check(self.lib.nvc_set_hiz_staging(self.ctx, int(hiz_stage_texels)), self.ctx, "nvc_set_hiz_staging")
         self.task_wglimit = int(task_wglimit)
         self.cluster_limit = int(cluster_limit)
 

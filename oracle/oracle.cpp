@@ -22,6 +22,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -433,6 +436,84 @@ void clusterRange(const NvcCullData& cd, bool late, const NvcMeshTaskCommand* cm
 	}
 }
 
+// Minimal persistent worker pool: the multi-threaded oracle is also the reported CPU baseline, so it should not pay
+// for creating (cores) threads in every pass.
+class Pool
+{
+public:
+	static Pool& get()
+	{
+		static Pool p;
+		return p;
+	}
+
+	// runs job(0..count-1) on up to `count` workers (the caller takes index 0) and waits for all of them
+	void run(int count, const std::function<void(int)>& job)
+	{
+		if (count <= 1)
+		{
+			job(0);
+			return;
+		}
+		std::unique_lock<std::mutex> lock(mutex_);
+		while (int(workers_.size()) < count - 1)
+			workers_.emplace_back([this, idx = int(workers_.size())]() { loop(idx); });
+		job_ = &job;
+		active_ = count - 1;
+		pending_ = count - 1;
+		++generation_;
+		lock.unlock();
+		wake_.notify_all();
+		job(0);
+		lock.lock();
+		done_.wait(lock, [this]() { return pending_ == 0; });
+		job_ = nullptr;
+	}
+
+private:
+	Pool() {}
+	~Pool()
+	{
+		{
+			std::lock_guard<std::mutex> lock(mutex_);
+			stop_ = true;
+			++generation_;
+		}
+		wake_.notify_all();
+		for (auto& w : workers_)
+			w.join();
+	}
+
+	void loop(int idx)
+	{
+		uint64_t seen = 0;
+		for (;;)
+		{
+			std::unique_lock<std::mutex> lock(mutex_);
+			wake_.wait(lock, [&]() { return generation_ != seen; });
+			seen = generation_;
+			if (stop_)
+				return;
+			if (idx >= active_)
+				continue;
+			const std::function<void(int)>* job = job_;
+			lock.unlock();
+			(*job)(idx + 1);
+			lock.lock();
+			if (--pending_ == 0)
+				done_.notify_all();
+		}
+	}
+
+	std::mutex mutex_;
+	std::condition_variable wake_, done_;
+	std::vector<std::thread> workers_;
+	const std::function<void(int)>* job_ = nullptr;
+	int active_ = 0, pending_ = 0;
+	uint64_t generation_ = 0;
+	bool stop_ = false;
+};
+
 template <typename F>
 void parallelRanges(uint32_t n, int threads, F&& fn)
 {
@@ -443,14 +524,10 @@ void parallelRanges(uint32_t n, int threads, F&& fn)
 		fn(0, 0u, n);
 		return;
 	}
-	std::vector<std::thread> pool;
-	for (int t = 0; t < nt; ++t)
-	{
+	Pool::get().run(nt, [&](int t) {
 		uint32_t b = uint32_t(uint64_t(n) * t / nt), e = uint32_t(uint64_t(n) * (t + 1) / nt);
-		pool.emplace_back([&fn, t, b, e]() { fn(t, b, e); });
-	}
-	for (auto& th : pool)
-		th.join();
+		fn(t, b, e);
+	});
 }
 
 } // namespace
@@ -479,29 +556,51 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 	std::vector<std::vector<Emit>> parts(size_t(std::max(1, nt)));
 	parallelRanges(n, nt, [&](int t, uint32_t b, uint32_t e) { drawcullRange(cd, late != 0, draws, meshes, draw_visibility, hiz ? &hv : nullptr, b, e, parts[size_t(t)], lod_out); });
 
-	uint32_t count = 0; // commandCount; vkCmdFillBuffer(dccb, 0, 4, 0) niagara.cpp:1541
+	// commandCount starts at 0 (vkCmdFillBuffer(dccb, 0, 4, 0) niagara.cpp:1541).  Slot of every emitted draw = exclusive
+	// prefix sum in ascending di order (= the serial atomicAdd sequence); the per-thread lists are written in parallel.
+	const size_t np = parts.size();
+	std::vector<uint32_t> part_base(np + 1, 0);
+	for (size_t t = 0; t < np; ++t)
+	{
+		uint64_t units = 0;
+		if (task)
+			for (const Emit& e : parts[t])
+			{
+				const NvcMeshLod& lod = meshes[draws[e.di].meshIndex].lods[e.lod];
+				units += (lod.meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
+			}
+		else
+			units = parts[t].size();
+		part_base[t + 1] = uint32_t(part_base[t] + units);
+	}
+	const uint32_t count = part_base[np];
+
 	if (task)
 	{
 		NvcMeshTaskCommand* out = static_cast<NvcMeshTaskCommand*>(commands);
-		for (auto& part : parts)
-			for (const Emit& e : part)
+		parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+			for (uint32_t t = pb; t < pe; ++t)
 			{
-				const NvcMeshDraw& draw = draws[e.di];
-				const NvcMeshLod& lod = meshes[draw.meshIndex].lods[e.lod];
-				uint32_t taskGroups = (lod.meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
-				uint32_t dci = count;                                                           // :123 atomicAdd
-				count += taskGroups;
-				if (uint64_t(dci) + taskGroups <= wglimit) // :129 drop on overflow, counter still advances
-					for (uint32_t i = 0; i < taskGroups; ++i)
-					{
-						NvcMeshTaskCommand& c = out[dci + i];
-						c.drawId = e.di;
-						c.taskOffset = lod.meshletOffset + i * NVC_TASK_WGSIZE;
-						c.taskCount = std::min(NVC_TASK_WGSIZE, lod.meshletCount - i * NVC_TASK_WGSIZE);
-						c.lateDrawVisibility = e.dv;
-						c.meshletVisibilityOffset = draw.meshletVisibilityOffset + i * NVC_TASK_WGSIZE;
-					}
+				uint32_t dci = part_base[t]; // :123 atomicAdd
+				for (const Emit& e : parts[t])
+				{
+					const NvcMeshDraw& draw = draws[e.di];
+					const NvcMeshLod& lod = meshes[draw.meshIndex].lods[e.lod];
+					uint32_t taskGroups = (lod.meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE;
+					if (uint64_t(dci) + taskGroups <= wglimit) // :129 drop on overflow, counter still advances
+						for (uint32_t i = 0; i < taskGroups; ++i)
+						{
+							NvcMeshTaskCommand& c = out[dci + i];
+							c.drawId = e.di;
+							c.taskOffset = lod.meshletOffset + i * NVC_TASK_WGSIZE;
+							c.taskCount = std::min(NVC_TASK_WGSIZE, lod.meshletCount - i * NVC_TASK_WGSIZE);
+							c.lateDrawVisibility = e.dv;
+							c.meshletVisibilityOffset = draw.meshletVisibilityOffset + i * NVC_TASK_WGSIZE;
+						}
+					dci += taskGroups;
+				}
 			}
+		});
 
 		// tasksubmit.comp.glsl:27-47
 		uint32_t clamped = std::min(count, wglimit);
@@ -516,19 +615,24 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 	else
 	{
 		NvcMeshDrawCommand* out = static_cast<NvcMeshDrawCommand*>(commands);
-		for (auto& part : parts)
-			for (const Emit& e : part)
+		parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+			for (uint32_t t = pb; t < pe; ++t)
 			{
-				const NvcMesh& mesh = meshes[draws[e.di].meshIndex];
-				const NvcMeshLod& lod = mesh.lods[e.lod];
-				NvcMeshDrawCommand& c = out[count++]; // :143-150
-				c.drawId = e.di;
-				c.indexCount = lod.indexCount;
-				c.instanceCount = 1;
-				c.firstIndex = lod.indexOffset;
-				c.vertexOffset = mesh.vertexOffset;
-				c.firstInstance = 0;
+				uint32_t dci = part_base[t];
+				for (const Emit& e : parts[t])
+				{
+					const NvcMesh& mesh = meshes[draws[e.di].meshIndex];
+					const NvcMeshLod& lod = mesh.lods[e.lod];
+					NvcMeshDrawCommand& c = out[dci++]; // :143-150
+					c.drawId = e.di;
+					c.indexCount = lod.indexCount;
+					c.instanceCount = 1;
+					c.firstIndex = lod.indexOffset;
+					c.vertexOffset = mesh.vertexOffset;
+					c.firstInstance = 0;
+				}
 			}
+		});
 		command_count4[0] = count;
 		command_count4[1] = command_count4[2] = command_count4[3] = 0;
 	}
@@ -555,14 +659,25 @@ int orc_clustercull(const NvcCullData* cull, int late, const NvcMeshTaskCommand*
 	std::vector<std::vector<uint32_t>> parts(static_cast<size_t>(nt));
 	parallelRanges(ncmd, nt, [&](int t, uint32_t b, uint32_t e) { clusterRange(cd, late != 0, task_commands, draws, meshlets, meshlet_visibility, hiz ? &hv : nullptr, b, e, parts[size_t(t)]); });
 
-	uint32_t count = 0; // vkCmdFillBuffer(ccb, 0, 4, 0) niagara.cpp:1586
-	for (auto& part : parts)
-		for (uint32_t ci : part)
+	// clusterCount starts at 0 (vkCmdFillBuffer(ccb, 0, 4, 0) niagara.cpp:1586); index = position in ascending
+	// (commandId, mgi) order (:135 atomicAdd), entries past CLUSTER_LIMIT are dropped (:137)
+	const size_t np = parts.size();
+	std::vector<uint64_t> part_base(np + 1, 0);
+	for (size_t t = 0; t < np; ++t)
+		part_base[t + 1] = part_base[t] + parts[t].size();
+	const uint32_t count = uint32_t(part_base[np]);
+	parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+		for (uint32_t t = pb; t < pe; ++t)
 		{
-			uint32_t index = count++; // :135 atomicAdd
-			if (index < climit)       // :137
-				cluster_indices[index] = ci;
+			uint64_t index = part_base[t];
+			for (uint32_t ci : parts[t])
+			{
+				if (index < climit)
+					cluster_indices[index] = ci;
+				++index;
+			}
 		}
+	});
 
 	// clustersubmit.comp.glsl:25-45
 	uint32_t clamped = std::min(count, climit);

@@ -19,11 +19,11 @@ def _torch():
     return torch
 
 
-def _paths(s, **kw):
+def _paths(s, hiz_stage_texels=None, **kw):
     from niagara_b200.path import VisibilityPath
 
     torch = _torch()
-    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, **kw)
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, hiz_stage_texels=hiz_stage_texels, **kw)
     o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8, **kw)
     g.set_visibility_bits(s.visibility_bits)
     o.set_visibility_bits(s.visibility_bits)
@@ -119,6 +119,17 @@ def test_moving_camera_multi_frame(golden_dir):
         host.make_camera((-20, 40, 10), host.quat_from_axis_angle((1, 0.3, 0), -0.7)),
     ]
     _run_frames(s, frames=5, cameras=cams)
+
+
+@pytest.mark.parametrize("texels", [6144, 11264, 87, 5])
+def test_tma_staged_hiz(golden_dir, texels):
+    """coarse Hi-Z mips staged into shared memory by one TMA bulk copy per CTA (nvc_set_hiz_staging): same results.
+    Close-up draws so that many lookups land in the staged mips."""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 30000, screen=(1920, 1080))
+    s.draws["position"][:, 2] = -np.abs(s.draws["position"][:, 2]) * 0.1 - 3
+    s.draws["position"][:, :2] *= 0.03
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((1, -0.5, 2), host.quat_from_axis_angle((0, 1, 0), 0.2))]
+    _run_frames(s, frames=3, cameras=cams, hiz_stage_texels=texels)
 
 
 def test_draw_path_without_mesh_shading(golden_dir):
