@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-draws", type=int, default=1_000_000, help="draws in the bounded CPU-baseline sample (default: the whole C4 scene, one frame ~ 10-60 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the NCCL allgather of the visible command slabs")
+    ap.add_argument("--gather", default="ce", choices=["ce", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), nccl = ncclAllGather, none = skip")
     return ap.parse_args()
 
 
@@ -133,7 +133,7 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(args, scene, threads):
+def cpu_baseline(args, scene, threads, repeats=5):
     """The CPU restatement (oracle/, `kind: port` — the reference has no CPU cull path) on a bounded sample:
     the first `cpu_sample_draws` draws of the same scene, one steady-state frame, all host threads."""
     import oracle_lib
@@ -147,23 +147,39 @@ def cpu_baseline(args, scene, threads):
     o = oracle_lib.OraclePath(scene.meshes, scene.meshlets, draws, *scene.screen, threads=threads, cmd_capacity=max(64, (n * 2 + 63) // 64 * 64))
     o.set_visibility_bits(bits)
     o.frame(cd, scene.depth, cluster_backface=True)  # warm-up frame: establishes dvb / mvb
-    tested = 0
-    t0 = time.perf_counter()
-    # identical pass order; count the meshlets the two cluster passes test
-    o.cull(cd, late=False)
-    tested += int(o.read_task_commands(int(o.dccb[1]) * 64)["taskCount"].sum())
-    o.render_clusters(cd, late=False, cluster_backface=True)
-    o.pyramid(scene.depth)
-    o.cull(cd, late=True)
-    tested += int(o.read_task_commands(int(o.dccb[1]) * 64)["taskCount"].sum())
-    o.render_clusters(cd, late=True, cluster_backface=True)
-    dt = time.perf_counter() - t0
+
+    def one_frame():
+        tested = 0
+        t0 = time.perf_counter()
+        # identical pass order; count the meshlets the two cluster passes test
+        o.cull(cd, late=False)
+        ncmd_e = int(o.dccb[1]) * 64
+        o.render_clusters(cd, late=False, cluster_backface=True)
+        o.pyramid(scene.depth)
+        o.cull(cd, late=True)
+        ncmd_l = int(o.dccb[1]) * 64
+        o.render_clusters(cd, late=True, cluster_backface=True)
+        dt = time.perf_counter() - t0
+        # static scene: the late command list is also what the early pass of the next frame sees
+        tested = 2 * int(o.read_task_commands(ncmd_l)["taskCount"].sum()) if ncmd_e == ncmd_l else None
+        return dt, tested
+
+    # best of >= `repeats` steady-state frames (best of >= 5 after warm-up), bounded to ~20 s
+    best, tested, frames, t_begin = None, 0, 0, time.perf_counter()
+    while frames < repeats or (frames < 5 and time.perf_counter() - t_begin < 20.0):
+        dt, n_tested = one_frame()
+        frames += 1
+        if n_tested is None:  # state still converging (first frames): count explicitly
+            n_tested = tested
+        tested = n_tested
+        best = dt if best is None else min(best, dt)
+    dt = best
     return {
         "value": tested / dt,
         "unit": "meshlets/s",
         "cores": threads,
         "kind": "port",
-        "sample": "one steady-state frame over the first %d draws (%d meshlet tests, %dx%d depth pyramid) of the same scene, %.2f s" % (n, tested, scene.screen[0], scene.screen[1], dt),
+        "sample": "best of %d steady-state frames over the first %d draws (%d meshlet tests per frame, %dx%d depth pyramid) of the same scene, %.3f s per frame" % (frames, n, tested, scene.screen[0], scene.screen[1], dt),
         "draws_per_s": 2 * n / dt,
         "seconds": dt,
     }
@@ -185,7 +201,7 @@ def run_reference(args):
     res = None
     t_steps = []
     for i in range(args.warmup + args.steps):
-        r = cpu_baseline(sample_args, scene, threads)
+        r = cpu_baseline(sample_args, scene, threads, repeats=1)
         if i >= args.warmup:
             t_steps.append(r)
         res = r
@@ -247,10 +263,13 @@ def main():
     depth = depth_host.to(dev)
     lib = path.lib
 
-    # ---- multi-GPU: one NCCL allgather of the per-rank visible command slabs + counts ----
-    gather = world > 1 and not args.no_gather
+    # ---- multi-GPU: all-gather of the per-rank visible command slabs + counters ----
+    gather = args.gather if world > 1 else "none"
     slab_cmds = (D * max(1, (args.meshlets_per_draw + 63) // 64) + 63) // 64 * 64 if args.workload == "C4" else 0
-    if gather and slab_cmds:
+    if not slab_cmds:
+        gather = "none"
+    slab_bytes = slab_cmds * layout.MESHTASKCOMMAND_DTYPE.itemsize
+    if gather == "nccl":
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = (ctypes.c_ubyte * 128)()
@@ -260,12 +279,18 @@ def main():
         dist.broadcast(uid, 0)
         uid_host = (ctypes.c_ubyte * 128)(*uid.cpu().tolist())
         check(lib.nvc_nccl_init(path.ctx, uid_host, rank, world), path.ctx, "nvc_nccl_init")
-        slab_bytes = slab_cmds * layout.MESHTASKCOMMAND_DTYPE.itemsize
         gathered = torch.zeros(world * slab_bytes, dtype=torch.uint8, device=dev)
         gathered_counts = torch.zeros(world * 4, dtype=torch.int32, device=dev)
         comm_stream = torch.cuda.Stream(dev)
-    else:
-        gather = False
+    elif gather == "ce":
+        ticket = (ctypes.c_ubyte * 192)()
+        check(lib.nvc_gather_create(path.ctx, slab_bytes, rank, world, ticket), path.ctx, "nvc_gather_create")
+        mine = torch.tensor(list(ticket), dtype=torch.uint8, device=dev)
+        everyone = torch.zeros(world * 192, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine)
+        tickets = (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())
+        check(lib.nvc_gather_connect(path.ctx, tickets), path.ctx, "nvc_gather_connect")
+        dist.barrier()
 
     names = ["drawcull_early", "clustercull_early", "pyramid", "drawcull_late", "clustercull_late"]
 
@@ -283,9 +308,11 @@ def main():
         mark(3)
         path.cull(cd, late=True)
         mark(4)
-        if gather:
-            # the late command slab is final once drawcull(late) is done: gather it on a side stream while the
-            # late cluster pass runs
+        if gather == "ce":
+            # the late command slab is final once drawcull(late) is done: push it to every peer with the copy engines
+            # while the late cluster pass runs on the SMs
+            check(lib.nvc_gather_push(path.ctx, path._stream(), ctypes.c_void_p(path.dcb.data_ptr()), ctypes.c_void_p(path.dccb.data_ptr())), path.ctx, "nvc_gather_push")
+        elif gather == "nccl":
             done = torch.cuda.Event()
             done.record()
             comm_stream.wait_event(done)
@@ -296,7 +323,9 @@ def main():
             )
         path.render_clusters(cd, late=True, cluster_backface=True)
         mark(5)
-        if gather:
+        if gather == "ce":
+            check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
+        elif gather == "nccl":
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     def sync_all():
@@ -446,7 +475,7 @@ def main():
             "data": "synthetic",
             "config": {
                 "workload": "%s: %s; per GPU" % (scene.name, scene.note),
-                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit (5 launches)%s" % ("; + NCCL allgather of the late MeshTaskCommand slabs+counts overlapped with the late cluster pass" if gather else ""),
+                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit (5 launches)%s" % ({"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), overlapped with the late cluster pass", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a side stream", "none": ""}[gather]),
                 "counting": "value = meshlet instances TESTED by the two cluster passes per second (early %d + late %d per step per GPU); draws_per_s likewise (early %d + late %d)" % (tested_early, tested_late, early_reached, D),
                 "l2": "inputs larger than L2 (Meshlet[] %d MB + MeshDraw[] %d MB + Mesh[] %d MB + depth %d MB per step vs 126 MB L2), no flush" % (scene.meshlets.nbytes >> 20, scene.draws.nbytes >> 20, scene.meshes.nbytes >> 20, scene.depth.nbytes >> 20),
                 "cluster_backface": 1,
@@ -470,7 +499,7 @@ def main():
                 "meshlets_per_s_kernel": M / (k_ms * 1e-3),
             },
             "clocks": clocks,
-            "gpu_launches": 5 * K,
+            "gpu_launches": (5 + (2 if gather == "ce" else 0)) * K,
         }
         if e2e:
             line["e2e"] = e2e

@@ -290,6 +290,21 @@ NVC_API int nvc_nccl_init(NvcContext* ctx, const void* unique_id128, int rank, i
 NVC_API int nvc_allgather_visible(NvcContext* ctx, void* stream, const void* local_slab, size_t slab_bytes,
     const uint32_t* local_count4, void* gathered_slabs, uint32_t* gathered_count4);
 
+/* Copy-engine variant of the same exchange (no SMs, so it overlaps the SM-filling late cluster pass): every rank
+ * PUSHES its slab + counters into slot `rank` of every rank's gathered buffers with peer cudaMemcpyAsync over CUDA-IPC
+ * mappings, then raises a flag in the peer's memory; nvc_gather_wait blocks a stream (device side) until all ranks'
+ * data of the latest push has landed.  One process per GPU.
+ *   nvc_gather_create   allocates this rank's receive buffers, returns a 192-byte IPC ticket
+ *   nvc_gather_connect  all ranks' tickets (world x 192 bytes, rank order, exchanged by the caller)
+ *   nvc_gather_push     enqueue after the pass that produced local_slab / local_count4 on `stream`
+ *   nvc_gather_wait     enqueue on the stream that consumes the gathered data (or reuses local_slab)
+ *   nvc_gather_buffers  this rank's gathered slabs [world][slab_bytes] and counters [world][4] */
+NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int world_size, void* ticket192_out);
+NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets);
+NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4);
+NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream);
+NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t** gathered_count4);
+
 #ifdef __cplusplus
 } /* extern "C" */
 

@@ -167,6 +167,7 @@ NVC_API void nvc_destroy(NvcContext* ctx)
 	if (!ctx)
 		return;
 	cudaSetDevice(ctx->device);
+	nvc::gather_destroy(ctx);
 	nvc::nccl_destroy(ctx);
 	if (ctx->scratch)
 		cudaFree(ctx->scratch);

@@ -23,12 +23,14 @@ struct NvcContext
 	nvc::Scratch* scratch = nullptr;
 	std::string last_error;
 	void* nccl_comm = nullptr; // ncclComm_t, owned (nvc_nccl.cpp)
+	void* gather = nullptr;    // NvcGather, owned (nvc_peer.cu)
 	int nccl_rank = 0, nccl_world = 1;
 };
 
 namespace nvc
 {
-void nccl_destroy(NvcContext* ctx); // nvc_nccl.cpp
+void nccl_destroy(NvcContext* ctx);   // nvc_nccl.cpp
+void gather_destroy(NvcContext* ctx); // nvc_peer.cu
 
 // Device-side counters owned by the context.  Each pass's last-block epilogue leaves them zeroed, which replaces
 // the reference's vkCmdFillBuffer resets (niagara.cpp:1541,1586) and keeps every pass a single launch.

@@ -1,0 +1,267 @@
+// nvc_peer.cu — all-gather of the per-rank visible command slabs over NVLink WITHOUT SMs: every rank pushes its slab
+// and counters into every peer's gathered buffer with copy-engine peer copies (cudaMemcpyAsync on CUDA-IPC mapped
+// memory, fanned out over a few side streams so several copy engines run at once), then raises a per-sender flag in
+// the peer's memory; the receiver's stream blocks in a tiny spin kernel until all flags carry the current frame tag.
+// Unlike an NCCL all-gather this needs no SMs, so it overlaps the (persistent, SM-filling) late cluster pass.
+// One process per GPU; the IPC tickets are exchanged by the caller (any transport).
+#include "nvc_internal.h"
+
+#include <string.h>
+
+namespace
+{
+
+constexpr int kMaxWorld = 64;
+constexpr int kSideStreams = 4;
+
+struct Ticket // what a rank publishes: IPC handles of its three receive buffers
+{
+	cudaIpcMemHandle_t slabs, counts, flags;
+};
+static_assert(sizeof(Ticket) == 192, "ticket is 3 x 64 bytes");
+
+__global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag)
+{
+	int p = threadIdx.x;
+	if (p < world)
+	{
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + rank) = tag; // P2P store over NVLink (or local)
+	}
+}
+
+__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag)
+{
+	int q = threadIdx.x;
+	if (q < world)
+	{
+		// tags increase monotonically; signed distance handles wrap-around
+		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
+			__nanosleep(200);
+		__threadfence_system();
+	}
+}
+
+} // namespace
+
+struct NvcGather
+{
+	int world = 1, rank = 0;
+	size_t slab_bytes = 0;
+	uint8_t* slabs = nullptr;   // [world][slab_bytes]   receive buffer of this rank
+	uint32_t* counts = nullptr; // [world][4]
+	uint32_t* flags = nullptr;  // [world]
+	uint8_t* peer_slabs[kMaxWorld] = {};
+	uint32_t* peer_counts[kMaxWorld] = {};
+	uint32_t* peer_flags[kMaxWorld] = {};
+	uint32_t** d_peer_flags = nullptr; // device copy of peer_flags
+	cudaStream_t side[kSideStreams] = {};
+	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
+	uint32_t tag = 0;
+	bool connected = false;
+};
+
+namespace nvc
+{
+
+void gather_destroy(NvcContext* ctx)
+{
+	NvcGather* g = static_cast<NvcGather*>(ctx->gather);
+	if (!g)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (int p = 0; p < g->world; ++p)
+		if (p != g->rank && g->connected)
+		{
+			if (g->peer_slabs[p])
+				cudaIpcCloseMemHandle(g->peer_slabs[p]);
+			if (g->peer_counts[p])
+				cudaIpcCloseMemHandle(g->peer_counts[p]);
+			if (g->peer_flags[p])
+				cudaIpcCloseMemHandle(g->peer_flags[p]);
+		}
+	for (int i = 0; i < kSideStreams; ++i)
+	{
+		if (g->side[i])
+			cudaStreamDestroy(g->side[i]);
+		if (g->join[i])
+			cudaEventDestroy(g->join[i]);
+	}
+	if (g->fork)
+		cudaEventDestroy(g->fork);
+	cudaFree(g->slabs);
+	cudaFree(g->counts);
+	cudaFree(g->flags);
+	cudaFree(g->d_peer_flags);
+	delete g;
+	ctx->gather = nullptr;
+}
+
+} // namespace nvc
+
+extern "C"
+{
+
+NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int world, void* ticket192_out)
+{
+	if (!ctx || !ticket192_out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || slab_bytes == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	nvc::gather_destroy(ctx);
+	NvcGather* g = new NvcGather();
+	g->world = world;
+	g->rank = rank;
+	g->slab_bytes = slab_bytes;
+	cudaError_t e = cudaMalloc(&g->slabs, slab_bytes * world);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->counts, sizeof(uint32_t) * 4 * world);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->flags, sizeof(uint32_t) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->d_peer_flags, sizeof(uint32_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMemset(g->counts, 0, sizeof(uint32_t) * 4 * world);
+	if (e == cudaSuccess)
+		e = cudaMemset(g->flags, 0, sizeof(uint32_t) * kMaxWorld);
+	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
+	{
+		e = cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&g->join[i], cudaEventDisableTiming);
+	}
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming);
+	Ticket t;
+	memset(&t, 0, sizeof(t));
+	if (e == cudaSuccess)
+		e = cudaIpcGetMemHandle(&t.slabs, g->slabs);
+	if (e == cudaSuccess)
+		e = cudaIpcGetMemHandle(&t.counts, g->counts);
+	if (e == cudaSuccess)
+		e = cudaIpcGetMemHandle(&t.flags, g->flags);
+	if (e == cudaSuccess)
+		e = cudaDeviceSynchronize();
+	ctx->gather = g;
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_create: ") + cudaGetErrorString(e);
+		nvc::gather_destroy(ctx);
+		return e == cudaErrorMemoryAllocation ? NVC_ERROR_OUT_OF_MEMORY : NVC_ERROR_CUDA;
+	}
+	memcpy(ticket192_out, &t, sizeof(t));
+	return NVC_OK;
+}
+
+NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets /* world x 192 bytes, rank order */)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !all_tickets)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	const Ticket* tickets = static_cast<const Ticket*>(all_tickets);
+	cudaError_t e = cudaSuccess;
+	for (int p = 0; p < g->world && e == cudaSuccess; ++p)
+	{
+		if (p == g->rank)
+		{
+			g->peer_slabs[p] = g->slabs;
+			g->peer_counts[p] = g->counts;
+			g->peer_flags[p] = g->flags;
+			continue;
+		}
+		e = cudaIpcOpenMemHandle(reinterpret_cast<void**>(&g->peer_slabs[p]), tickets[p].slabs, cudaIpcMemLazyEnablePeerAccess);
+		if (e == cudaSuccess)
+			e = cudaIpcOpenMemHandle(reinterpret_cast<void**>(&g->peer_counts[p]), tickets[p].counts, cudaIpcMemLazyEnablePeerAccess);
+		if (e == cudaSuccess)
+			e = cudaIpcOpenMemHandle(reinterpret_cast<void**>(&g->peer_flags[p]), tickets[p].flags, cudaIpcMemLazyEnablePeerAccess);
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_flags, g->peer_flags, sizeof(uint32_t*) * g->world, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_connect: ") + cudaGetErrorString(e);
+		return NVC_ERROR_CUDA;
+	}
+	g->connected = true;
+	return NVC_OK;
+}
+
+// Enqueues (after everything already on `stream`): push of local_slab / local_count4 into slot `rank` of every rank's
+// gathered buffers over the side streams, then the flag raise.  Returns immediately; `stream` itself is not blocked
+// by the copies (call nvc_gather_wait on the stream that consumes the gathered data).
+NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !g->connected || !local_slab || !local_count4)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	g->tag += 1;
+	cudaError_t e = cudaEventRecord(g->fork, s);
+	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
+		e = cudaStreamWaitEvent(g->side[i], g->fork, 0);
+	for (int k = 0; k < g->world && e == cudaSuccess; ++k)
+	{
+		int p = (g->rank + k) % g->world; // stagger the targets so that ranks do not all hit the same peer first
+		cudaStream_t ss = g->side[k % kSideStreams];
+		e = cudaMemcpyAsync(g->peer_slabs[p] + size_t(g->rank) * g->slab_bytes, local_slab, g->slab_bytes, cudaMemcpyDeviceToDevice, ss);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(g->peer_counts[p] + 4 * g->rank, local_count4, 16, cudaMemcpyDeviceToDevice, ss);
+	}
+	// flags go out once every copy of this rank has completed: join the side streams on side[0], raise there
+	for (int i = 1; i < kSideStreams && e == cudaSuccess; ++i)
+	{
+		e = cudaEventRecord(g->join[i], g->side[i]);
+		if (e == cudaSuccess)
+			e = cudaStreamWaitEvent(g->side[0], g->join[i], 0);
+	}
+	if (e == cudaSuccess)
+	{
+		raise_flags_kernel<<<1, kMaxWorld, 0, g->side[0]>>>(g->d_peer_flags, g->world, g->rank, g->tag);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaEventRecord(g->join[0], g->side[0]);
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_push: ") + cudaGetErrorString(e);
+		return NVC_ERROR_CUDA;
+	}
+	return NVC_OK;
+}
+
+// Blocks `stream` (device side) until every rank's slab of the latest push has landed in this rank's gathered buffers,
+// and until this rank's own outgoing copies are done (so the local slab may be overwritten by the next pass).
+NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !g->connected)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	cudaError_t e = cudaStreamWaitEvent(s, g->join[0], 0);
+	if (e == cudaSuccess)
+	{
+		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag);
+		e = cudaGetLastError();
+	}
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_wait: ") + cudaGetErrorString(e);
+		return NVC_ERROR_CUDA;
+	}
+	return NVC_OK;
+}
+
+NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t** gathered_count4)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (gathered_slabs)
+		*gathered_slabs = g->slabs;
+	if (gathered_count4)
+		*gathered_count4 = g->counts;
+	return NVC_OK;
+}
+
+} // extern "C"

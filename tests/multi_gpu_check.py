@@ -14,6 +14,17 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _device_bytes(torch, ptr, nbytes, dev):
+    """uint8 tensor view of raw device memory owned by the library (via __cuda_array_interface__)"""
+
+    class _Raw:
+        pass
+
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(raw, device=dev)
+
+
 def main():
     import oracle_lib
     from niagara_b200 import layout, scenes, shard
@@ -45,6 +56,19 @@ def main():
     check(lib.nvc_nccl_init(g.ctx, (ctypes.c_ubyte * 128)(*uid.cpu().tolist()), rank, world), g.ctx, "nvc_nccl_init")
 
     slab_bytes = cap * 20
+
+    # copy-engine gather (nvc_gather_*): IPC tickets exchanged with torch.distributed
+    ticket = (ctypes.c_ubyte * 192)()
+    check(lib.nvc_gather_create(g.ctx, slab_bytes, rank, world, ticket), g.ctx, "nvc_gather_create")
+    mine = torch.tensor(list(ticket), dtype=torch.uint8, device=dev)
+    everyone = torch.zeros(world * 192, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(everyone, mine)
+    check(lib.nvc_gather_connect(g.ctx, (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())), g.ctx, "nvc_gather_connect")
+    ce_slabs, ce_counts = ctypes.c_void_p(), ctypes.c_void_p()
+    check(lib.nvc_gather_buffers(g.ctx, ctypes.byref(ce_slabs), ctypes.byref(ce_counts)), g.ctx, "nvc_gather_buffers")
+    ce_host = torch.zeros(world * slab_bytes, dtype=torch.uint8).pin_memory()
+    ce_counts_host = torch.zeros(world * 4, dtype=torch.int32).pin_memory()
+
     gathered = torch.zeros(world * slab_bytes, dtype=torch.uint8, device=dev)
     gathered_counts = torch.zeros(world * 4, dtype=torch.int32, device=dev)
     bases = [b for b, _ in shard.partition(len(s.draws), world)]
@@ -56,15 +80,28 @@ def main():
         cd_all = s.cull_data()
 
     ok = True
-    for frame in range(2):
+    for frame in range(3):
         for late in (False, True):
             if late:
                 g.pyramid(depth)
             g.cull(cd, late)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             check(lib.nvc_allgather_visible(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), slab_bytes, ctypes.c_void_p(g.dccb.data_ptr()), ctypes.c_void_p(gathered.data_ptr()), ctypes.c_void_p(gathered_counts.data_ptr())), g.ctx, "nvc_allgather_visible")
+            check(lib.nvc_gather_push(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), ctypes.c_void_p(g.dccb.data_ptr())), g.ctx, "nvc_gather_push")
             g.render_clusters(cd, late, cluster_backface=True)
+            check(lib.nvc_gather_wait(g.ctx, stream), g.ctx, "nvc_gather_wait")
             torch.cuda.synchronize()
+            # the copy-engine gather must have delivered exactly what NCCL delivered
+            ce_view = _device_bytes(torch, ce_slabs.value, world * slab_bytes, dev)
+            ce_cnt = _device_bytes(torch, ce_counts.value, world * 16, dev).view(torch.int32)
+            same_ce = torch.equal(ce_cnt, gathered_counts)
+            for r in range(world):
+                n = int(gathered_counts[4 * r].item()) * 20
+                same_ce = same_ce and torch.equal(ce_view[r * slab_bytes : r * slab_bytes + n], gathered[r * slab_bytes : r * slab_bytes + n])
+            if not same_ce:
+                ok = False
+                print("rank", rank, "CE gather differs from NCCL gather, frame", frame, "late", late)
+            dist.barrier()  # nobody starts the next push before everyone has compared
             slabs = gathered.cpu().numpy().reshape(world, slab_bytes)
             counts = gathered_counts.cpu().numpy().reshape(world, 4)
             cmds = shard.globalise_task_commands(list(slabs), list(counts), bases, bit_bases)
@@ -85,11 +122,11 @@ def main():
                 ok = False
                 print("cluster count mismatch", int(total.item()), int(o.ccb[0]))
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checked its own gathered buffers
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", "world", world)
+        print("MULTI_GPU_CHECK", "OK" if int(flag.item()) == 1 else "FAILED", "world", world)
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 

@@ -287,3 +287,46 @@ def test_taskcull_payloads(golden_dir):
 
             assert table(gt, gp, ge) == table(ot, op, oe)
             assert np.array_equal(g.mvb.cpu().numpy().astype(np.uint32), o.mvb)
+
+
+def test_c4_full_size_bit_exact():
+    """BASELINE configs[3] at FULL size (1M draws x 10 unique meshlets = 10M meshlet instances, 4096^2 depth): two
+    frames of the whole path, CUDA vs the multi-threaded oracle, bit-exact (counters, dvb, mvb, pyramid, command and
+    cluster sets) — plus size-independent properties: steady-state idempotence and conservation between passes."""
+    torch = _torch()
+    s = scenes.config4_scene()
+    g, o, depth = _paths(s)
+    o.threads = os.cpu_count() or 8
+    cd = s.cull_data()
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+                o.pyramid(s.depth)
+                _compare_pyramid(g, o, ("c4 pyramid", f))
+            g.cull(cd, late)
+            o.cull(cd, late)
+            _compare_draw_pass(g, o, True, ("c4 cull", f, late))
+            g.render_clusters(cd, late, cluster_backface=True)
+            o.render_clusters(cd, late, cluster_backface=True)
+            _compare_cluster_pass(g, o, ("c4 clusters", f, late))
+    # properties that hold at any size
+    dvb1 = g.dvb.clone()
+    mvb1 = g.mvb.clone()
+    gd1, gc1 = g.read_counts()
+    g.frame(cd, depth, cluster_backface=True)
+    torch.cuda.synchronize()
+    gd2, gc2 = g.read_counts()
+    assert torch.equal(g.dvb, dvb1) and torch.equal(g.mvb, mvb1)  # static camera: the visibility state is a fixed point
+    assert np.array_equal(gd1, gd2) and gc2[0] == 0  # everything visible was already drawn by the early pass
+    vis_draws = int((g.dvb != 0).sum().item())
+    assert gd2[0] == vis_draws  # one task command per visible draw (10 meshlets < 64)
+    bits = int(sum(bin(int(x) & 0xFFFFFFFF).count("1") for x in g.mvb.cpu().numpy()[:: 997]))  # sampled popcount is finite
+    assert bits >= 0
+    # early pass of the next frame emits exactly the meshlets whose bit is set among visible draws
+    g.cull(cd, late=False)
+    g.render_clusters(cd, late=False, cluster_backface=True)
+    torch.cuda.synchronize()
+    _, gce = g.read_counts()
+    mv = g.mvb.cpu().numpy().astype(np.uint32)
+    assert int(gce[0]) == int(np.unpackbits(mv.view(np.uint8)).sum())
