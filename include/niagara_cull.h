@@ -185,6 +185,14 @@ NVC_API const char* nvc_status_string(int status);
 NVC_API const char* nvc_last_error(const NvcContext* ctx);
 NVC_API const char* nvc_version(void);
 
+/* Optional, once per geometry upload (where the reference uploads `mb`, niagara.cpp:1040-1046): builds a context-owned,
+ * read-only cull view of Mesh[] — a 32-byte head per mesh {center, radius, lodCount, lods[0].meshletOffset/Count,
+ * vertexOffset} plus the 8 LOD errors — so that nvc_drawcull touches ONE 32-byte sector per draw for single-LOD / LOD-0
+ * task draws instead of the 3-4 sectors the 208-byte AoS record spreads those fields over.  Used automatically by
+ * nvc_drawcull calls that pass the same `meshes` pointer; results are identical.  The Mesh[] contents must not change
+ * afterwards (call again after re-uploading; meshes = NULL releases the view). */
+NVC_API int nvc_prepare_meshes(NvcContext* ctx, void* stream, const NvcMesh* meshes, uint32_t mesh_count);
+
 /* Tuning: stage the coarse tail of the depth pyramid (top mips, at most `texels` texels, capped at 11264 = 44 KB) into
  * shared memory once per CTA of the late cluster pass with one TMA bulk copy (cp.async.bulk, SASS UBLKCP); lookups
  * whose whole warp samples a staged mip then read shared memory.  0 (default) disables it: on the measured workloads

@@ -171,7 +171,46 @@ NVC_API void nvc_destroy(NvcContext* ctx)
 	nvc::nccl_destroy(ctx);
 	if (ctx->scratch)
 		cudaFree(ctx->scratch);
+	if (ctx->mesh_heads)
+		cudaFree(ctx->mesh_heads);
+	if (ctx->mesh_errors)
+		cudaFree(ctx->mesh_errors);
 	delete ctx;
+}
+
+NVC_API int nvc_prepare_meshes(NvcContext* ctx, void* stream, const NvcMesh* meshes, uint32_t mesh_count)
+{
+	if (!ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	if (ctx->mesh_heads)
+	{
+		cudaDeviceSynchronize();
+		cudaFree(ctx->mesh_heads);
+		cudaFree(ctx->mesh_errors);
+		ctx->mesh_heads = nullptr;
+		ctx->mesh_errors = nullptr;
+		ctx->prepared_meshes = nullptr;
+		ctx->prepared_mesh_count = 0;
+	}
+	if (!meshes || mesh_count == 0)
+		return NVC_OK; // un-prepare
+	cudaError_t e = cudaMalloc(&ctx->mesh_heads, size_t(mesh_count) * sizeof(nvc::MeshCullHead));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&ctx->mesh_errors, size_t(mesh_count) * NVC_MAX_LODS * sizeof(float));
+	if (e == cudaSuccess)
+		e = nvc::launch_pack_meshes(meshes, mesh_count, static_cast<nvc::MeshCullHead*>(ctx->mesh_heads), ctx->mesh_errors, static_cast<cudaStream_t>(stream));
+	if (e != cudaSuccess)
+	{
+		cudaFree(ctx->mesh_heads);
+		cudaFree(ctx->mesh_errors);
+		ctx->mesh_heads = nullptr;
+		ctx->mesh_errors = nullptr;
+		return e == cudaErrorMemoryAllocation ? NVC_ERROR_OUT_OF_MEMORY : cuda_fail(ctx, e, "nvc_prepare_meshes");
+	}
+	ctx->prepared_meshes = meshes;
+	ctx->prepared_mesh_count = mesh_count;
+	return NVC_OK;
 }
 
 NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels)
@@ -203,6 +242,11 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	p.cull = *cull;
 	p.draws = draws;
 	p.meshes = meshes;
+	if (ctx->mesh_heads && ctx->prepared_meshes == meshes)
+	{
+		p.mesh_heads = static_cast<const nvc::MeshCullHead*>(ctx->mesh_heads);
+		p.mesh_errors = ctx->mesh_errors;
+	}
 	p.draw_visibility = draw_visibility;
 	p.commands = commands;
 	p.command_count4 = command_count4;

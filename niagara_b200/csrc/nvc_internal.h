@@ -24,6 +24,11 @@ struct NvcContext
 	std::string last_error;
 	void* nccl_comm = nullptr; // ncclComm_t, owned (nvc_nccl.cpp)
 	void* gather = nullptr;    // NvcGather, owned (nvc_peer.cu)
+	// derived mesh cull view (nvc_prepare_meshes)
+	const void* prepared_meshes = nullptr;
+	uint32_t prepared_mesh_count = 0;
+	void* mesh_heads = nullptr;
+	float* mesh_errors = nullptr;
 	int nccl_rank = 0, nccl_world = 1;
 };
 
@@ -61,11 +66,27 @@ struct HiZDesc
 	uint32_t stage_level, stage_texels;
 };
 
+// Derived, read-only cull view of the reference's 208-byte Mesh records, built once per geometry upload by
+// nvc_prepare_meshes: one 32-byte head per mesh (everything a single-LOD / LOD-0 task draw needs = ONE sector instead
+// of the 3-4 sectors the AoS struct spreads it over) and the 8 LOD errors as a second 32-byte record.
+struct MeshCullHead
+{
+	float center[3];
+	float radius;
+	uint32_t lodCount;
+	uint32_t lod0MeshletOffset;
+	uint32_t lod0MeshletCount;
+	uint32_t vertexOffset;
+};
+static_assert(sizeof(MeshCullHead) == 32, "one sector");
+
 struct DrawCullParams
 {
 	NvcCullData cull;
 	const NvcMeshDraw* draws;
 	const NvcMesh* meshes;
+	const MeshCullHead* mesh_heads; // may be null: read everything from `meshes`
+	const float* mesh_errors;       // [mesh][8], valid when mesh_heads != null
 	uint32_t* draw_visibility;
 	void* commands;
 	uint32_t* command_count4;
@@ -102,6 +123,7 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaS
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream);
+cudaError_t launch_pack_meshes(const NvcMesh* meshes, uint32_t count, MeshCullHead* heads, float* errors, cudaStream_t stream);
 cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late, int* blocks_per_sm_late_staged, uint32_t stage_bytes);
 uint32_t hiz_stage_bytes(const HiZDesc& hiz);
 void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_texels);

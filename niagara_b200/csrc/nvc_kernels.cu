@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	uint32_t units = 0; // commands this thread appends: taskGroups (TASK) or 1
 	uint32_t dv = 0;
 	uint32_t meshIndex = 0, lodIndex = 0, mvOffset = 0;
+	uint32_t meshletOffset = 0, meshletCount = 0; // selected LOD's meshlet range (TASK)
 
 	if (di < cd.drawCount)
 	{
@@ -184,7 +185,13 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 		if (reached)
 		{
 			const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
-			float4 m0 = ldg_f4(mp); // center.xyz, radius
+			const bool packed = p.mesh_heads != nullptr;
+			// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
+			const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + meshIndex) : mp;
+			float4 m0 = ldg_f4(hp); // center.xyz, radius
+			uint4 h1 = make_uint4(0u, 0u, 0u, 0u);
+			if (packed)
+				h1 = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
 
 			f3 mc = { m0.x, m0.y, m0.z };
 			f3 rc = rotate_quat(mc, d1);
@@ -206,16 +213,21 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 					float d = __fsub_rn(length3(center), radius);
 					float distance = d > 0.f ? d : 0.f;
 					float threshold = __fdiv_rn(__fmul_rn(distance, cd.lodTarget), d0.w);
-					uint32_t lodCount = __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
+					uint32_t lodCount = packed ? h1.x : __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
 					lodCount = min(lodCount, NVC_MAX_LODS);
+					const float* errors = packed ? p.mesh_errors + size_t(meshIndex) * NVC_MAX_LODS : nullptr;
 					for (uint32_t i = 1; i < lodCount; ++i)
-						if (__ldg(reinterpret_cast<const float*>(mp + 48 + i * 20 + 16)) < threshold)
+					{
+						float err = packed ? __ldg(errors + i) : __ldg(reinterpret_cast<const float*>(mp + 48 + i * 20 + 16));
+						if (err < threshold)
 							lodIndex = i;
+					}
 				}
 				emit = true;
 				if (TASK)
 				{
-					uint32_t meshletCount = __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 12));
+					meshletCount = (packed && lodIndex == 0) ? h1.z : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 12));
+					meshletOffset = (packed && lodIndex == 0) ? h1.y : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 8));
 					units = (meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
 				}
 				else
@@ -278,7 +290,6 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			// :129 drop on overflow; the counter has already advanced
 			if (staged || uint64_t(dci) + units <= p.task_wglimit)
 			{
-				uint32_t meshletOffset = __ldg(lp + 2), meshletCount = __ldg(lp + 3);
 				uint32_t* out = staged ? s_stage + local * 5u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshTaskCommand*>(p.commands) + dci);
 				for (uint32_t i = 0; i < units; ++i, out += 5)
 				{
@@ -1013,6 +1024,32 @@ __global__ void __launch_bounds__(kPyrBlock, NVC_PYRAMID_MIN_BLOCKS) pyramid_ker
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
+
+__global__ void pack_meshes_kernel(const NvcMesh* __restrict__ meshes, uint32_t count, MeshCullHead* __restrict__ heads, float* __restrict__ errors)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const NvcMesh& m = meshes[i];
+	MeshCullHead h;
+	h.center[0] = m.center[0], h.center[1] = m.center[1], h.center[2] = m.center[2];
+	h.radius = m.radius;
+	h.lodCount = m.lodCount;
+	h.lod0MeshletOffset = m.lods[0].meshletOffset;
+	h.lod0MeshletCount = m.lods[0].meshletCount;
+	h.vertexOffset = m.vertexOffset;
+	heads[i] = h;
+	for (uint32_t l = 0; l < NVC_MAX_LODS; ++l)
+		errors[size_t(i) * NVC_MAX_LODS + l] = m.lods[l].error;
+}
+
+cudaError_t launch_pack_meshes(const NvcMesh* meshes, uint32_t count, MeshCullHead* heads, float* errors, cudaStream_t stream)
+{
+	if (count == 0)
+		return cudaSuccess;
+	pack_meshes_kernel<<<(count + 255) / 256, 256, 0, stream>>>(meshes, count, heads, errors);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
 {

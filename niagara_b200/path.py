@@ -25,7 +25,7 @@ def _round_up(v, m):
 
 
 class VisibilityPath:
-    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, hiz_stage_texels=None):
+    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, hiz_stage_texels=None, prepare_meshes=True):
         """meshes / meshlets / draws: structured numpy arrays (layout.MESH_DTYPE / MESHLET_DTYPE / MESHDRAW_DTYPE) or
         already-resident torch uint8 tensors.  draws must already carry meshletVisibilityOffset
         (host.visibility_offsets)."""
@@ -49,6 +49,9 @@ class VisibilityPath:
         self.mb = self._upload(meshes)
         self.mlb = self._upload(meshlets)
         self.db = self._upload(draws)
+        if prepare_meshes:  # derived cull view of Mesh[] (once per geometry upload)
+            mesh_count = self.mb.numel() // layout.MESH_DTYPE.itemsize
+            check(self.lib.nvc_prepare_meshes(self.ctx, self._stream(), _ptr(self.mb), mesh_count), self.ctx, "nvc_prepare_meshes")
 
         # niagara.cpp:1062-1090
         self.dvb = torch.zeros(max(1, self.draw_count), dtype=torch.int32, device=self.device)

@@ -19,11 +19,11 @@ def _torch():
     return torch
 
 
-def _paths(s, hiz_stage_texels=None, **kw):
+def _paths(s, hiz_stage_texels=None, prepare_meshes=True, **kw):
     from niagara_b200.path import VisibilityPath
 
     torch = _torch()
-    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, hiz_stage_texels=hiz_stage_texels, **kw)
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, hiz_stage_texels=hiz_stage_texels, prepare_meshes=prepare_meshes, **kw)
     o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8, **kw)
     g.set_visibility_bits(s.visibility_bits)
     o.set_visibility_bits(s.visibility_bits)
@@ -130,6 +130,14 @@ def test_tma_staged_hiz(golden_dir, texels):
     s.draws["position"][:, :2] *= 0.03
     cams = [host.make_camera((0, 0, 0)), host.make_camera((1, -0.5, 2), host.quat_from_axis_angle((0, 1, 0), 0.2))]
     _run_frames(s, frames=3, cameras=cams, hiz_stage_texels=texels)
+
+
+@pytest.mark.parametrize("mesh_shading", [True, False])
+def test_without_prepared_mesh_view(golden_dir, mesh_shading):
+    """nvc_prepare_meshes is optional: the plain AoS Mesh[] path must give the same results (task and draw commands)"""
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 30000, screen=(1024, 768))
+    toggles = None if mesh_shading else dict(mesh_shading=False, cluster_occlusion=False)
+    _run_frames(s, frames=2, toggles=toggles, mesh_shading=mesh_shading, prepare_meshes=False)
 
 
 def test_draw_path_without_mesh_shading(golden_dir):
