@@ -277,6 +277,8 @@ static int fill_cluster_params(NvcContext* ctx, const NvcCullData* cull, int lat
 	p.meshlet_visibility = meshlet_visibility;
 	p.scratch = ctx->scratch;
 	p.cluster_limit = ctx->limits.cluster_limit;
+	p.one = 1.0f;
+	p.neg_one = -1.0f;
 	bool need_hiz = late && cull->clusterOcclusionEnabled == 1;
 	if (!fill_hiz(hiz, p.hiz) && need_hiz)
 		return NVC_ERROR_INVALID_ARGUMENT;

@@ -108,6 +108,7 @@ struct ClusterParams
 	Scratch* scratch;
 	HiZDesc hiz;
 	uint32_t cluster_limit;
+	float one, neg_one; // 1.0f / -1.0f as run-time values: see nvc_math2.cuh (keeps ptxas from contracting packed adds)
 };
 
 struct PyramidParams

@@ -9,6 +9,7 @@
 // Compiled with -fmad=false; see nvc_math.cuh for the arithmetic contract.
 #include "nvc_internal.h"
 #include "nvc_math.cuh"
+#include "nvc_math2.cuh"
 #include "nvc_tma.cuh"
 
 #include <cuda_runtime.h>
@@ -58,8 +59,11 @@ typedef NvcCullData ClusterConsts;
 // Tuning knobs (A/B measured on B200, profiles/r1_variants.md): software prefetch of the next chunk's loads did not pay
 // (the extra registers cost more occupancy than the overlap wins); capping registers at 40 so that 6 CTAs (48 warps)
 // are resident per SM did.
-#ifndef NVC_PREFETCH
-#define NVC_PREFETCH 0
+// NVC_PACKED=1 evaluates two chunks per iteration with Blackwell's packed FP32x2 instructions (FMUL2 / FFMA2,
+// nvc_math2.cuh): bit-exact (38/38 parity tests) but not faster on B200 — the packed forms appear to occupy the FMA
+// pipe for two cycles, so no issue slots are won (profiles/r1_variants.md).  Kept as a build-time variant.
+#ifndef NVC_PACKED
+#define NVC_PACKED 0
 #endif
 #ifndef NVC_CLUSTER_MIN_BLOCKS
 #define NVC_CLUSTER_MIN_BLOCKS 6
@@ -480,6 +484,134 @@ __device__ __forceinline__ void meshlet_compute(const ClusterParams& p, const Cl
 	visible = alive;
 }
 
+// ---- two items per lane, packed FP32x2 arithmetic (nvc_math2.cuh) --------------------------------------------------
+
+// texel footprint of one item from its (already packed-computed) unnormalised coordinates
+__device__ __forceinline__ float sample_min_xy(const float* texels, uint32_t offset, uint32_t w, uint32_t h, float x, float y, float fracx, float fracy)
+{
+	float fx0 = floorf(x), fy0 = floorf(y);
+	float wmax = (float)(w - 1), hmax = (float)(h - 1);
+	uint32_t x0 = (uint32_t)fminf(fmaxf(fx0, 0.f), wmax);
+	uint32_t y0 = (uint32_t)fminf(fmaxf(fy0, 0.f), hmax);
+	uint32_t x1 = (uint32_t)fminf(fmaxf(__fadd_rn(fx0, 1.f), 0.f), wmax);
+	uint32_t y1 = (uint32_t)fminf(fmaxf(__fadd_rn(fy0, 1.f), 0.f), hmax);
+	const float inf = __int_as_float(0x7f800000);
+	uint32_t r0 = offset + y0 * w, r1 = offset + y1 * w;
+	float t00 = __ldg(texels + (r0 + x0));
+	float t01 = __ldg(texels + (r0 + x1));
+	float t10 = __ldg(texels + (r1 + x0));
+	float t11 = __ldg(texels + (r1 + x1));
+	bool usex1 = fracx != 0.f, usey1 = fracy != 0.f;
+	t01 = usex1 ? t01 : inf;
+	t10 = usey1 ? t10 : inf;
+	t11 = (usex1 && usey1) ? t11 : inf;
+	return fminf(fminf(t00, t01), fminf(t10, t11));
+}
+
+// occlusion_visible() for two items
+template <typename CD>
+__device__ __forceinline__ void occlusion_visible2(const Pk& k, const CD& cd, const HiZDesc& hiz, f3x2 center, f2 radius, bool& va, bool& vb)
+{
+	aabb2 aabb;
+	bool oka, okb;
+	project_sphere2(k, center, radius, cd.znear, cd.P00, cd.P11, aabb, oka, okb);
+	int la, lb;
+	occlusion_mip2(k, aabb, cd.pyramidWidth, cd.pyramidHeight, int(hiz.levels) - 1, la, lb);
+	uint32_t wa = max(1u, hiz.width >> la), ha = max(1u, hiz.height >> la);
+	uint32_t wb = max(1u, hiz.width >> lb), hb = max(1u, hiz.height >> lb);
+	const f2 half = bc(0.5f);
+	f2 u = mul2(add2(k, aabb.x, aabb.z), half);
+	f2 v = mul2(add2(k, aabb.y, aabb.w), half);
+	// x = u * w - 0.5 (min_footprint), fract = x - floor(x)
+	f2 x = sub2(k, mul2(u, pk((float)wa, (float)wb)), half);
+	f2 y = sub2(k, mul2(v, pk((float)ha, (float)hb)), half);
+	f2 fx = sub2(k, x, pk(floorf(lo(x)), floorf(hi(x))));
+	f2 fy = sub2(k, y, pk(floorf(lo(y)), floorf(hi(y))));
+	float da = sample_min_xy(hiz.texels, hiz.level_offset[la], wa, ha, lo(x), lo(y), lo(fx), lo(fy));
+	float db = sample_min_xy(hiz.texels, hiz.level_offset[lb], wb, hb, hi(x), hi(y), hi(fx), hi(fy));
+	f2 den = sub2(k, center.z, radius);
+	float dsa = __fdiv_rn(cd.znear, lo(den)), dsb = __fdiv_rn(cd.znear, hi(den));
+	va = !oka || dsa > da;
+	vb = !okb || dsb > db;
+}
+
+// meshlet_compute() for the items of two chunks at once (A = chunk `base`, B = chunk `base + 32`)
+template <bool LATE>
+__device__ __forceinline__ void meshlet_compute2(const ClusterParams& p, const ClusterConsts& cc, const Pk& k, const ItemRef& ra, ItemData& da, const ItemRef& rb, ItemData& db,
+    bool& visible_a, bool& skip_a, bool& oldbit_a, bool& visible_b, bool& skip_b, bool& oldbit_b)
+{
+	const NvcCullData& cd = p.cull;
+	bool alive_a = ra.active, alive_b = rb.active;
+	skip_a = skip_b = false;
+	oldbit_a = oldbit_b = false;
+
+	if (cd.clusterOcclusionEnabled == 1 && cd.postPass == 0) // :86
+	{
+		bool bit_a = (da.word >> (ra.mvi & 31u)) & 1u, bit_b = (db.word >> (rb.mvi & 31u)) & 1u;
+		oldbit_a = bit_a;
+		oldbit_b = bit_b;
+		if (!LATE)
+		{
+			alive_a = alive_a && bit_a; // :91-92
+			alive_b = alive_b && bit_b;
+		}
+		else
+		{
+			skip_a = ra.lateVis == 1 && bit_a; // :97-98
+			skip_b = rb.lateVis == 1 && bit_b;
+		}
+	}
+	visible_a = visible_b = false;
+	if (!LATE)
+	{
+		if (!__any_sync(0xffffffffu, alive_a || alive_b))
+			return; // nothing in these chunks was visible last frame
+		if (alive_a && !da.have_geom)
+			load_geometry(p, ra, da);
+		if (alive_b && !db.have_geom)
+			load_geometry(p, rb, db);
+	}
+
+	f3x2 lc = { pk(half_bits_to_float(da.b0.x & 0xffffu), half_bits_to_float(db.b0.x & 0xffffu)), pk(half_bits_to_float(da.b0.x >> 16), half_bits_to_float(db.b0.x >> 16)),
+		pk(half_bits_to_float(da.b0.y & 0xffffu), half_bits_to_float(db.b0.y & 0xffffu)) };
+	f3x2 qv = { pk(da.d1.x, db.d1.x), pk(da.d1.y, db.d1.y), pk(da.d1.z, db.d1.z) };
+	f2 qw = pk(da.d1.w, db.d1.w);
+	f2 scale = pk(da.d0.w, db.d0.w);
+	f3x2 rc = rotate_quat2(k, lc, qv, qw);
+	f3x2 center = { add2(k, mul2(rc.x, scale), pk(da.d0.x, db.d0.x)), add2(k, mul2(rc.y, scale), pk(da.d0.y, db.d0.y)), add2(k, mul2(rc.z, scale), pk(da.d0.z, db.d0.z)) };
+	center = transform_point2(k, cc.view, center);
+	f2 radius = mul2(pk(half_bits_to_float(da.b0.y >> 16), half_bits_to_float(db.b0.y >> 16)), scale);
+
+	bool fa, fb;
+	frustum_visible2(k, cc, center, radius, fa, fb); // :104-108
+	alive_a = alive_a && fa;
+	alive_b = alive_b && fb;
+
+	if (cd.clusterBackfaceEnabled != 0) // :102
+	{
+		f3x2 la = { s8_div127_2(int(int8_t(da.b1 & 0xffu)), int(int8_t(db.b1 & 0xffu))), s8_div127_2(int(int8_t((da.b1 >> 8) & 0xffu)), int(int8_t((db.b1 >> 8) & 0xffu))),
+			s8_div127_2(int(int8_t((da.b1 >> 16) & 0xffu)), int(int8_t((db.b1 >> 16) & 0xffu))) };
+		f3x2 axis = transform_vector2(k, cc.view, rotate_quat2(k, la, qv, qw));
+		f2 cutoff = s8_div127_2(int(int8_t(da.b1 >> 24)), int(int8_t(db.b1 >> 24)));
+		// math.h:41-44 with camera_position = 0
+		f2 lhs = dot3_2(k, center, axis);
+		f2 rhs = add2(k, mul2(cutoff, length3_2(k, center)), radius);
+		alive_a = alive_a && !(lo(lhs) >= lo(rhs));
+		alive_b = alive_b && !(hi(lhs) >= hi(rhs));
+	}
+
+	if (LATE && cd.clusterOcclusionEnabled == 1 && __any_sync(0xffffffffu, alive_a || alive_b)) // :110
+	{
+		bool oa, ob;
+		occlusion_visible2(k, cc, p.hiz, center, radius, oa, ob);
+		alive_a = alive_a && oa;
+		alive_b = alive_b && ob;
+	}
+
+	visible_a = alive_a;
+	visible_b = alive_b;
+}
+
 // clustercull.comp.glsl:126-131 for one 32-item chunk: lanes with consecutive bit indices inside one word form a run;
 // the run's head lane applies the whole run with at most two atomics (the GLSL issues one atomic per lane).
 __device__ __forceinline__ void update_visibility_bits(uint32_t* mvb, bool active, bool visible, uint32_t mvi)
@@ -565,6 +697,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 	const uint32_t nbatch = (ncmd + 31u) / 32u;
 	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
 	const bool bits_known = cd.postPass == 0; // meshlet_test read the previous bit (clustercull.comp.glsl:86)
+	const Pk pkc = { bc(p.one), bc(p.neg_one) };
 
 	for (;;)
 	{
@@ -642,35 +775,12 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			return r;
 		};
 
-		ItemRef cur = map_chunk(0);
-		ItemData cur_data;
-		if (total)
-			meshlet_fetch<LATE>(p, cur, cur_data);
-
-		for (uint32_t base = 0; base < total; base += 32)
-		{
-#if NVC_PREFETCH
-			// software pipeline: the next chunk's loads are in flight while this chunk is evaluated
-			ItemRef next = cur;
-			ItemData next_data = cur_data;
-			if (base + 32 < total)
-			{
-				next = map_chunk(base + 32);
-				meshlet_fetch<LATE>(p, next, next_data);
-			}
-#endif
-			if (!hiz_ready)
-			{
-				hiz_stage_wait(&s_hiz_bar);
-				hiz_ready = true;
-			}
-			bool skip, oldbit, visible;
-			meshlet_compute<LATE, STAGED>(p, cc, s_hiz, cur, cur_data, visible, skip, oldbit);
-
+		// one chunk's bookkeeping after its verdicts are known: visibility bits (late) and compaction
+		auto commit_chunk = [&](const ItemRef& r, bool visible, bool skip, bool oldbit) {
 			// :126-131 — the GLSL rewrites every valid lane's bit; bits that already hold the new value need no
 			// traffic, so the whole chunk skips the update when no lane changes state (the steady-state case)
-			if (track_late && __any_sync(0xffffffffu, cur.active && (!bits_known || oldbit != visible)))
-				update_visibility_bits(p.meshlet_visibility, cur.active, visible, cur.mvi);
+			if (track_late && __any_sync(0xffffffffu, r.active && (!bits_known || oldbit != visible)))
+				update_visibility_bits(p.meshlet_visibility, r.active, visible, r.mvi);
 
 			const bool out = visible && !skip; // :133
 			const uint32_t omask = __ballot_sync(0xffffffffu, out);
@@ -680,19 +790,49 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 				if (nst + n > kStage)
 					flush_stage(p, stage, nst);
 				if (out)
-					stage[nst + __popc(omask & lanemask_lt())] = cur.code;
+					stage[nst + __popc(omask & lanemask_lt())] = r.code;
 				nst += n;
 			}
-#if NVC_PREFETCH
-			cur = next;
-			cur_data = next_data;
-#else
+		};
+
+		if (NVC_PACKED && !STAGED)
+		{
+			// two chunks (64 meshlets) per iteration, evaluated together with packed FP32x2 arithmetic
+			for (uint32_t base = 0; base < total; base += 64)
+			{
+				ItemRef ra = map_chunk(base), rb = map_chunk(base + 32);
+				ItemData da, db;
+				meshlet_fetch<LATE>(p, ra, da);
+				meshlet_fetch<LATE>(p, rb, db);
+				bool va, sa, oa, vb, sb, ob;
+				meshlet_compute2<LATE>(p, cc, pkc, ra, da, rb, db, va, sa, oa, vb, sb, ob);
+				commit_chunk(ra, va, sa, oa);
+				if (base + 32 < total)
+					commit_chunk(rb, vb, sb, ob);
+			}
+			continue;
+		}
+
+		ItemRef cur = map_chunk(0);
+		ItemData cur_data;
+		if (total)
+			meshlet_fetch<LATE>(p, cur, cur_data);
+
+		for (uint32_t base = 0; base < total; base += 32)
+		{
+			if (!hiz_ready)
+			{
+				hiz_stage_wait(&s_hiz_bar);
+				hiz_ready = true;
+			}
+			bool skip, oldbit, visible;
+			meshlet_compute<LATE, STAGED>(p, cc, s_hiz, cur, cur_data, visible, skip, oldbit);
+			commit_chunk(cur, visible, skip, oldbit);
 			if (base + 32 < total)
 			{
 				cur = map_chunk(base + 32);
 				meshlet_fetch<LATE>(p, cur, cur_data);
 			}
-#endif
 		}
 	}
 	if (nst)
