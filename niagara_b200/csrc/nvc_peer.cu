@@ -12,7 +12,7 @@ namespace
 {
 
 constexpr int kMaxWorld = 64;
-constexpr int kSideStreams = 4;
+constexpr int kSideStreams = 8; // one per peer at 8 GPUs: independent copy engines
 
 struct Ticket // what a rank publishes: IPC handles of its three receive buffers
 {
