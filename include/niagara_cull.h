@@ -246,6 +246,19 @@ NVC_API int nvc_taskcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
     const NvcMeshDraw* draws, const NvcMeshlet* meshlets, uint32_t* meshlet_visibility,
     NvcMeshTaskPayload* payloads, uint32_t* emit_counts, const NvcHiZ* hiz);
 
+/* Consumer-side walk of the cluster pass output, exactly as meshlet.mesh.glsl:89-105 decodes it under
+ * vkCmdDrawMeshTasksIndirectEXT(ccb, 4): one slot per mesh workgroup, slot = x + y * 256 + z * 16 for the dispatch
+ * (16, Y, 16) stored in cluster_count4[1..3]; ci == ~0 -> skipped; command = taskCommands[ci & 0xffffff];
+ * mi = command.taskOffset + (ci >> 24).  Writes per slot {drawId, mi, vertexCount, triangleCount} (all ~0 for skipped
+ * slots) and stats[4] = {decoded slots, skipped slots, invalid slots (lane >= taskCount), triangles}.  Used to prove the
+ * output is a drop-in for the reference's consumers; not part of the per-frame path.  records may be NULL (stats only). */
+typedef struct NvcClusterRecord
+{
+	uint32_t drawId, meshletIndex, vertexCount, triangleCount;
+} NvcClusterRecord;
+NVC_API int nvc_decode_clusters(NvcContext* ctx, void* stream, const uint32_t* cluster_indices, const uint32_t* cluster_count4,
+    const NvcMeshTaskCommand* task_commands, const NvcMeshlet* meshlets, NvcClusterRecord* records, uint32_t* stats4);
+
 /* depthreduce.comp.glsl:14-22 + the per-mip loop of niagara.cpp:1703-1733, as ONE launch.
  *   depth  float[depth_height][depth_width], reverse-Z (the D32 depthTarget)
  *   hiz    layout from nvc_hiz_layout(depth_width, depth_height) with `texels` set */

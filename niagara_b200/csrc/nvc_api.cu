@@ -326,6 +326,15 @@ NVC_API int nvc_taskcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_taskcull");
 }
 
+NVC_API int nvc_decode_clusters(NvcContext* ctx, void* stream, const uint32_t* cluster_indices, const uint32_t* cluster_count4,
+    const NvcMeshTaskCommand* task_commands, const NvcMeshlet* meshlets, NvcClusterRecord* records, uint32_t* stats4)
+{
+	if (!ctx || !cluster_indices || !cluster_count4 || !task_commands || !meshlets || !stats4)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaError_t e = nvc::launch_decode_clusters(cluster_indices, cluster_count4, task_commands, meshlets, records, stats4, uint32_t(ctx->sm_count) * 8u, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_decode_clusters");
+}
+
 NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
     uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz)
 {

@@ -1165,6 +1165,73 @@ __global__ void __launch_bounds__(kPyrBlock, NVC_PYRAMID_MIN_BLOCKS) pyramid_ker
 // launchers
 // ------------------------------------------------------------------------------------------------------
 
+// meshlet.mesh.glsl:89-105 — what every mesh workgroup of vkCmdDrawMeshTasksIndirectEXT(ccb, 4) reads before it starts
+// emitting vertices: slot -> cluster index -> task command -> meshlet.
+__global__ void __launch_bounds__(256) decode_clusters_kernel(const uint32_t* __restrict__ cluster_indices, const uint32_t* __restrict__ cluster_count4,
+    const NvcMeshTaskCommand* __restrict__ task_commands, const NvcMeshlet* __restrict__ meshlets, NvcClusterRecord* __restrict__ records, uint32_t* __restrict__ stats4)
+{
+	// dispatch (X, Y, Z) = (16, Y, 16): workgroup (x, y, z) reads clusterIndices[x + y * 256 + z * CLUSTER_TILE]
+	const uint32_t gx = cluster_count4[1], gy = cluster_count4[2], gz = cluster_count4[3];
+	const uint32_t slots = gx * gy * gz;
+	uint32_t decoded = 0, skipped = 0, invalid = 0, triangles = 0;
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < slots; w += gridDim.x * blockDim.x)
+	{
+		// enumerate workgroups x fastest, then z, then y so that slot = x + z * 16 + y * 256 is also w for (16, Y, 16)
+		uint32_t x = w % gx, z = (w / gx) % gz, y = w / (gx * gz);
+		uint32_t slot = x + y * 256u + z * NVC_CLUSTER_TILE;
+		uint32_t ci = cluster_indices[slot];
+		NvcClusterRecord r = { ~0u, ~0u, ~0u, ~0u };
+		if (ci == ~0u)
+			skipped++; // SetMeshOutputsEXT(0, 0)  :96-100
+		else
+		{
+			const uint32_t* cp = reinterpret_cast<const uint32_t*>(task_commands + (ci & 0xffffffu)); // :102
+			uint32_t lane = ci >> 24;
+			uint32_t mi = cp[1] + lane; // :103
+			if (lane >= cp[2])
+				invalid++;
+			r.drawId = cp[0];
+			r.meshletIndex = mi;
+			r.vertexCount = meshlets[mi].vertexCount;     // :107
+			r.triangleCount = meshlets[mi].triangleCount; // :108
+			decoded++;
+			triangles += r.triangleCount;
+		}
+		if (records)
+			records[slot] = r;
+	}
+	// warp-aggregate the four statistics, one atomic per warp and counter
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1)
+	{
+		decoded += __shfl_xor_sync(0xffffffffu, decoded, o);
+		skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+		invalid += __shfl_xor_sync(0xffffffffu, invalid, o);
+		triangles += __shfl_xor_sync(0xffffffffu, triangles, o);
+	}
+	if ((threadIdx.x & 31u) == 0)
+	{
+		if (decoded)
+			atomicAdd(stats4 + 0, decoded);
+		if (skipped)
+			atomicAdd(stats4 + 1, skipped);
+		if (invalid)
+			atomicAdd(stats4 + 2, invalid);
+		if (triangles)
+			atomicAdd(stats4 + 3, triangles);
+	}
+}
+
+cudaError_t launch_decode_clusters(const uint32_t* cluster_indices, const uint32_t* cluster_count4, const NvcMeshTaskCommand* task_commands, const NvcMeshlet* meshlets,
+    NvcClusterRecord* records, uint32_t* stats4, uint32_t blocks, cudaStream_t stream)
+{
+	cudaError_t e = cudaMemsetAsync(stats4, 0, 16, stream);
+	if (e != cudaSuccess)
+		return e;
+	decode_clusters_kernel<<<blocks, 256, 0, stream>>>(cluster_indices, cluster_count4, task_commands, meshlets, records, stats4);
+	return cudaGetLastError();
+}
+
 __global__ void pack_meshes_kernel(const NvcMesh* __restrict__ meshes, uint32_t count, MeshCullHead* __restrict__ heads, float* __restrict__ errors)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -45,6 +45,7 @@ SIGNATURES = [
         ctypes.c_int,
         [c_void_p, c_void_p, ctypes.POINTER(CullData), ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(HiZ)],
     ),
+    ("nvc_decode_clusters", ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("nvc_depth_pyramid", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(HiZ)]),
     ("nvc_host_random_draws", None, [c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float]),
     ("nvc_host_visibility_offsets", ctypes.c_uint32, [c_void_p, ctypes.c_uint32, c_void_p, c_u32_p]),

@@ -156,6 +156,19 @@ class VisibilityPath:
             if self.mesh_shading:
                 self.render_clusters(cull_data, late=True, post_pass=1, cluster_backface=cluster_backface)
 
+    def decode_clusters(self, want_records=True):
+        """consumer-side walk of cib/ccb/dcb like meshlet.mesh.glsl:89-105 (nvc_decode_clusters); returns
+        (records[slots, 4] uint32 or None, stats[4] = decoded, skipped, invalid, triangles)"""
+        torch.cuda.current_stream(self.device).synchronize()
+        ccb = self.ccb.cpu().numpy().astype(np.uint32)
+        slots = int(ccb[2]) * 256
+        records = torch.empty((max(slots, 1), 4), dtype=torch.int32, device=self.device) if want_records else None
+        stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+        check(self.lib.nvc_decode_clusters(self.ctx, self._stream(), _ptr(self.cib), _ptr(self.ccb), _ptr(self.dcb), _ptr(self.mlb), _ptr(records), _ptr(stats)), self.ctx, "nvc_decode_clusters")
+        torch.cuda.current_stream(self.device).synchronize()
+        rec = records[:slots].cpu().numpy().astype(np.uint32) if want_records else None
+        return rec, stats.cpu().numpy().astype(np.uint32)
+
     # -- readback helpers (tests / e2e) -----------------------------------------------------------------------
     def read_counts(self):
         return self.dccb.cpu().numpy().astype(np.uint32), self.ccb.cpu().numpy().astype(np.uint32)

@@ -722,6 +722,40 @@ int orc_taskcull(const NvcCullData* cull, int late, const NvcMeshTaskCommand* ta
 	return NVC_OK;
 }
 
+// ---- meshlet.mesh.glsl:89-105: what the mesh workgroups of vkCmdDrawMeshTasksIndirectEXT(ccb, 4) decode ----------
+int orc_decode_clusters(const uint32_t* cluster_indices, const uint32_t* cluster_count4, const NvcMeshTaskCommand* task_commands,
+    const NvcMeshlet* meshlets, NvcClusterRecord* records, uint32_t* stats4)
+{
+	uint32_t gx = cluster_count4[1], gy = cluster_count4[2], gz = cluster_count4[3];
+	stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0;
+	for (uint32_t y = 0; y < gy; ++y)
+		for (uint32_t z = 0; z < gz; ++z)
+			for (uint32_t x = 0; x < gx; ++x)
+			{
+				uint32_t slot = x + y * 256 + z * NVC_CLUSTER_TILE; // :94
+				uint32_t ci = cluster_indices[slot];
+				NvcClusterRecord r = { ~0u, ~0u, ~0u, ~0u };
+				if (ci == ~0u) // :96
+					stats4[1]++;
+				else
+				{
+					const NvcMeshTaskCommand& command = task_commands[ci & 0xffffff]; // :102
+					uint32_t mi = command.taskOffset + (ci >> 24);                   // :103
+					if ((ci >> 24) >= command.taskCount)
+						stats4[2]++;
+					r.drawId = command.drawId;
+					r.meshletIndex = mi;
+					r.vertexCount = meshlets[mi].vertexCount;
+					r.triangleCount = meshlets[mi].triangleCount;
+					stats4[0]++;
+					stats4[3] += r.triangleCount;
+				}
+				if (records)
+					records[slot] = r;
+			}
+	return NVC_OK;
+}
+
 // ---- depthreduce.comp.glsl:14-22 + niagara.cpp:1703-1733: level i = MIN-sample of level i-1 (depth for i = 0)
 int orc_depth_pyramid(const float* depth, uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz, int threads)
 {

@@ -31,6 +31,8 @@ def load():
     lib.orc_taskcull.argtypes = [ctypes.POINTER(layout.CullData), ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(layout.HiZ), ctypes.c_int]
     lib.orc_depth_pyramid.restype = ctypes.c_int
     lib.orc_depth_pyramid.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(layout.HiZ), ctypes.c_int]
+    lib.orc_decode_clusters.restype = ctypes.c_int
+    lib.orc_decode_clusters.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.orc_half_to_float.restype = ctypes.c_float
     lib.orc_half_to_float.argtypes = [ctypes.c_uint16]
     lib.orc_rotate_quat.argtypes = [vp, vp, vp]
@@ -134,6 +136,14 @@ class OraclePath:
             self.cull(cull_data, late=True, post_pass=1)
             if self.mesh_shading:
                 self.render_clusters(cull_data, late=True, post_pass=1, cluster_backface=cluster_backface)
+
+    def decode_clusters(self, want_records=True):
+        slots = int(self.ccb[2]) * 256
+        records = np.zeros((max(slots, 1), 4), dtype=np.uint32) if want_records else None
+        stats = np.zeros(4, dtype=np.uint32)
+        s = self.lib.orc_decode_clusters(_p(self.cib), _p(self.ccb), _p(self.dcb), _p(self.meshlets), _p(records), _p(stats))
+        assert s == 0
+        return (records[:slots] if want_records else None), stats
 
     # readback in the same shape as VisibilityPath
     def read_counts(self):

@@ -235,3 +235,24 @@ def test_multithreaded_oracle_equals_serial(golden_dir):
         res.append((dccb.copy(), ccb.copy(), o.read_task_commands(dccb[1] * 64), o.read_cluster_indices((ccb[0] + 255) // 256 * 256), o.dvb.copy(), o.mvb.copy(), o.pyramid_texels.copy()))
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
+
+
+def test_decode_clusters_matches_consumer_rule(golden_dir):
+    """oracle decode (meshlet.mesh.glsl:89-105 walk over the (16, Y, 16) dispatch) == direct numpy decode"""
+    s = _scene(golden_dir, n=4000)
+    cd = s.cull_data()
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen)
+    o.set_visibility_bits(s.visibility_bits)
+    o.frame(cd, s.depth, cluster_backface=True)  # frame 0: the late pass emits everything visible
+    _, ccb = o.read_counts()
+    n = int(ccb[0])
+    assert n > 100
+    rec, stats = o.decode_clusters()
+    assert stats[0] == n and stats[2] == 0 and stats[1] == int(ccb[2]) * 256 - n
+    cmds = o.read_task_commands(int(o.dccb[1]) * 64)
+    ci = o.read_cluster_indices(n)
+    want_draw = cmds["drawId"][ci & 0xFFFFFF]
+    want_mi = cmds["taskOffset"][ci & 0xFFFFFF] + (ci >> 24)
+    assert np.array_equal(rec[:n, 0], want_draw) and np.array_equal(rec[:n, 1], want_mi)
+    assert np.array_equal(rec[:n, 3], s.meshlets["triangleCount"][want_mi]) and stats[3] == s.meshlets["triangleCount"][want_mi].sum()
+    assert (rec[n:] == 0xFFFFFFFF).all()
