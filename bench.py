@@ -294,24 +294,39 @@ def main():
 
     names = ["drawcull_early", "clustercull_early", "pyramid", "drawcull_late", "clustercull_late"]
 
+    # With the copy-engine gather the late commands go to their own buffer (the C ABI takes the command buffer per
+    # call): the slab pushed after drawcull(late) of frame k then stays untouched until drawcull(late) of frame k+1, so
+    # the exchange has the late cluster pass AND the next frame's early passes to complete — frames in flight like the
+    # reference's MAX_FRAMES = 2 (config.h:31).  The wait sits right before the slab is overwritten (and after the loop).
+    dcb_early = path.dcb
+    dcb_late = torch.zeros_like(path.dcb) if gather == "ce" else path.dcb
+    pending = {"push": False}
+
     def frame(events=None):
         def mark(i):
             if events is not None:
                 events[i].record()
 
         mark(0)
+        path.dcb = dcb_early
         path.cull(cd, late=False)
         mark(1)
         path.render_clusters(cd, late=False, cluster_backface=True)
         mark(2)
         path.pyramid(depth)
         mark(3)
+        path.dcb = dcb_late
+        if gather == "ce" and pending["push"]:
+            # the previous frame's slab (and every peer's copy of it) must have landed before it is overwritten
+            check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
+            pending["push"] = False
         path.cull(cd, late=True)
         mark(4)
         if gather == "ce":
             # the late command slab is final once drawcull(late) is done: push it to every peer with the copy engines
-            # while the late cluster pass runs on the SMs
+            # while the late cluster pass (and the next frame's early passes) run on the SMs
             check(lib.nvc_gather_push(path.ctx, path._stream(), ctypes.c_void_p(path.dcb.data_ptr()), ctypes.c_void_p(path.dccb.data_ptr())), path.ctx, "nvc_gather_push")
+            pending["push"] = True
         elif gather == "nccl":
             done = torch.cuda.Event()
             done.record()
@@ -323,10 +338,14 @@ def main():
             )
         path.render_clusters(cd, late=True, cluster_backface=True)
         mark(5)
-        if gather == "ce":
-            check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
-        elif gather == "nccl":
+        if gather == "nccl":
             torch.cuda.current_stream().wait_stream(comm_stream)
+
+    def drain():
+        """end of a timed region: the last frame's exchange must be complete on every rank"""
+        if gather == "ce" and pending["push"]:
+            check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
+            pending["push"] = False
 
     def sync_all():
         torch.cuda.synchronize()
@@ -337,6 +356,7 @@ def main():
     # ---- warm-up: establishes the steady two-phase state (dvb / mvb) and warms caches / clocks ----
     for _ in range(max(3, args.warmup)):
         frame()
+    drain()
     torch.cuda.synchronize()
 
     # probe one frame for the per-pass work counts (static scene: identical every step)
@@ -372,6 +392,7 @@ def main():
     start.record()
     for k in range(K):
         frame(ev[k])
+    drain()
     stop.record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
@@ -436,6 +457,7 @@ def main():
         # upload(2) is already in flight from the warm-up: the timed region still performs K uploads for K frames
         for k in range(2, K + 2):
             e2e_frame(k, False)
+        drain()
         stop.record()
         sync_all()
         copy_stream.synchronize()
@@ -475,7 +497,7 @@ def main():
             "data": "synthetic",
             "config": {
                 "workload": "%s: %s; per GPU" % (scene.name, scene.note),
-                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit (5 launches)%s" % ({"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), overlapped with the late cluster pass", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a side stream", "none": ""}[gather]),
+                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid, late drawcull+tasksubmit, late clustercull+clustersubmit (5 launches)%s" % ({"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), every frame, pipelined one frame deep: the exchange of frame k must complete before drawcull(late) of frame k+1 overwrites the slab, and the last one before the clock stops", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a side stream", "none": ""}[gather]),
                 "counting": "value = meshlet instances TESTED by the two cluster passes per second (early %d + late %d per step per GPU); draws_per_s likewise (early %d + late %d)" % (tested_early, tested_late, early_reached, D),
                 "l2": "inputs larger than L2 (Meshlet[] %d MB + MeshDraw[] %d MB + Mesh[] %d MB + depth %d MB per step vs 126 MB L2), no flush" % (scene.meshlets.nbytes >> 20, scene.draws.nbytes >> 20, scene.meshes.nbytes >> 20, scene.depth.nbytes >> 20),
                 "cluster_backface": 1,
