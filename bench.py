@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-draws", type=int, default=1_000_000, help="draws in the bounded CPU-baseline sample (default: the whole C4 scene, one frame ~ 10-60 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="ce", choices=["ce", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), nccl = ncclAllGather, none = skip")
+    ap.add_argument("--gather", default="ce", choices=["ce", "sm", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), nccl = ncclAllGather, none = skip")
     return ap.parse_args()
 
 
@@ -54,6 +54,21 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the late cluster kernel from the committed `ncu --set full`
+    capture of this same command (profiles/r1_frame_ncu_full_summary.json); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_frame_ncu_full_summary.json")
+    try:
+        for k in json.load(open(path)):
+            if "clustercull_kernel<1" in k["Kernel Name"]:
+                rd, wr = k["dram__bytes_read.sum"].split(), k["dram__bytes_write.sum"].split()
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                return float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
+    except Exception:
+        pass
+    return None
 
 
 def build_scene(args, rank):
@@ -265,6 +280,9 @@ def main():
 
     # ---- multi-GPU: all-gather of the per-rank visible command slabs + counters ----
     gather = args.gather if world > 1 else "none"
+    sm_push = gather == "sm"
+    if sm_push:
+        gather = "ce"  # same protocol (nvc_gather_*), the slab is pushed by a small kernel instead of the copy engines
     slab_cmds = (D * max(1, (args.meshlets_per_draw + 63) // 64) + 63) // 64 * 64 if args.workload == "C4" else 0
     if not slab_cmds:
         gather = "none"
@@ -290,6 +308,7 @@ def main():
         dist.all_gather_into_tensor(everyone, mine)
         tickets = (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())
         check(lib.nvc_gather_connect(path.ctx, tickets), path.ctx, "nvc_gather_connect")
+        check(lib.nvc_gather_set_mode(path.ctx, int(sm_push)), path.ctx, "nvc_gather_set_mode")
         dist.barrier()
 
     names = ["drawcull_early", "clustercull_early", "pyramid", "drawcull_late", "clustercull_late"]
@@ -515,13 +534,15 @@ def main():
                 "peak_source": peak_src,
                 "unit": "GB/s",
                 "frac": achieved / peak_gbs,
-                "traffic": None,
+                "traffic": profiled_traffic(),
+                "traffic_source": "ncu --set full, profiles/r1_frame_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": k_ms,
                 "meshlets_per_s_kernel": M / (k_ms * 1e-3),
             },
             "clocks": clocks,
-            "gpu_launches": (5 + (2 if gather == "ce" else 0)) * K,
+            "gpu_launches": (5 + ((3 if sm_push else 2) if gather == "ce" else 0)) * K,
+            "gather_transport": ("sm-push" if sm_push else gather),
         }
         if e2e:
             line["e2e"] = e2e

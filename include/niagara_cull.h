@@ -325,6 +325,9 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets);
 NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4);
 NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream);
 NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t** gathered_count4);
+/* transport of nvc_gather_push: 0 = copy engines (default), 1 = a 32-CTA kernel on a high-priority stream that writes only
+ * the valid count x 20 bytes with 16-byte peer stores (also selectable with NVC_GATHER_MODE=sm) */
+NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push);
 
 #ifdef __cplusplus
 } /* extern "C" */

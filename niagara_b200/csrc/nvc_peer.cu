@@ -6,6 +6,7 @@
 // One process per GPU; the IPC tickets are exchanged by the caller (any transport).
 #include "nvc_internal.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace
@@ -28,6 +29,34 @@ __global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int r
 		__threadfence_system();
 		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + rank) = tag; // P2P store over NVLink (or local)
 	}
+}
+
+// SM variant of the push: a few CTAs stream the VALID part of the local slab (count x 20 bytes, known only on the
+// device) to every rank's slot with 16-byte peer stores.  Launched on a high-priority stream right before the late
+// cluster pass so that its CTAs are placed first; the persistent cluster kernel fills the remaining slots.
+__global__ void __launch_bounds__(512) push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* const* peer_slabs,
+    uint32_t* const* peer_counts, size_t slab_bytes, int world, int rank)
+{
+	const uint32_t count = local_count4[0];
+	size_t bytes = size_t(count) * sizeof(NvcMeshTaskCommand);
+	bytes = bytes < slab_bytes ? bytes : slab_bytes;
+	const size_t n16 = (bytes + 15) / 16; // slab_bytes is a multiple of 64 commands = 1280 bytes, so rounding up stays inside
+	const size_t stride = size_t(gridDim.x) * blockDim.x;
+	for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+	{
+		uint4 v = __ldg(local_slab + i);
+		for (int k = 0; k < world; ++k)
+		{
+			int p = (rank + k) % world;
+			reinterpret_cast<uint4*>(peer_slabs[p] + size_t(rank) * slab_bytes)[i] = v;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x < uint32_t(world))
+	{
+		uint4 c = *reinterpret_cast<const uint4*>(local_count4);
+		*reinterpret_cast<uint4*>(peer_counts[threadIdx.x] + 4 * rank) = c;
+	}
+	__threadfence_system();
 }
 
 __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag)
@@ -55,6 +84,10 @@ struct NvcGather
 	uint32_t* peer_counts[kMaxWorld] = {};
 	uint32_t* peer_flags[kMaxWorld] = {};
 	uint32_t** d_peer_flags = nullptr; // device copy of peer_flags
+	uint8_t** d_peer_slabs = nullptr;
+	uint32_t** d_peer_counts = nullptr;
+	cudaStream_t hi = nullptr; // high-priority stream of the SM push
+	int mode = 0;              // 0 = copy engines, 1 = SM push kernel
 	cudaStream_t side[kSideStreams] = {};
 	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
 	uint32_t tag = 0;
@@ -94,6 +127,10 @@ void gather_destroy(NvcContext* ctx)
 	cudaFree(g->counts);
 	cudaFree(g->flags);
 	cudaFree(g->d_peer_flags);
+	cudaFree(g->d_peer_slabs);
+	cudaFree(g->d_peer_counts);
+	if (g->hi)
+		cudaStreamDestroy(g->hi);
 	delete g;
 	ctx->gather = nullptr;
 }
@@ -120,6 +157,18 @@ NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int 
 		e = cudaMalloc(&g->flags, sizeof(uint32_t) * kMaxWorld);
 	if (e == cudaSuccess)
 		e = cudaMalloc(&g->d_peer_flags, sizeof(uint32_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->d_peer_slabs, sizeof(uint8_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->d_peer_counts, sizeof(uint32_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+	{
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		e = cudaStreamCreateWithPriority(&g->hi, cudaStreamNonBlocking, hi);
+	}
+	if (const char* env = getenv("NVC_GATHER_MODE"))
+		g->mode = (strcmp(env, "sm") == 0) ? 1 : 0;
 	if (e == cudaSuccess)
 		e = cudaMemset(g->counts, 0, sizeof(uint32_t) * 4 * world);
 	if (e == cudaSuccess)
@@ -178,6 +227,10 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets /* world
 	}
 	if (e == cudaSuccess)
 		e = cudaMemcpy(g->d_peer_flags, g->peer_flags, sizeof(uint32_t*) * g->world, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_slabs, g->peer_slabs, sizeof(uint8_t*) * g->world, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_counts, g->peer_counts, sizeof(uint32_t*) * g->world, cudaMemcpyHostToDevice);
 	if (e != cudaSuccess)
 	{
 		ctx->last_error = std::string("nvc_gather_connect: ") + cudaGetErrorString(e);
@@ -198,6 +251,29 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	g->tag += 1;
 	cudaError_t e = cudaEventRecord(g->fork, s);
+	if (g->mode == 1 && e == cudaSuccess)
+	{
+		// SM push: one kernel on the high-priority stream, then the flag raise behind it
+		e = cudaStreamWaitEvent(g->hi, g->fork, 0);
+		if (e == cudaSuccess)
+		{
+			push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), local_count4, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess)
+		{
+			raise_flags_kernel<<<1, kMaxWorld, 0, g->hi>>>(g->d_peer_flags, g->world, g->rank, g->tag);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess)
+			e = cudaEventRecord(g->join[0], g->hi);
+		if (e != cudaSuccess)
+		{
+			ctx->last_error = std::string("nvc_gather_push: ") + cudaGetErrorString(e);
+			return NVC_ERROR_CUDA;
+		}
+		return NVC_OK;
+	}
 	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
 		e = cudaStreamWaitEvent(g->side[i], g->fork, 0);
 	for (int k = 0; k < g->world && e == cudaSuccess; ++k)
@@ -249,6 +325,15 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 		ctx->last_error = std::string("nvc_gather_wait: ") + cudaGetErrorString(e);
 		return NVC_ERROR_CUDA;
 	}
+	return NVC_OK;
+}
+
+NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	g->mode = sm_push ? 1 : 0;
 	return NVC_OK;
 }
 

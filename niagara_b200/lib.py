@@ -62,6 +62,7 @@ SIGNATURES = [
     ("nvc_gather_connect", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_push", ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     ("nvc_gather_wait", ctypes.c_int, [c_void_p, c_void_p]),
+    ("nvc_gather_set_mode", ctypes.c_int, [c_void_p, ctypes.c_int]),
     ("nvc_gather_buffers", ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
 ]
 

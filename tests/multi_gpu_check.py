@@ -80,7 +80,8 @@ def main():
         cd_all = s.cull_data()
 
     ok = True
-    for frame in range(3):
+    for frame in range(4):
+        check(lib.nvc_gather_set_mode(g.ctx, frame % 2), g.ctx, "nvc_gather_set_mode")  # alternate copy engines / SM push
         for late in (False, True):
             if late:
                 g.pyramid(depth)
