@@ -31,16 +31,12 @@ __device__ __forceinline__ f2 pk(float a, float b)
 
 __device__ __forceinline__ float lo(f2 v)
 {
-	float a, b;
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-	return a;
+	return __uint_as_float(static_cast<uint32_t>(v));
 }
 
 __device__ __forceinline__ float hi(f2 v)
 {
-	float a, b;
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-	return b;
+	return __uint_as_float(static_cast<uint32_t>(v >> 32));
 }
 
 __device__ __forceinline__ f2 bc(float s) // broadcast a scalar to both halves
