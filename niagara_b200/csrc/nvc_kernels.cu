@@ -65,6 +65,9 @@ typedef NvcCullData ClusterConsts;
 #ifndef NVC_PACKED
 #define NVC_PACKED 0
 #endif
+#ifndef NVC_UNIFORM_FLATTEN
+#define NVC_UNIFORM_FLATTEN 1
+#endif
 #ifndef NVC_CLUSTER_MIN_BLOCKS
 #define NVC_CLUSTER_MIN_BLOCKS 6
 #endif
@@ -737,12 +740,19 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 		const uint32_t rel_mvo = c_mvo - excl;
 		const uint32_t nz = __ballot_sync(0xffffffffu, c_count != 0);
 		const bool nz_prefix = (nz & (nz + 1u)) == 0; // non-empty commands form a prefix (always, except stale slots)
+		// all 32 commands carry the same meshlet count (instanced meshes at one LOD, the synthetic scenes): then
+		// command = item / count, one multiply-high with a per-batch reciprocal (exact: item < 2^11, count <= 64)
+		const uint32_t count0 = __shfl_sync(0xffffffffu, c_count, 0);
+		const bool uniform = NVC_UNIFORM_FLATTEN && count0 >= 2 && __all_sync(0xffffffffu, c_count == count0); // (count 1: the reciprocal would not fit)
+		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u; // ceil(2^32 / count0)
 
 		// item -> command mapping of the chunk starting at `base` (executed by all lanes)
 		auto map_chunk = [&](uint32_t base) -> ItemRef {
 			const uint32_t item = base + lane;
 			uint32_t j;
-			if (nz_prefix)
+			if (uniform)
+				j = __umulhi(item, recip);
+			else if (nz_prefix)
 			{
 				// head bits: commands that START inside this chunk (bit 0 excluded: that command is `first`)
 				uint32_t rel = excl - base;
