@@ -65,6 +65,9 @@ typedef NvcCullData ClusterConsts;
 #ifndef NVC_PACKED
 #define NVC_PACKED 0
 #endif
+#ifndef NVC_ALIVE_FLATTEN
+#define NVC_ALIVE_FLATTEN 1
+#endif
 #ifndef NVC_UNIFORM_FLATTEN
 #define NVC_UNIFORM_FLATTEN 1
 #endif
@@ -379,11 +382,53 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 // per-meshlet test shared by clustercull / taskcull
 // ------------------------------------------------------------------------------------------------------
 
+// position of the r-th (0-based) set bit of the 64-bit mask {hi, lo}; r < popc(mask)
+__device__ __forceinline__ uint32_t select_bit64(uint32_t lo, uint32_t hi, uint32_t r)
+{
+	uint32_t c = __popc(lo);
+	bool upper = r >= c;
+	uint32_t w = upper ? hi : lo;
+	r = upper ? r - c : r;
+	uint32_t pos = upper ? 32u : 0u;
+	uint32_t t;
+	t = __popc(w & 0xffffu);
+	if (r >= t)
+	{
+		r -= t;
+		pos += 16;
+		w >>= 16;
+	}
+	t = __popc(w & 0xffu);
+	if (r >= t)
+	{
+		r -= t;
+		pos += 8;
+		w >>= 8;
+	}
+	t = __popc(w & 0xfu);
+	if (r >= t)
+	{
+		r -= t;
+		pos += 4;
+		w >>= 4;
+	}
+	t = __popc(w & 0x3u);
+	if (r >= t)
+	{
+		r -= t;
+		pos += 2;
+		w >>= 2;
+	}
+	pos += (r >= (w & 1u)) ? 1u : 0u;
+	return pos;
+}
+
 // One lane's work item inside a chunk and the raw data its test needs.
 struct ItemRef
 {
 	uint32_t drawId, lateVis, mi, mvi, code; // code = commandId | (mgi << 24), the value appended on success
 	bool active;
+	bool alive_known; // early pass, item list built from the set visibility bits: the bit test is already decided
 };
 
 struct ItemData
@@ -419,7 +464,13 @@ __device__ __forceinline__ void meshlet_fetch(const ClusterParams& p, const Item
 	d.b1 = 0;
 	d.word = 0;
 	d.have_geom = false;
-	if (r.active)
+	if (r.active && !LATE && r.alive_known)
+	{
+		d.word = 0xffffffffu; // the item exists because its bit is set
+		load_geometry(p, r, d);
+		d.have_geom = true;
+	}
+	else if (r.active)
 	{
 		if (track) // early: read-only this pass.  late: only this lane's own bit matters and nobody else changes it.
 			d.word = LATE ? __ldcg(p.meshlet_visibility + (r.mvi >> 5)) : __ldg(p.meshlet_visibility + (r.mvi >> 5));
@@ -724,8 +775,31 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			c_mvo = __ldg(cp + 4);
 		}
 
-		// flatten (command, mgi) pairs: inclusive scan of taskCount over the batch
-		uint32_t incl = c_count;
+		// Early pass with visibility tracking: only meshlets whose bit is set can survive (clustercull.comp.glsl:91-92), and
+		// the bits are known up front — so flatten the SET BITS of every command's 64-bit visibility window instead of
+		// all its lanes.  Meshlets that were invisible last frame then cost nothing (no geometry fetch, no arithmetic).
+		const bool alive_flatten = NVC_ALIVE_FLATTEN && !LATE && cd.clusterOcclusionEnabled == 1 && cd.postPass == 0;
+		uint32_t amask_lo = 0, amask_hi = 0;
+		uint32_t eff_count = c_count;
+		if (alive_flatten)
+		{
+			if (c_count)
+			{
+				const uint32_t sh = c_mvo & 31u;
+				const uint32_t nwords = (sh + c_count + 31u) >> 5; // 1..3 words hold the command's bits
+				const uint32_t* wp = p.meshlet_visibility + (c_mvo >> 5);
+				uint32_t w0 = __ldg(wp), w1 = nwords > 1 ? __ldg(wp + 1) : 0u, w2 = nwords > 2 ? __ldg(wp + 2) : 0u;
+				amask_lo = __funnelshift_r(w0, w1, sh);
+				amask_hi = __funnelshift_r(w1, w2, sh);
+				// keep the command's own `count` bits
+				amask_lo &= c_count >= 32 ? 0xffffffffu : ((1u << c_count) - 1u);
+				amask_hi &= c_count >= 64 ? 0xffffffffu : (c_count > 32 ? ((1u << (c_count - 32)) - 1u) : 0u);
+			}
+			eff_count = __popc(amask_lo) + __popc(amask_hi);
+		}
+
+		// flatten (command, item) pairs: inclusive scan of the per-command item count over the batch
+		uint32_t incl = eff_count;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
@@ -733,17 +807,14 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			if (lane >= uint32_t(o))
 				incl += n;
 		}
-		const uint32_t excl = incl - c_count;
+		const uint32_t excl = incl - eff_count;
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		// per-command values with the exclusive offset folded in, so an item only needs `item + rel`
-		const uint32_t rel_task = c_task - excl;
-		const uint32_t rel_mvo = c_mvo - excl;
-		const uint32_t nz = __ballot_sync(0xffffffffu, c_count != 0);
+		const uint32_t nz = __ballot_sync(0xffffffffu, eff_count != 0);
 		const bool nz_prefix = (nz & (nz + 1u)) == 0; // non-empty commands form a prefix (always, except stale slots)
 		// all 32 commands carry the same meshlet count (instanced meshes at one LOD, the synthetic scenes): then
 		// command = item / count, one multiply-high with a per-batch reciprocal (exact: item < 2^11, count <= 64)
-		const uint32_t count0 = __shfl_sync(0xffffffffu, c_count, 0);
-		const bool uniform = NVC_UNIFORM_FLATTEN && count0 >= 2 && __all_sync(0xffffffffu, c_count == count0); // (count 1: the reciprocal would not fit)
+		const uint32_t count0 = __shfl_sync(0xffffffffu, eff_count, 0);
+		const bool uniform = NVC_UNIFORM_FLATTEN && count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0); // (count 1: the reciprocal would not fit)
 		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u; // ceil(2^32 / count0)
 
 		// item -> command mapping of the chunk starting at `base` (executed by all lanes)
@@ -756,9 +827,9 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			{
 				// head bits: commands that START inside this chunk (bit 0 excluded: that command is `first`)
 				uint32_t rel = excl - base;
-				uint32_t hbit = (c_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
+				uint32_t hbit = (eff_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
 				uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
-				uint32_t first = __popc(__ballot_sync(0xffffffffu, c_count != 0 && incl <= base));
+				uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && incl <= base));
 				j = first + __popc(heads & lanemask_le());
 			}
 			else
@@ -778,9 +849,16 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			r.active = item < total;
 			r.drawId = __shfl_sync(0xffffffffu, c_draw, j);
 			r.lateVis = __shfl_sync(0xffffffffu, c_late, j);
-			r.mi = __shfl_sync(0xffffffffu, rel_task, j) + item;
-			r.mvi = __shfl_sync(0xffffffffu, rel_mvo, j) + item;
-			const uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j);
+			uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j); // rank of the item inside its command
+			if (alive_flatten)
+			{
+				// the rank-th SET bit of the command's visibility window is the meshlet's lane index
+				const uint32_t mlo = __shfl_sync(0xffffffffu, amask_lo, j), mhi = __shfl_sync(0xffffffffu, amask_hi, j);
+				mgi = r.active ? select_bit64(mlo, mhi, mgi) : 0u;
+			}
+			r.mi = __shfl_sync(0xffffffffu, c_task, j) + mgi;
+			r.mvi = __shfl_sync(0xffffffffu, c_mvo, j) + mgi;
+			r.alive_known = alive_flatten;
 			r.code = (batch * 32u + j) | (mgi << 24); // :138
 			return r;
 		};
@@ -917,6 +995,7 @@ __global__ void __launch_bounds__(kClusterBlock) taskcull_kernel(const ClusterPa
 			r.mi = c_task + mgi;
 			r.mvi = c_mvo + mgi;
 			r.code = cid | (mgi << 24);
+			r.alive_known = false;
 			ItemData d;
 			meshlet_fetch<LATE>(p, r, d);
 			meshlet_compute<LATE, false>(p, cc, nullptr, r, d, visible, skip, oldbit);
