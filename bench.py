@@ -2,7 +2,7 @@
 """bench.py — throughput of the visibility hot path on B200 (metric of BASELINE.json: meshlets culled/sec, with draws
 culled/sec and the HBM-roofline fraction of the dominant kernel alongside).
 
-    python bench.py --gpus 1 --steps 20 --warmup 3
+    python bench.py --gpus 1 --steps 100 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU restatement (oracle/, multi-threaded) on the host cores
 
@@ -32,8 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=["C4", "C2"])
     ap.add_argument("--draws", type=int, default=1_000_000)
@@ -113,7 +113,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"),
                 stderr=subprocess.DEVNULL,
             )
@@ -414,7 +414,6 @@ def main():
     drain()
     stop.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = start.elapsed_time(stop)
     pass_ms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(5)] for k in range(K)])
 
@@ -494,6 +493,7 @@ def main():
             "what": "per step: H2D MeshDraw[] + depth target from pinned host memory (double-buffered: the copy for frame k+1 overlaps frame k), the 5-launch frame, D2H counters then the visible MeshTaskCommand and cluster-index slabs",
         }
 
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (device-resident and e2e)
     if rank == 0:
         # ---- roofline of the dominant kernel (clustercull LATE): algorithmic bytes per SURVEY §8(d) ----
         M, C, v = tested_late, int(dccb_l[0]), int(ccb_l[0])
