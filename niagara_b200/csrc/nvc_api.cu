@@ -49,6 +49,19 @@ void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_tex
 namespace
 {
 
+// Pass calls launch on the caller's stream, which lives on the context's device: that device must be current
+// (the reference drives one VkDevice from one thread; nothing here switches devices behind the caller's back).
+bool device_is_current(NvcContext* ctx)
+{
+	int current = -1;
+	if (cudaGetDevice(&current) != cudaSuccess || current != ctx->device)
+	{
+		ctx->last_error = "the context's CUDA device is not the calling thread's current device";
+		return false;
+	}
+	return true;
+}
+
 bool fill_hiz(const NvcHiZ* in, nvc::HiZDesc& out)
 {
 	memset(&out, 0, sizeof(out));
@@ -236,6 +249,8 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 		return NVC_ERROR_INVALID_ARGUMENT;
 	if (cull->drawCount && (!draws || !meshes || !draw_visibility))
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
 
 	nvc::DrawCullParams p;
 	memset(&p, 0, sizeof(p));
@@ -267,6 +282,8 @@ static int fill_cluster_params(NvcContext* ctx, const NvcCullData* cull, int lat
 	if (!ctx || !cull || !task_commands || !command_count4 || !draws || !meshlets)
 		return NVC_ERROR_INVALID_ARGUMENT;
 	if (cull->clusterOcclusionEnabled == 1 && !meshlet_visibility)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	memset(&p, 0, sizeof(p));
 	p.cull = *cull;
@@ -339,6 +356,8 @@ NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
     uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz)
 {
 	if (!ctx || !depth || !hiz || depth_width == 0 || depth_height == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	nvc::PyramidParams p;
 	memset(&p, 0, sizeof(p));
