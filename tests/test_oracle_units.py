@@ -256,3 +256,40 @@ def test_decode_clusters_matches_consumer_rule(golden_dir):
     assert np.array_equal(rec[:n, 0], want_draw) and np.array_equal(rec[:n, 1], want_mi)
     assert np.array_equal(rec[:n, 3], s.meshlets["triangleCount"][want_mi]) and stats[3] == s.meshlets["triangleCount"][want_mi].sum()
     assert (rec[n:] == 0xFFFFFFFF).all()
+
+
+def test_two_phase_invariants(golden_dir):
+    """Size-independent properties of the two-phase scheme, on a moving camera:
+    * no meshlet instance is emitted by both the early and the late pass of a frame (no double draw);
+    * every meshlet instance the late pass finds visible was emitted by one of them (nothing missed);
+    * after the late pass dvb / mvb hold exactly the late verdicts; the early pass never changes them."""
+    s = _scene(golden_dir, n=6000, screen=(800, 600))
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen)
+    o.set_visibility_bits(s.visibility_bits)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((12, -4, 9), host.quat_from_axis_angle((0, 1, 0), 0.35)), host.make_camera((25, 3, -14), host.quat_from_axis_angle((0.1, 1, 0), 0.9))]
+    for f in range(4):
+        s.camera = cams[f % len(cams)]
+        cd = s.cull_data()
+        dvb0, mvb0 = o.dvb.copy(), o.mvb.copy()
+        o.cull(cd, late=False)
+        o.render_clusters(cd, late=False, cluster_backface=True)
+        assert np.array_equal(o.dvb, dvb0) and np.array_equal(o.mvb, mvb0)
+        early = oracle_lib.cluster_pairs(o.read_cluster_indices(int(o.ccb[0])), o.read_task_commands(int(o.dccb[1]) * 64))
+        o.pyramid(s.depth)
+        o.cull(cd, late=True)
+        o.render_clusters(cd, late=True, cluster_backface=True)
+        cmds = o.read_task_commands(int(o.dccb[1]) * 64)
+        late = oracle_lib.cluster_pairs(o.read_cluster_indices(int(o.ccb[0])), cmds)
+        assert len(np.intersect1d(early, late)) == 0
+        # late-visible set = set bits of the meshlets the late pass processed
+        live = cmds[cmds["taskCount"] > 0]
+        vis = []
+        for c in live:
+            mvi = c["meshletVisibilityOffset"] + np.arange(c["taskCount"], dtype=np.uint64)
+            bits = (o.mvb[(mvi >> 5).astype(np.int64)] >> (mvi & 31).astype(np.uint32)) & 1
+            mi = c["taskOffset"] + np.nonzero(bits)[0]
+            vis.append((np.uint64(c["drawId"]) << np.uint64(32)) | mi.astype(np.uint64))
+        vis = np.sort(np.concatenate(vis)) if vis else np.zeros(0, np.uint64)
+        both = np.union1d(early, late)
+        assert np.isin(vis, both).all()
+        assert len(late) > 0 or f > 0
