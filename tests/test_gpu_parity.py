@@ -404,3 +404,44 @@ def test_decode_clusters_consumer_walk(golden_dir):
             gv, ov = grec[grec[:, 0] != 0xFFFFFFFF], orec[orec[:, 0] != 0xFFFFFFFF]
             assert len(gv) == n and np.array_equal(key(gv), key(ov))
     assert n >= 0
+
+
+def test_c3_bistro_standin_two_pass(golden_dir):
+    """BASELINE configs[2] stand-in (bistro.gltf is not shipped with the reference): kitten + pirate geometry
+    cooked by the reference's scene.cpp, instanced with its PCG32 recipe to ~3M LOD-0 meshlets, packed around the
+    camera; full two-pass Hi-Z occlusion + meshlet cone cull over three frames with a moving camera, bit-exact, plus the
+    two-phase invariants (no meshlet emitted twice in a frame, every late-visible meshlet emitted once)."""
+    torch = _torch()
+    meshes, meshlets, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten_pirate.nvcg"))
+    n = 16500
+    s = scenes.reference_random_scene(meshes, meshlets, n, screen=(1920, 1080), occluders=80)
+    s.draws["position"] *= 0.3  # +-90 around the origin: most of the scene is inside the 200 draw distance
+    lod0 = int(meshes["lods"]["meshletCount"][s.draws["meshIndex"], 0].sum())
+    assert 2.8e6 < lod0 < 3.3e6
+    g, o, depth = _paths(s)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((8, -2, 15), host.quat_from_axis_angle((0, 1, 0), 0.5)), host.make_camera((-20, 6, 30), host.quat_from_axis_angle((0.2, 1, 0), 2.2))]
+    for f in range(3):
+        s.camera = cams[f]
+        cd = s.cull_data()
+        g.cull(cd, False)
+        o.cull(cd, False)
+        _compare_draw_pass(g, o, True, ("c3 cull early", f))
+        g.render_clusters(cd, False, cluster_backface=True)
+        o.render_clusters(cd, False, cluster_backface=True)
+        _compare_cluster_pass(g, o, ("c3 clusters early", f))
+        gd, gc = g.read_counts()
+        early = oracle_lib.cluster_pairs(g.read_cluster_indices(int(gc[0])), g.read_task_commands(int(gd[1]) * 64))
+        g.pyramid(depth)
+        o.pyramid(s.depth)
+        g.cull(cd, True)
+        o.cull(cd, True)
+        _compare_draw_pass(g, o, True, ("c3 cull late", f))
+        g.render_clusters(cd, True, cluster_backface=True)
+        o.render_clusters(cd, True, cluster_backface=True)
+        _compare_cluster_pass(g, o, ("c3 clusters late", f))
+        gd, gc = g.read_counts()
+        late = oracle_lib.cluster_pairs(g.read_cluster_indices(int(gc[0])), g.read_task_commands(int(gd[1]) * 64))
+        assert len(np.intersect1d(early, late)) == 0
+        rec, stats = g.decode_clusters()
+        assert stats[2] == 0 and stats[0] == gc[0]
+    assert int(o.read_counts()[1][0]) >= 0 and len(early) + len(late) > 10000
