@@ -71,6 +71,31 @@ def profiled_traffic():
     return None
 
 
+def profiled_warp_instructions():
+    """smsp__inst_executed.sum of the late cluster kernel (same committed ncu capture); the static C4 scene executes the
+    same instruction stream every launch."""
+    path = os.path.join(ROOT, "profiles", "r1_frame_ncu_full_summary.json")
+    try:
+        for k in json.load(open(path)):
+            if "clustercull_kernel<1" in k["Kernel Name"]:
+                return float(k["smsp__inst_executed.sum"].split()[0])
+    except Exception:
+        pass
+    return None
+
+
+def issue_roofline(kernel_ms, clocks, args):
+    """The late cluster kernel is bound by instruction issue, not HBM: warp instructions per launch (ncu)
+    over the live kernel time, against 148 SMs x 4 schedulers x 1 instruction / clock at the measured SM clock."""
+    inst = profiled_warp_instructions() if (args.workload == "C4" and args.draws == 1_000_000 and args.meshlets_per_draw == 10) else None
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    if not inst:
+        return None
+    peak = 148 * 4 * mhz * 1e6
+    achieved = inst / (kernel_ms * 1e-3)
+    return {"kernel": "clustercull_kernel<LATE=1>", "warp_instructions_per_launch": inst, "achieved_ginst_s": achieved / 1e9, "peak_ginst_s": peak / 1e9, "frac": achieved / peak, "source": "smsp__inst_executed.sum from profiles/r1_frame_ncu_full_summary.json"}
+
+
 def build_scene(args, rank):
     """Synthetic scene of the workload; cached under /tmp so that several bench invocations in one session (bench,
     ncu launch list, ncu full capture) do not regenerate 0.5 GB of inputs each."""
@@ -541,6 +566,7 @@ def main():
                 "meshlets_per_s_kernel": M / (k_ms * 1e-3),
             },
             "clocks": clocks,
+            "issue_roofline": issue_roofline(k_ms, clocks, args),
             "gpu_launches": (5 + ((3 if sm_push else 2) if gather == "ce" else 0)) * K,
             "gather_transport": ("sm-push" if sm_push else gather),
         }
