@@ -81,7 +81,9 @@ def occlusion_mip(aabb, pw, ph):  # math.h:24-39
         sx = aabb[2] - aabb[0]
         sy = aabb[3] - aabb[1]
         a, b = sx * pw, sy * ph
-        m = np.where(a > b, a, b)
+        # GLSL leaves max() with a NaN operand undefined; like GPU hardware (FMNMX / IEEE maxNum) and the oracle, the
+        # defined operand wins
+        m = np.fmax(a, b)
         pos = m > 0
         L = np.where(pos & np.isfinite(m), ceil_log2_exact(np.where(pos & np.isfinite(m), m, F(1.0))), 0)
         level = np.zeros(m.shape, dtype=np.float32)
