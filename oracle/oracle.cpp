@@ -4,9 +4,13 @@
 // This file is the parity oracle and the reported CPU baseline.  Only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load it; the product (niagara_b200/) never does.
 //
-// PARITY UNPINNED: the reference (zeux/niagara @ 95f289b) has no tests, golden vectors or CPU cull path
-//  and its GLSL cannot be compiled or run here (no Vulkan, no glslang).  This is therefore
-// OUR restatement of the GLSL below, with the interpretation rules of SURVEY.md Appendix C:
+// PARITY: the reference (zeux/niagara @ 95f289b) has no tests, golden vectors or CPU cull path
+// and there is no Vulkan driver or glslang here, so parity against a LIVE VULKAN RUN stays unpinned.  What this
+// restatement IS pinned to: the reference's own shader text executed on the host — oracle/refshader compiles
+// src/shaders/{drawcull,tasksubmit,clustercull,clustersubmit,depthreduce}.comp.glsl and meshlet.task.glsl (with
+// mesh.h / math.h / config.h) through a GLSL shim into oracle/_ref/librefshader.so, and tests/test_refshader.py
+// requires every pass of this file to equal those shaders bit for bit.  What remains an interpretation (shared by
+// this file, the shim and the CUDA path) is what GLSL leaves to the implementation:
 //   * IEEE-754 binary32, round-to-nearest-even, NO fused multiply-add (build with -ffp-contract=off),
 //     operations in GLSL source order and associativity; true division; correctly rounded sqrt.
 //   * ceil(log2(x)) evaluated exactly from the float's exponent/mantissa; exp2(int) exact.

@@ -1,0 +1,392 @@
+// =====================================================================================================
+// driver.cpp — runs the reference's own shaders (compiled through glsl_shim.h, see gen.py) on host arrays.
+// TEST INFRASTRUCTURE ONLY (oracle/_ref/librefshader.so).  It plays the part of niagara.cpp's frame loop for
+// the visibility path: the buffer fills, descriptor bindings, push constants and dispatch sizes below restate
+//   cull lambda      niagara.cpp:1530-1574   fill(dccb,0,4) -> drawcull (ceil(drawCount/64) groups) -> tasksubmit (1 group)
+//   render lambda    niagara.cpp:1582-1610   fill(ccb,0,4)  -> clustercull (indirect dccb+4)       -> clustersubmit (1 group)
+//   task submission  niagara.cpp:1666-1679   vkCmdDrawMeshTasksIndirectEXT(dccb+4) with meshlet.task
+//   pyramid lambda   niagara.cpp:1703-1733   per mip: depthreduce over ceil(w/32) x ceil(h/32) groups
+// Workgroups of one dispatch are spread over host threads (the shaders' atomics are real atomics); the invocations
+// of a workgroup run in ascending gl_LocalInvocationIndex order on one thread, as fibers when the shader uses
+// barrier().  Output order therefore differs from run to run exactly as on a GPU; compare as sets.
+// =====================================================================================================
+#include "../../include/niagara_cull.h"
+#include "glsl_shim.h"
+#include "rs_shader.h"
+
+#include <stdio.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
+#include <vector>
+
+namespace glsl
+{
+thread_local uvec3 gl_GlobalInvocationID, gl_LocalInvocationID, gl_WorkGroupID;
+thread_local uint gl_LocalInvocationIndex;
+} // namespace glsl
+
+extern const RsShader rs_shader_drawcull, rs_shader_tasksubmit, rs_shader_clustercull, rs_shader_clustersubmit, rs_shader_depthreduce, rs_shader_meshlet_task;
+
+namespace
+{
+
+using glsl::uint;
+
+// ---- fibers: one per invocation of a workgroup whose shader calls barrier() ---------------------------------------
+struct Fiber
+{
+	ucontext_t ctx;
+	std::vector<char> stack;
+	bool done = false;
+};
+
+thread_local ucontext_t* t_scheduler = nullptr;
+thread_local Fiber* t_current = nullptr;
+thread_local void (*t_main)() = nullptr;
+thread_local uint t_emit[3];
+
+void fiberEntry()
+{
+	t_main();
+	t_current->done = true;
+	swapcontext(&t_current->ctx, t_scheduler);
+}
+
+void setInvocation(const uint* ls, uint gx, uint gy, uint gz, uint lx, uint ly, uint lz)
+{
+	glsl::gl_WorkGroupID = glsl::uvec3(gx, gy, gz);
+	glsl::gl_LocalInvocationID = glsl::uvec3(lx, ly, lz);
+	glsl::gl_GlobalInvocationID = glsl::uvec3(gx * ls[0] + lx, gy * ls[1] + ly, gz * ls[2] + lz);
+	glsl::gl_LocalInvocationIndex = (lz * ls[1] + ly) * ls[0] + lx;
+}
+
+void runGroup(const RsShader& s, uint gx, uint gy, uint gz)
+{
+	const uint* ls = s.local_size;
+	uint count = ls[0] * ls[1] * ls[2];
+	if (!s.uses_barrier)
+	{
+		for (uint i = 0; i < count; ++i)
+		{
+			setInvocation(ls, gx, gy, gz, i % ls[0], (i / ls[0]) % ls[1], i / (ls[0] * ls[1]));
+			s.main();
+		}
+		return;
+	}
+
+	static thread_local std::vector<Fiber> fibers;
+	fibers.resize(count);
+	ucontext_t scheduler;
+	t_scheduler = &scheduler;
+	t_main = s.main;
+	for (uint i = 0; i < count; ++i)
+	{
+		Fiber& f = fibers[i];
+		f.done = false;
+		f.stack.resize(256 * 1024);
+		getcontext(&f.ctx);
+		f.ctx.uc_stack.ss_sp = f.stack.data();
+		f.ctx.uc_stack.ss_size = f.stack.size();
+		f.ctx.uc_link = nullptr;
+		makecontext(&f.ctx, fiberEntry, 0);
+	}
+	// every pass resumes each live invocation once; an invocation returns here at its next barrier() or at its end
+	for (bool live = true; live;)
+	{
+		live = false;
+		for (uint i = 0; i < count; ++i)
+		{
+			Fiber& f = fibers[i];
+			if (f.done)
+				continue;
+			setInvocation(ls, gx, gy, gz, i % ls[0], (i / ls[0]) % ls[1], i / (ls[0] * ls[1]));
+			t_current = &f;
+			swapcontext(&scheduler, &f.ctx);
+			live = live || !f.done;
+		}
+	}
+	t_scheduler = nullptr;
+}
+
+// vkCmdDispatch(x, y, z): groups spread over `threads` host threads; after(gx, gy, gz) runs on the group's thread
+void dispatch(const RsShader& s, uint x, uint y, uint z, int threads, const std::function<void(uint, uint, uint)>& after = nullptr)
+{
+	uint64_t total = uint64_t(x) * y * z;
+	if (total == 0)
+		return;
+	std::atomic<uint64_t> next{ 0 };
+	const uint64_t chunk = 16;
+	auto worker = [&]() {
+		for (;;)
+		{
+			uint64_t b = next.fetch_add(chunk);
+			if (b >= total)
+				return;
+			for (uint64_t g = b; g < std::min(total, b + chunk); ++g)
+			{
+				uint gx = uint(g % x), gy = uint((g / x) % y), gz = uint(g / (uint64_t(x) * y));
+				runGroup(s, gx, gy, gz);
+				if (after)
+					after(gx, gy, gz);
+			}
+		}
+	};
+	int nt = int(std::min<uint64_t>(uint64_t(std::max(1, threads)), (total + chunk - 1) / chunk));
+	if (nt <= 1)
+		return worker();
+	std::vector<std::thread> pool;
+	for (int t = 0; t < nt; ++t)
+		pool.emplace_back(worker);
+	for (std::thread& t : pool)
+		t.join();
+}
+
+glsl::texture2D pyramidView(const NvcHiZ* hiz)
+{
+	glsl::texture2D t = {};
+	if (!hiz || !hiz->texels)
+		return t;
+	t.levels = hiz->levels;
+	for (uint l = 0; l < hiz->levels; ++l)
+	{
+		t.texels[l] = hiz->texels + hiz->level_offset[l];
+		t.width[l] = std::max(1u, hiz->width >> l);
+		t.height[l] = std::max(1u, hiz->height >> l);
+	}
+	return t;
+}
+
+// Globals of meshlet.task.glsl (mesh.h): projection (unused by the task stage), CullData, screen size
+struct TaskGlobals
+{
+	float projection[16];
+	NvcCullData cullData;
+	float screenWidth, screenHeight;
+};
+
+} // namespace
+
+// the reference's mesh.h once more, only to check that the shim's types give its structs the layout of the host arrays
+namespace glsl
+{
+namespace rs_layout
+{
+#include "mesh.h"
+static_assert(sizeof(MeshDraw) == sizeof(NvcMeshDraw) && sizeof(Mesh) == sizeof(NvcMesh) && sizeof(MeshLod) == 20, "MeshDraw / Mesh");
+static_assert(sizeof(Meshlet) == sizeof(NvcMeshlet) && sizeof(CullData) == sizeof(NvcCullData), "Meshlet / CullData");
+static_assert(sizeof(MeshTaskCommand) == sizeof(NvcMeshTaskCommand) && sizeof(MeshDrawCommand) == sizeof(NvcMeshDrawCommand), "commands");
+static_assert(sizeof(MeshTaskPayload) == sizeof(NvcMeshTaskPayload), "payload");
+static_assert(offsetof(Globals, cullData) == 64 && offsetof(Globals, screenWidth) == 64 + sizeof(NvcCullData), "Globals");
+static_assert(offsetof(Mesh, lods) == offsetof(NvcMesh, lods) && offsetof(MeshDraw, meshIndex) == offsetof(NvcMeshDraw, meshIndex), "offsets");
+static_assert(offsetof(CullData, drawCount) == offsetof(NvcCullData, drawCount) && offsetof(CullData, postPass) == offsetof(NvcCullData, postPass), "CullData offsets");
+} // namespace rs_layout
+} // namespace glsl
+
+namespace
+{
+
+static_assert(sizeof(glsl::float16_t) == 2, "float16_t must be storage compatible");
+static_assert(sizeof(glsl::vec3) == 12 && sizeof(glsl::vec4) == 16 && sizeof(glsl::mat4) == 64, "std430 layouts used by mesh.h");
+
+} // namespace
+
+namespace glsl
+{
+
+void barrier()
+{
+	if (t_scheduler)
+		swapcontext(&t_current->ctx, t_scheduler);
+}
+
+void EmitMeshTasksEXT(uint x, uint y, uint z)
+{
+	t_emit[0] = x;
+	t_emit[1] = y;
+	t_emit[2] = z;
+}
+
+} // namespace glsl
+
+extern "C"
+{
+
+// names of the shader files this library was generated from (space separated)
+const char* rs_sources(void)
+{
+	static char buf[512];
+	snprintf(buf, sizeof(buf), "%s %s %s %s %s %s", rs_shader_drawcull.source, rs_shader_tasksubmit.source, rs_shader_clustercull.source,
+	    rs_shader_clustersubmit.source, rs_shader_depthreduce.source, rs_shader_meshlet_task.source);
+	return buf;
+}
+
+int rs_drawcull(const NvcCullData* pass, int late, int task, const void* draws, size_t draws_bytes, const void* meshes, size_t meshes_bytes,
+    uint32_t* draw_visibility, size_t dvb_bytes, void* commands, size_t commands_bytes, uint32_t* command_count4, const NvcHiZ* hiz, int threads)
+{
+	glsl::texture2D pyramid = pyramidView(hiz);
+	if (late && pass->occlusionEnabled == 1 && pyramid.levels == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	command_count4[0] = 0; // vkCmdFillBuffer(dccb, 0, 4, 0)
+
+	const RsShader& s = rs_shader_drawcull;
+	s.spec(0, late);
+	s.spec(1, task);
+	s.bind(0, const_cast<void*>(draws), draws_bytes);
+	s.bind(1, const_cast<void*>(meshes), meshes_bytes);
+	s.bind(2, commands, commands_bytes); // DrawCommands and TaskCommands alias binding 2
+	s.bind(3, command_count4, 16);
+	s.bind(4, draw_visibility, dvb_bytes);
+	s.bind(5, &pyramid, sizeof(pyramid));
+	s.bind(6, nullptr, 0);
+	s.push(pass, sizeof(*pass));
+	dispatch(s, (pass->drawCount + s.local_size[0] - 1) / s.local_size[0], 1, 1, threads);
+
+	if (task)
+	{
+		const RsShader& ts = rs_shader_tasksubmit;
+		ts.bind(0, command_count4, 16);
+		ts.bind(1, commands, commands_bytes);
+		dispatch(ts, 1, 1, 1, 1);
+	}
+	return NVC_OK;
+}
+
+int rs_clustercull(const NvcCullData* pass, int late, const void* task_commands, size_t commands_bytes, const uint32_t* command_count4,
+    const void* draws, size_t draws_bytes, const void* meshlets, size_t meshlets_bytes, uint32_t* meshlet_visibility, size_t mvb_bytes,
+    uint32_t* cluster_indices, size_t cib_bytes, uint32_t* cluster_count4, const NvcHiZ* hiz, int threads)
+{
+	glsl::texture2D pyramid = pyramidView(hiz);
+	if (late && pass->clusterOcclusionEnabled == 1 && pyramid.levels == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	cluster_count4[0] = 0; // vkCmdFillBuffer(ccb, 0, 4, 0)
+
+	const RsShader& s = rs_shader_clustercull;
+	s.spec(0, late);
+	s.bind(0, const_cast<void*>(task_commands), commands_bytes);
+	s.bind(1, const_cast<void*>(draws), draws_bytes);
+	s.bind(2, const_cast<void*>(meshlets), meshlets_bytes);
+	s.bind(3, meshlet_visibility, mvb_bytes);
+	s.bind(4, &pyramid, sizeof(pyramid));
+	s.bind(5, cluster_indices, cib_bytes);
+	s.bind(6, cluster_count4, 16);
+	s.bind(7, nullptr, 0);
+	s.push(pass, sizeof(*pass));
+	dispatch(s, command_count4[1], command_count4[2], command_count4[3], threads); // vkCmdDispatchIndirect(dccb, 4)
+
+	const RsShader& cs = rs_shader_clustersubmit;
+	cs.bind(0, cluster_count4, 16);
+	cs.bind(1, cluster_indices, cib_bytes);
+	dispatch(cs, 1, 1, 1, 1);
+	return NVC_OK;
+}
+
+int rs_taskcull(const NvcCullData* pass, int late, const void* task_commands, size_t commands_bytes, const uint32_t* command_count4,
+    const void* draws, size_t draws_bytes, const void* meshlets, size_t meshlets_bytes, uint32_t* meshlet_visibility, size_t mvb_bytes,
+    NvcMeshTaskPayload* payloads, uint32_t* emit_counts, const NvcHiZ* hiz, int threads)
+{
+	glsl::texture2D pyramid = pyramidView(hiz);
+	if (late && pass->clusterOcclusionEnabled == 1 && pyramid.levels == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+
+	TaskGlobals globals = {};
+	globals.cullData = *pass;
+
+	const RsShader& s = rs_shader_meshlet_task;
+	s.spec(0, late);
+	s.bind(0, const_cast<void*>(task_commands), commands_bytes);
+	s.bind(1, const_cast<void*>(draws), draws_bytes);
+	s.bind(2, const_cast<void*>(meshlets), meshlets_bytes);
+	s.bind(5, meshlet_visibility, mvb_bytes);
+	s.bind(6, &pyramid, sizeof(pyramid));
+	s.bind(9, nullptr, 0);
+	s.push(&globals, sizeof(globals));
+	uint gx = command_count4[1], gy = command_count4[2];
+	dispatch(s, gx, gy, command_count4[3], threads, [&](uint x, uint y, uint) {
+		uint commandId = x * 64 + y;
+		emit_counts[commandId] = t_emit[0];
+		memcpy(&payloads[commandId], s.payload(), sizeof(NvcMeshTaskPayload));
+	});
+	return NVC_OK;
+}
+
+int rs_depth_pyramid(const float* depth, uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz, int threads)
+{
+	const RsShader& s = rs_shader_depthreduce;
+	glsl::texture2D source = {};
+	source.levels = 1;
+	source.texels[0] = depth;
+	source.width[0] = depth_width;
+	source.height[0] = depth_height;
+
+	for (uint32_t i = 0; i < hiz->levels; ++i)
+	{
+		uint32_t levelWidth = std::max(1u, hiz->width >> i), levelHeight = std::max(1u, hiz->height >> i);
+		glsl::image2D target = { hiz->texels + hiz->level_offset[i], levelWidth, levelHeight };
+		float reduceData[4] = { float(levelWidth), float(levelHeight), 0, 0 };
+
+		s.bind(0, &target, sizeof(target));
+		s.bind(1, &source, sizeof(source));
+		s.bind(2, nullptr, 0);
+		s.push(reduceData, sizeof(reduceData));
+		dispatch(s, (levelWidth + s.local_size[0] - 1) / s.local_size[0], (levelHeight + s.local_size[1] - 1) / s.local_size[1], 1, threads);
+
+		source.texels[0] = target.texels; // mipSource = mipTarget
+		source.width[0] = levelWidth;
+		source.height[0] = levelHeight;
+	}
+	return NVC_OK;
+}
+
+// ---- math.h functions of the reference, exported for scalar cross-checks (they live in every shader TU; the
+// ---- drawcull one is used) ------------------------------------------------------------------------------------------
+} // extern "C"
+
+namespace glsl
+{
+namespace rs_drawcull
+{
+bool projectSphere(vec3 c, float r, float znear, float P00, float P11, vec4& aabb);
+float getOcclusionMip(vec4 aabb, float pyramidWidth, float pyramidHeight);
+bool coneCull(vec3 center, float radius, vec3 cone_axis, float cone_cutoff, vec3 camera_position);
+vec3 rotateQuat(vec3 v, vec4 q);
+} // namespace rs_drawcull
+} // namespace glsl
+
+extern "C"
+{
+
+int rs_project_sphere(const float c[3], float r, float znear, float P00, float P11, float aabb[4])
+{
+	glsl::vec4 a;
+	bool ok = glsl::rs_drawcull::projectSphere(glsl::vec3(c[0], c[1], c[2]), r, znear, P00, P11, a);
+	if (ok)
+		for (int i = 0; i < 4; ++i)
+			aabb[i] = a[i];
+	return ok ? 1 : 0;
+}
+
+float rs_occlusion_mip(const float aabb[4], float pw, float ph)
+{
+	return glsl::rs_drawcull::getOcclusionMip(glsl::vec4(aabb[0], aabb[1], aabb[2], aabb[3]), pw, ph);
+}
+
+int rs_cone_cull(const float center[3], float radius, const float axis[3], float cutoff)
+{
+	return glsl::rs_drawcull::coneCull(glsl::vec3(center[0], center[1], center[2]), radius, glsl::vec3(axis[0], axis[1], axis[2]), cutoff, glsl::vec3(0, 0, 0)) ? 1 : 0;
+}
+
+void rs_rotate_quat(const float v[3], const float q[4], float out[3])
+{
+	glsl::vec3 r = glsl::rs_drawcull::rotateQuat(glsl::vec3(v[0], v[1], v[2]), glsl::vec4(q[0], q[1], q[2], q[3]));
+	out[0] = r.x;
+	out[1] = r.y;
+	out[2] = r.z;
+}
+
+} // extern "C"

@@ -19,12 +19,12 @@ def _torch():
     return torch
 
 
-def _paths(s, hiz_stage_texels=None, prepare_meshes=True, **kw):
+def _paths(s, hiz_stage_texels=None, prepare_meshes=True, checker=None, **kw):
     from niagara_b200.path import VisibilityPath
 
     torch = _torch()
     g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, hiz_stage_texels=hiz_stage_texels, prepare_meshes=prepare_meshes, **kw)
-    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8, **kw)
+    o = (checker or oracle_lib.OraclePath)(s.meshes, s.meshlets, s.draws, *s.screen, threads=8, **kw)
     g.set_visibility_bits(s.visibility_bits)
     o.set_visibility_bits(s.visibility_bits)
     depth = torch.from_numpy(s.depth).cuda()
@@ -91,6 +91,23 @@ def test_kitten_4096_two_phase(golden_dir):
     s = scenes.instanced_scene(os.path.join(golden_dir, "kitten.nvcg"), 4096)
     g, o = _run_frames(s, frames=3)
     assert o.read_counts()[0][0] > 0
+
+
+def test_cuda_vs_reference_shaders(golden_dir):
+    """The CUDA path against the reference's OWN GLSL shaders run on the host (oracle/_ref/librefshader.so: the text of
+    src/shaders/*.glsl compiled through oracle/refshader/glsl_shim.h by build(); the prebuilt library travels to the
+    GPU box).  Same bar as against the oracle: bit-exact, order inside dcb / cib aside."""
+    import refshader_lib
+
+    if not refshader_lib.available():
+        pytest.skip("oracle/_ref/librefshader.so was not built (needs /root/reference at build time)")
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 20000, screen=(1280, 720))
+    g, r = _run_frames(s, frames=2, checker=refshader_lib.RefShaderPath)
+    assert r.read_counts()[0][0] > 0
+    s = scenes.config2_scene(draw_count=50000, num_meshes=256, screen=(1024, 1024))
+    _run_frames(s, frames=2, checker=refshader_lib.RefShaderPath)
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten.nvcg"), 3000)
+    _run_frames(s, frames=2, checker=refshader_lib.RefShaderPath, toggles=dict(mesh_shading=False, cluster_occlusion=False), mesh_shading=False)
 
 
 @pytest.mark.parametrize(
