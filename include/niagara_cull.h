@@ -171,7 +171,9 @@ typedef enum NvcStatus
 	NVC_ERROR_CUDA = -2,
 	NVC_ERROR_NO_DEVICE = -3,
 	NVC_ERROR_OUT_OF_MEMORY = -4,
-	NVC_ERROR_NCCL = -5
+	NVC_ERROR_NCCL = -5,
+	NVC_ERROR_UNSUPPORTED = -6, /* valid input this build has no decoder for (see nvc_scene_cache_read) */
+	NVC_ERROR_CORRUPT = -7      /* a scene cache whose sections do not add up */
 } NvcStatus;
 
 typedef struct NvcContext NvcContext;
@@ -330,6 +332,108 @@ NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t*
  * the valid count x 20 bytes with 16-byte peer stores (also selectable with NVC_GATHER_MODE=sm) */
 NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push);
 
+/* ---- widening N2: scene cache (.cache v7) reader — the on-disk format that feeds the path ----------------
+ * Replaces loadSceneCache (src/scenecache.cpp:273-370) for the arrays the visibility path consumes.  Host-only, no
+ * CUDA calls: the caller maps the file, parses it once and copies Meshlet[] / Mesh[] / MeshDraw[] / Animation[] /
+ * Keyframe[] straight from the mapping to the device (they are stored raw, scenecache.cpp:170,181-186).  The
+ * meshopt-compressed sections are located by the header's byte counts; the per-meshlet stream ("meshlet codec",
+ * scenecache.cpp:84-117,256-271) has a decoder here, the vertex / index / RT-position streams (rendering data, not
+ * read by the visibility path) are reported with their extents and NVC_ERROR_UNSUPPORTED on read. */
+
+#define NVC_SCENE_CACHE_MAGIC 0x434E4353u /* 'SCNC', scenecache.cpp:12 */
+#define NVC_SCENE_CACHE_VERSION 7u        /* scenecache.cpp:13 */
+
+/* scenecache.cpp:16-55 — 160 bytes */
+typedef struct NvcSceneCacheHeader
+{
+	uint32_t magic, version;
+	uint64_t hashMeta;
+	uint32_t meshletMaxVertices, meshletMaxTriangles;
+	uint8_t clrtMode, compressed, pad0_[2];
+	uint32_t compressedVertexBytes, compressedIndexBytes, compressedMeshletDataBytes, compressedMeshletVtx0Bytes;
+	uint32_t vertexCount, indexCount, meshletCount, meshletdataCount, meshletvtx0Count, meshCount;
+	uint32_t materialCount, drawCount, texturePathCount, lightCount, animationCount, keyframeCount;
+	uint32_t ommArrayDataSize, ommIndexDataSize, ommDescCount, ommStates;
+	NvcCamera camera;
+	float sunDirection[3];
+	uint32_t pad1_;
+} NvcSceneCacheHeader;
+
+/* sections in file order (saveSceneCache, scenecache.cpp:158-197) */
+typedef enum NvcSceneCacheSectionId
+{
+	NVC_CACHE_VERTICES = 0, /* Vertex 16 B, vertex codec when compressed */
+	NVC_CACHE_INDICES,      /* uint32, index codec when compressed */
+	NVC_CACHE_MESHLETS,     /* Meshlet 24 B, always raw */
+	NVC_CACHE_MESHLETDATA,  /* uint32 words, meshlet codec when compressed */
+	NVC_CACHE_MESHLETVTX0,  /* uint16, vertex codec (stride 8) when compressed */
+	NVC_CACHE_MESHES,       /* Mesh 208 B */
+	NVC_CACHE_MATERIALS,    /* Material 64 B */
+	NVC_CACHE_DRAWS,        /* MeshDraw 48 B */
+	NVC_CACHE_LIGHTS,       /* Light 32 B */
+	NVC_CACHE_ANIMATIONS,   /* Animation 24 B */
+	NVC_CACHE_KEYFRAMES,    /* Keyframe 32 B */
+	NVC_CACHE_OMM_DATA,     /* bytes */
+	NVC_CACHE_OMM_INDICES,  /* bytes */
+	NVC_CACHE_OMM_DESCS,    /* uint32 */
+	NVC_CACHE_TEXTURE_PATHS, /* char[256] each */
+	NVC_CACHE_SECTION_COUNT
+} NvcSceneCacheSectionId;
+
+typedef struct NvcSceneCacheSection
+{
+	uint64_t offset;        /* from the start of the file */
+	uint64_t stored_bytes;  /* bytes occupied in the file */
+	uint64_t decoded_bytes; /* count * element_size */
+	uint32_t count, element_size;
+	uint32_t compressed;    /* 1: stored_bytes is a meshopt stream, not the array */
+	uint32_t pad_;
+} NvcSceneCacheSection;
+
+typedef struct NvcSceneCacheInfo
+{
+	NvcSceneCacheHeader header;
+	NvcSceneCacheSection sections[NVC_CACHE_SECTION_COUNT];
+} NvcSceneCacheInfo;
+
+/* scene.h:141-161 */
+typedef struct NvcKeyframe
+{
+	float translation[3];
+	float scale;
+	float rotation[4]; /* x,y,z,w */
+} NvcKeyframe;
+
+typedef struct NvcAnimation
+{
+	int32_t drawIndex, lightIndex;
+	float startTime, period;
+	uint32_t keyframeOffset, keyframeCount;
+} NvcAnimation;
+
+/* Validates magic / version / that every section lies inside the file (and, when compressed, that the per-meshlet
+ * stream's size chain adds up to compressedMeshletDataBytes), fills the section table.  The caller decides about
+ * hashMeta / meshlet limits / clrtMode / ommStates (loadSceneCache's other rejections, scenecache.cpp:283-290). */
+NVC_API int nvc_scene_cache_parse(const void* file, size_t file_size, NvcSceneCacheInfo* out);
+/* Copies (raw sections) or decodes (compressed NVC_CACHE_MESHLETDATA) one section into dst[decoded_bytes]. */
+NVC_API int nvc_scene_cache_read(const void* file, size_t file_size, const NvcSceneCacheInfo* info, int section,
+    void* dst, size_t dst_bytes);
+
+/* ---- widening N3: animated MeshDraw updates (niagara.cpp:1362-1411, the frame loop's keyframe evaluation) --------------
+ * Host: evaluates every animation with drawIndex >= 0 at animation_time exactly as the reference does (double index
+ * arithmetic, glm::mix for position / scale, glm::slerp for orientation), writes the new values into draws[] (the
+ * reference's `draws[animation.drawIndex]`) and appends {index, MeshDraw} to the packed update list.  Returns the
+ * number of updates written (<= max_updates), or a negative NvcStatus. */
+NVC_API int nvc_host_animate(const NvcAnimation* animations, uint32_t animation_count, const NvcKeyframe* keyframes,
+    uint32_t keyframe_count, double animation_time, NvcMeshDraw* draws, uint32_t draw_count,
+    uint32_t* update_indices, NvcMeshDraw* update_values, uint32_t max_updates);
+/* Device: draws[update_indices[i]] = update_values[i] for i < count (the reference memcpy's into its host-visible
+ * `db`, niagara.cpp:1394-1395; here the packed list is one H2D copy and one scatter launch).  Indices >= draw_count
+ * are ignored; indices must be unique (the importer gives every animation its own draw, scene.cpp:777) — with
+ * duplicates one of the values lands, unspecified which. */
+NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, uint32_t draw_count,
+    const uint32_t* update_indices, const NvcMeshDraw* update_values, uint32_t count);
+
 #ifdef __cplusplus
 } /* extern "C" */
 
@@ -351,6 +455,10 @@ static_assert(offsetof(NvcCullData, lodTarget) == 96, "CullData::lodTarget offse
 static_assert(offsetof(NvcCullData, drawCount) == 108, "CullData::drawCount offset");
 static_assert(offsetof(NvcCullData, clusterBackfaceEnabled) == 128, "CullData::clusterBackfaceEnabled offset");
 static_assert(offsetof(NvcCullData, postPass) == 132, "CullData::postPass offset");
+static_assert(sizeof(NvcSceneCacheHeader) == 160, "SceneHeader must match src/scenecache.cpp:16-55");
+static_assert(offsetof(NvcSceneCacheHeader, compressedVertexBytes) == 28 && offsetof(NvcSceneCacheHeader, vertexCount) == 44, "SceneHeader offsets");
+static_assert(offsetof(NvcSceneCacheHeader, camera) == 108 && offsetof(NvcSceneCacheHeader, sunDirection) == 144, "SceneHeader offsets");
+static_assert(sizeof(NvcKeyframe) == 32 && sizeof(NvcAnimation) == 24, "Keyframe / Animation must match src/scene.h:141-161");
 #endif
 
 #endif /* NIAGARA_CULL_H */

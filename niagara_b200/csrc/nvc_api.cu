@@ -105,6 +105,10 @@ NVC_API const char* nvc_status_string(int status)
 		return "out of memory";
 	case NVC_ERROR_NCCL:
 		return "NCCL error";
+	case NVC_ERROR_UNSUPPORTED:
+		return "unsupported input";
+	case NVC_ERROR_CORRUPT:
+		return "corrupt scene cache";
 	default:
 		return "unknown status";
 	}
@@ -373,6 +377,19 @@ NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
 	p.scratch = ctx->scratch;
 	cudaError_t e = nvc::launch_pyramid(p, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_depth_pyramid");
+}
+
+NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices,
+    const NvcMeshDraw* update_values, uint32_t count)
+{
+	if (!ctx || !draws || (count && (!update_indices || !update_values)))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if ((reinterpret_cast<uintptr_t>(draws) | reinterpret_cast<uintptr_t>(update_values)) & 15u)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaError_t e = nvc::launch_update_draws(draws, draw_count, update_indices, update_values, count, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_update_draws");
 }
 
 } // extern "C"

@@ -301,4 +301,79 @@ NVC_API void nvc_host_pass_data(const NvcCullData* frame, int for_drawcull, uint
 	*out = pass;
 }
 
+// ---- N3: keyframe evaluation of the frame loop, niagara.cpp:1362-1390 (draw branch) ---------------------------------
+// glm::mix(x, y, a) = x * (1 - a) + y * a (detail/func_common.inl:104-112); glm::slerp (ext/quaternion_common.inl:41-73):
+// dot = (w*w' + x*x') + (y*y' + z*z'), negate y when dot < 0, lerp when dot > 1 - FLT_EPSILON, else
+// (sin((1 - a) * angle) * x + sin(a * angle) * z) / sin(angle) with angle = acos(dot) — same libm calls as glm makes.
+static inline float mix1(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+
+NVC_API int nvc_host_animate(const NvcAnimation* animations, uint32_t animation_count, const NvcKeyframe* keyframes, uint32_t keyframe_count,
+    double animation_time, NvcMeshDraw* draws, uint32_t draw_count, uint32_t* update_indices, NvcMeshDraw* update_values, uint32_t max_updates)
+{
+	if ((animation_count && (!animations || !keyframes)) || !draws)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	uint32_t updates = 0;
+	for (uint32_t ai = 0; ai < animation_count; ++ai)
+	{
+		const NvcAnimation& animation = animations[ai];
+		if (animation.keyframeCount == 0 || uint64_t(animation.keyframeOffset) + animation.keyframeCount > keyframe_count)
+			return NVC_ERROR_INVALID_ARGUMENT;
+
+		double index = (animation_time - animation.startTime) / animation.period; // :1368
+		if (index < 0)
+			continue;
+		index = fmod(index, double(animation.keyframeCount)); // :1373
+
+		uint32_t index0 = uint32_t(int(index)) % animation.keyframeCount; // :1375-1376
+		uint32_t index1 = (index0 + 1) % animation.keyframeCount;
+		float t = float(index - floor(index)); // :1378, used as float(t)
+
+		const NvcKeyframe& k0 = keyframes[animation.keyframeOffset + index0];
+		const NvcKeyframe& k1 = keyframes[animation.keyframeOffset + index1];
+
+		if (animation.drawIndex < 0)
+			continue; // light animations (:1403-1410) are not part of the visibility path
+		if (uint32_t(animation.drawIndex) >= draw_count)
+			return NVC_ERROR_INVALID_ARGUMENT;
+
+		NvcMeshDraw& draw = draws[animation.drawIndex];
+		for (int c = 0; c < 3; ++c)
+			draw.position[c] = mix1(k0.translation[c], k1.translation[c], t); // :1386
+		draw.scale = mix1(k0.scale, k1.scale, t);                             // :1387
+
+		// :1388 glm::slerp(keyframe0.rotation, keyframe1.rotation, float(t)); rotation[] = x, y, z, w
+		const float* x = k0.rotation;
+		float z[4] = { k1.rotation[0], k1.rotation[1], k1.rotation[2], k1.rotation[3] };
+		float cosTheta = (x[3] * z[3] + x[0] * z[0]) + (x[1] * z[1] + x[2] * z[2]);
+		if (cosTheta < 0.0f)
+		{
+			for (int c = 0; c < 4; ++c)
+				z[c] = -z[c];
+			cosTheta = -cosTheta;
+		}
+		if (cosTheta > 1.0f - 1.1920928955078125e-07f)
+		{
+			for (int c = 0; c < 4; ++c)
+				draw.orientation[c] = mix1(x[c], z[c], t);
+		}
+		else
+		{
+			float angle = acosf(cosTheta);
+			float s0 = sinf((1.0f - t) * angle), s1 = sinf(t * angle), sd = sinf(angle);
+			for (int c = 0; c < 4; ++c)
+				draw.orientation[c] = (x[c] * s0 + z[c] * s1) / sd;
+		}
+
+		if (update_indices && update_values)
+		{
+			if (updates >= max_updates)
+				return NVC_ERROR_INVALID_ARGUMENT;
+			update_indices[updates] = uint32_t(animation.drawIndex);
+			update_values[updates] = draw;
+		}
+		++updates;
+	}
+	return int(updates);
+}
+
 } // extern "C"

@@ -1321,6 +1321,29 @@ cudaError_t launch_decode_clusters(const uint32_t* cluster_indices, const uint32
 	return cudaGetLastError();
 }
 
+// N3: draws[update_indices[i]] = update_values[i]; one thread per 16-byte third of a 48-byte MeshDraw
+__global__ void update_draws_kernel(NvcMeshDraw* __restrict__ draws, uint32_t draw_count, const uint32_t* __restrict__ update_indices,
+    const NvcMeshDraw* __restrict__ update_values, uint32_t count)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t i = t / 3u, part = t - i * 3u;
+	if (i >= count)
+		return;
+	uint32_t di = __ldg(update_indices + i);
+	if (di >= draw_count)
+		return;
+	reinterpret_cast<uint4*>(draws)[size_t(di) * 3u + part] = __ldg(reinterpret_cast<const uint4*>(update_values) + size_t(i) * 3u + part);
+}
+
+cudaError_t launch_update_draws(NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices, const NvcMeshDraw* update_values, uint32_t count, cudaStream_t stream)
+{
+	if (count == 0)
+		return cudaSuccess;
+	uint64_t threads = uint64_t(count) * 3u;
+	update_draws_kernel<<<uint32_t((threads + 255u) / 256u), 256, 0, stream>>>(draws, draw_count, update_indices, update_values, count);
+	return cudaGetLastError();
+}
+
 __global__ void pack_meshes_kernel(const NvcMesh* __restrict__ meshes, uint32_t count, MeshCullHead* __restrict__ heads, float* __restrict__ errors)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -62,3 +62,23 @@ def quat_from_axis_angle(axis, angle):
     ax = ax / np.linalg.norm(ax)
     s = math.sin(angle * 0.5)
     return (float(ax[0] * s), float(ax[1] * s), float(ax[2] * s), float(math.cos(angle * 0.5)))
+
+
+def animate(animations, keyframes, animation_time, draws):
+    """niagara.cpp:1362-1390: evaluates the keyframe tracks at animation_time into draws (in place) and returns the
+    packed update list (indices uint32[n], values MeshDraw[n]) for VisibilityPath.update_draws."""
+    import ctypes
+
+    import numpy as np
+
+    from . import layout
+    from .lib import NvcError, load_library
+
+    n = len(animations)
+    idx = np.zeros(max(n, 1), dtype=np.uint32)
+    val = np.zeros(max(n, 1), dtype=layout.MESHDRAW_DTYPE)
+    lib = load_library()
+    got = lib.nvc_host_animate(animations.ctypes.data if n else None, n, keyframes.ctypes.data if len(keyframes) else None, len(keyframes), float(animation_time), draws.ctypes.data, len(draws), idx.ctypes.data, val.ctypes.data, len(idx))
+    if got < 0:
+        raise NvcError("nvc_host_animate: " + lib.nvc_status_string(got).decode())
+    return idx[:got], val[:got]

@@ -190,6 +190,68 @@ class CullOptions(ctypes.Structure):
 
 assert ctypes.sizeof(CullData) == 144
 
+# scene.h:141-161 — animation tracks of the scene cache (widening N3)
+KEYFRAME_DTYPE = np.dtype([("translation", "<f4", (3,)), ("scale", "<f4"), ("rotation", "<f4", (4,))])
+ANIMATION_DTYPE = np.dtype([("drawIndex", "<i4"), ("lightIndex", "<i4"), ("startTime", "<f4"), ("period", "<f4"), ("keyframeOffset", "<u4"), ("keyframeCount", "<u4")])
+assert KEYFRAME_DTYPE.itemsize == 32 and ANIMATION_DTYPE.itemsize == 24
+
+CACHE_SECTIONS = ["vertices", "indices", "meshlets", "meshletdata", "meshletvtx0", "meshes", "materials", "draws", "lights", "animations", "keyframes", "omm_data", "omm_indices", "omm_descs", "texture_paths"]
+
+
+class SceneCacheHeader(ctypes.Structure):  # scenecache.cpp:16-55
+    _fields_ = [
+        ("magic", ctypes.c_uint32),
+        ("version", ctypes.c_uint32),
+        ("hashMeta", ctypes.c_uint64),
+        ("meshletMaxVertices", ctypes.c_uint32),
+        ("meshletMaxTriangles", ctypes.c_uint32),
+        ("clrtMode", ctypes.c_uint8),
+        ("compressed", ctypes.c_uint8),
+        ("pad0_", ctypes.c_uint8 * 2),
+        ("compressedVertexBytes", ctypes.c_uint32),
+        ("compressedIndexBytes", ctypes.c_uint32),
+        ("compressedMeshletDataBytes", ctypes.c_uint32),
+        ("compressedMeshletVtx0Bytes", ctypes.c_uint32),
+        ("vertexCount", ctypes.c_uint32),
+        ("indexCount", ctypes.c_uint32),
+        ("meshletCount", ctypes.c_uint32),
+        ("meshletdataCount", ctypes.c_uint32),
+        ("meshletvtx0Count", ctypes.c_uint32),
+        ("meshCount", ctypes.c_uint32),
+        ("materialCount", ctypes.c_uint32),
+        ("drawCount", ctypes.c_uint32),
+        ("texturePathCount", ctypes.c_uint32),
+        ("lightCount", ctypes.c_uint32),
+        ("animationCount", ctypes.c_uint32),
+        ("keyframeCount", ctypes.c_uint32),
+        ("ommArrayDataSize", ctypes.c_uint32),
+        ("ommIndexDataSize", ctypes.c_uint32),
+        ("ommDescCount", ctypes.c_uint32),
+        ("ommStates", ctypes.c_uint32),
+        ("camera", Camera),
+        ("sunDirection", ctypes.c_float * 3),
+        ("pad1_", ctypes.c_uint32),
+    ]
+
+
+class SceneCacheSection(ctypes.Structure):
+    _fields_ = [
+        ("offset", ctypes.c_uint64),
+        ("stored_bytes", ctypes.c_uint64),
+        ("decoded_bytes", ctypes.c_uint64),
+        ("count", ctypes.c_uint32),
+        ("element_size", ctypes.c_uint32),
+        ("compressed", ctypes.c_uint32),
+        ("pad_", ctypes.c_uint32),
+    ]
+
+
+class SceneCacheInfo(ctypes.Structure):
+    _fields_ = [("header", SceneCacheHeader), ("sections", SceneCacheSection * len(CACHE_SECTIONS))]
+
+
+assert ctypes.sizeof(SceneCacheHeader) == 160 and ctypes.sizeof(SceneCacheSection) == 40
+
 
 def load_nvcg(path):
     """Reads a geometry dump written by oracle/refscene/dump_scene (the reference's own scene.cpp output):

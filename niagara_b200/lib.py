@@ -6,7 +6,7 @@ import ctypes
 import os
 
 from . import _build
-from .layout import Camera, CullData, CullOptions, HiZ, Limits
+from .layout import Camera, CullData, CullOptions, HiZ, Limits, SceneCacheInfo
 
 _LIB = None
 
@@ -55,6 +55,14 @@ SIGNATURES = [
         [ctypes.POINTER(Camera), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(CullOptions), ctypes.POINTER(CullData), c_void_p],
     ),
     ("nvc_host_pass_data", None, [ctypes.POINTER(CullData), ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(CullData)]),
+    ("nvc_scene_cache_parse", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.POINTER(SceneCacheInfo)]),
+    ("nvc_scene_cache_read", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.POINTER(SceneCacheInfo), ctypes.c_int, c_void_p, ctypes.c_size_t]),
+    (
+        "nvc_host_animate",
+        ctypes.c_int,
+        [c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, ctypes.c_double, c_void_p, ctypes.c_uint32, c_void_p, c_void_p, ctypes.c_uint32],
+    ),
+    ("nvc_update_draws", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint32, c_void_p, c_void_p, ctypes.c_uint32]),
     ("nvc_nccl_unique_id", ctypes.c_int, [c_void_p]),
     ("nvc_nccl_init", ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int]),
     ("nvc_allgather_visible", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p]),

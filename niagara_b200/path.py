@@ -85,6 +85,16 @@ class VisibilityPath:
         raw = torch.from_numpy(np.ascontiguousarray(draws).view(np.uint8).reshape(-1))
         self.db.copy_(raw, non_blocking=True)
 
+    def scatter_draws(self, indices, values):
+        """Incremental form (N3): only the animated draws travel — one packed H2D copy of {index, MeshDraw} and one
+        scatter launch (nvc_update_draws) instead of rewriting the whole buffer."""
+        n = int(len(indices))
+        if n == 0:
+            return
+        idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.uint32).view(np.int32)).pin_memory().to(self.device, non_blocking=True)
+        val = torch.from_numpy(np.ascontiguousarray(values).view(np.uint8).reshape(-1)).pin_memory().to(self.device, non_blocking=True)
+        check(self.lib.nvc_update_draws(self.ctx, self._stream(), _ptr(self.db), self.draw_count, _ptr(idx), _ptr(val), n), self.ctx, "nvc_update_draws")
+
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.nvc_destroy(self.ctx)

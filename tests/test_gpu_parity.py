@@ -110,6 +110,43 @@ def test_cuda_vs_reference_shaders(golden_dir):
     _run_frames(s, frames=2, checker=refshader_lib.RefShaderPath, toggles=dict(mesh_shading=False, cluster_occlusion=False), mesh_shading=False)
 
 
+def test_scene_cache_and_animated_draws(golden_dir):
+    """Widening N2 + N3: a scene read from a reference-written compressed cache (nvc_scene_cache_*), animated with
+    nvc_host_animate, the changed draws scattered into the device buffer by nvc_update_draws; every frame bit-exact
+    against the oracle fed with the same host arrays."""
+    from niagara_b200 import scene_cache
+
+    torch = _torch()
+    s = scene_cache.load_scene(os.path.join(golden_dir, "animated.z.cache"), screen=(640, 480))
+    g, o, depth = _paths(s)
+    for f, t in enumerate((0.0, 0.9, 1.7, 2.05, 7.3)):
+        idx, val = host.animate(s.animations, s.keyframes, t, s.draws)
+        assert len(idx) == (0 if t < 0.5 else 3)
+        g.scatter_draws(idx, val)
+        o.draws[...] = s.draws
+        torch.cuda.synchronize()
+        assert np.array_equal(g.db.cpu().numpy().view(layout.MESHDRAW_DTYPE), s.draws)
+        cd = s.cull_data()
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+                o.pyramid(s.depth)
+            for post in (0, 1):
+                if post and not late:
+                    continue
+                g.cull(cd, late, post_pass=post)
+                o.cull(cd, late, post_pass=post)
+                _compare_draw_pass(g, o, True, ("cull", f, late, post))
+                g.render_clusters(cd, late, post_pass=post)
+                o.render_clusters(cd, late, post_pass=post)
+                _compare_cluster_pass(g, o, ("clusters", f, late, post))
+    # out-of-range indices are ignored, nothing else is touched
+    before = g.db.cpu().numpy().copy()
+    g.scatter_draws(np.array([len(s.draws) + 5], np.uint32), s.draws[:1])
+    torch.cuda.synchronize()
+    assert np.array_equal(g.db.cpu().numpy(), before)
+
+
 @pytest.mark.parametrize(
     "toggles",
     [dict(lod=False), dict(culling=False), dict(occlusion=False), dict(cluster_occlusion=False), dict(debug_lod_step=3)],
