@@ -434,9 +434,31 @@ NVC_API int nvc_host_animate(const NvcAnimation* animations, uint32_t animation_
 NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, uint32_t draw_count,
     const uint32_t* update_indices, const NvcMeshDraw* update_values, uint32_t count);
 
+/* ---- widening N4: meshlet bounds + normal cones on the GPU (the producer of Meshlet[]'s cull fields) --------------------
+ * scene.h:51-57 / mesh.h:3-9 — 16 B */
+typedef struct NvcVertex
+{
+	uint16_t vx, vy, vz; /* fp16 position */
+	uint16_t tp;
+	uint32_t np;
+	uint16_t tu, tv;
+} NvcVertex;
+
+/* Recomputes center / radius / cone_axis / cone_cutoff of meshlets[0..meshlet_count) from geometry, bit-identical to
+ * what the reference's cooker stores (scene.cpp:69-80 appendMeshlet -> meshopt_computeMeshletBounds,
+ * meshletutils.cpp:133-272,314-339): one thread per meshlet reads its references and triangles from
+ * meshletdata[dataOffset...] (layout of scene.cpp:36-50, triangle order as cooked — NOT as re-read from a compressed
+ * cache, whose codec rotates triangles) and the fp16 positions of vertices[baseVertex + ref].  The other Meshlet
+ * fields are inputs and stay untouched.  For streamed / re-skinned geometry whose bounds must follow the vertices.
+ * A meshlet whose words, references or triangle indices fall outside the given arrays is left untouched and counted
+ * in *rejected (device uint32, zeroed by the call; may be NULL). */
+NVC_API int nvc_cook_meshlet_bounds(NvcContext* ctx, void* stream, const NvcVertex* vertices, uint32_t vertex_count,
+    const uint32_t* meshletdata, uint32_t meshletdata_words, NvcMeshlet* meshlets, uint32_t meshlet_count, uint32_t* rejected);
+
 #ifdef __cplusplus
 } /* extern "C" */
 
+static_assert(sizeof(NvcVertex) == 16, "Vertex must match src/scene.h:51-57");
 static_assert(sizeof(NvcMeshlet) == 24, "Meshlet must match src/shaders/mesh.h:11-24");
 static_assert(sizeof(NvcMeshLod) == 20, "MeshLod must match src/shaders/mesh.h:53-60");
 static_assert(sizeof(NvcMesh) == 208, "Mesh must match src/shaders/mesh.h:62-78");

@@ -392,4 +392,15 @@ NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, 
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_update_draws");
 }
 
+NVC_API int nvc_cook_meshlet_bounds(NvcContext* ctx, void* stream, const NvcVertex* vertices, uint32_t vertex_count, const uint32_t* meshletdata,
+    uint32_t meshletdata_words, NvcMeshlet* meshlets, uint32_t meshlet_count, uint32_t* rejected)
+{
+	if (!ctx || (meshlet_count && (!vertices || !meshletdata || !meshlets)))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaError_t e = nvc::launch_cook_meshlet_bounds(vertices, vertex_count, meshletdata, meshletdata_words, meshlets, meshlet_count, rejected, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_cook_meshlet_bounds");
+}
+
 } // extern "C"

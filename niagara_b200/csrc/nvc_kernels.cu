@@ -9,6 +9,7 @@
 // Compiled with -fmad=false; see nvc_math.cuh for the arithmetic contract.
 #include "nvc_internal.h"
 #include "nvc_math.cuh"
+#include "nvc_cook.cuh"
 #include "nvc_math2.cuh"
 #include "nvc_tma.cuh"
 
@@ -1318,6 +1319,64 @@ cudaError_t launch_decode_clusters(const uint32_t* cluster_indices, const uint32
 	if (e != cudaSuccess)
 		return e;
 	decode_clusters_kernel<<<blocks, 256, 0, stream>>>(cluster_indices, cluster_count4, task_commands, meshlets, records, stats4);
+	return cudaGetLastError();
+}
+
+// N4: meshlet bounds + normal cone, one thread per meshlet (csrc/nvc_cook.cuh).  A meshlet whose data or vertices would
+// fall outside the given arrays is left untouched and counted in *rejected.
+__global__ void __launch_bounds__(128) cook_meshlet_bounds_kernel(const NvcVertex* __restrict__ vertices, uint32_t vertex_count, const uint32_t* __restrict__ meshletdata,
+    uint32_t meshletdata_words, NvcMeshlet* __restrict__ meshlets, uint32_t meshlet_count, uint32_t* __restrict__ rejected)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= meshlet_count)
+		return;
+	NvcMeshlet m = meshlets[i];
+	cook::MeshletView view;
+	view.vertices = vertices;
+	view.data = meshletdata + m.dataOffset;
+	view.baseVertex = m.baseVertex;
+	view.vertexCount = m.vertexCount;
+	view.triangleCount = m.triangleCount;
+	view.shortRefs = m.shortRefs;
+	uint32_t ref_words = m.shortRefs ? (uint32_t(m.vertexCount) + 1u) / 2u : m.vertexCount;
+	uint64_t words = uint64_t(ref_words) + (uint64_t(m.triangleCount) * 3u + 3u) / 4u;
+	bool ok = uint64_t(m.dataOffset) + words <= meshletdata_words;
+	if (ok)
+	{
+		for (uint32_t k = 0; k < m.vertexCount; ++k)
+			ok = ok && uint64_t(m.baseVertex) + view.ref(k) < vertex_count;
+		for (uint32_t t = 0; t < m.triangleCount; ++t)
+			for (uint32_t c = 0; c < 3; ++c)
+				ok = ok && view.corner(t, c) < m.vertexCount;
+	}
+	if (!ok)
+	{
+		if (rejected)
+			atomicAdd(rejected, 1u);
+		return;
+	}
+	cook::meshlet_bounds(view, &m);
+	// center[3] + radius + cone_axis[3] + cone_cutoff = the first 12 bytes of the Meshlet
+	uint32_t w[3];
+	memcpy(w, &m, 12);
+	uint32_t* dst = reinterpret_cast<uint32_t*>(meshlets + i);
+	dst[0] = w[0];
+	dst[1] = w[1];
+	dst[2] = w[2];
+}
+
+cudaError_t launch_cook_meshlet_bounds(const NvcVertex* vertices, uint32_t vertex_count, const uint32_t* meshletdata, uint32_t meshletdata_words, NvcMeshlet* meshlets,
+    uint32_t meshlet_count, uint32_t* rejected, cudaStream_t stream)
+{
+	if (rejected)
+	{
+		cudaError_t e = cudaMemsetAsync(rejected, 0, 4, stream);
+		if (e != cudaSuccess)
+			return e;
+	}
+	if (meshlet_count == 0)
+		return cudaSuccess;
+	cook_meshlet_bounds_kernel<<<(meshlet_count + 127u) / 128u, 128, 0, stream>>>(vertices, vertex_count, meshletdata, meshletdata_words, meshlets, meshlet_count, rejected);
 	return cudaGetLastError();
 }
 

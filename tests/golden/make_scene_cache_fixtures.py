@@ -8,6 +8,7 @@
   animated.z.meshletdata   meshletdata[] as the reference's loadSceneCache decodes animated.z.cache
   animated.nvca            animation golden (niagara.cpp:1362-1390 with glm::mix / glm::slerp at 44 times)
   kitten.z.cache           data/kitten.obj, compressed (792 meshlets: every code path of the meshlet codec)
+  kitten_cook.npz          fp16 positions + raw meshletdata of the cooked kitten (inputs of nvc_cook_meshlet_bounds)
   scene_cache_expected.json  sha256 of the reference-decoded kitten meshletdata (padding bytes masked) + counts
 
 Only runs where /root/reference exists.  Run: python tests/golden/make_scene_cache_fixtures.py"""
@@ -51,6 +52,10 @@ def main():
             "indices": int(c.header.indexCount),
         }
     }
+    # inputs of the meshlet-bounds kernel for the cooked kitten (N4): fp16 positions + meshletdata in COOKED triangle order
+    r = scene_cache.SceneCache(os.path.join(tmp, "kitten.raw.cache"))
+    verts = r.section("vertices").view(np.uint16).reshape(-1, 8)
+    np.savez_compressed(os.path.join(HERE, "kitten_cook.npz"), positions=np.ascontiguousarray(verts[:, :3]), meshletdata=r.section("meshletdata"))
     with open(os.path.join(HERE, "scene_cache_expected.json"), "w") as f:
         json.dump(expected, f, indent=1)
     shutil.rmtree(tmp)
