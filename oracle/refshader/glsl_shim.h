@@ -350,7 +350,8 @@ inline float sampleMinLevel(const texture2D& t, uint l, const vec2& uv)
 	float x = uv.x * float(w) - 0.5f, y = uv.y * float(h) - 0.5f;
 	float x0 = floorf(x), y0 = floorf(y);
 	float fx = x - x0, fy = y - y0;
-	auto clampi = [](float v, uint n) -> uint { return v <= 0.0f ? 0u : (v >= float(n - 1) ? n - 1 : uint(v)); };
+	// CLAMP_TO_EDGE; a NaN coordinate (undefined in Vulkan) lands on texel 0, as fmax(NaN, 0) does in the oracle / CUDA path
+	auto clampi = [](float v, uint n) -> uint { return !(v > 0.0f) ? 0u : (v >= float(n - 1) ? n - 1 : uint(v)); };
 	uint i0 = clampi(x0, w), i1 = clampi(x0 + 1.0f, w), j0 = clampi(y0, h), j1 = clampi(y0 + 1.0f, h);
 	float r = img[size_t(j0) * w + i0];
 	if (fx != 0.0f)
