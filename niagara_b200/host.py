@@ -57,6 +57,15 @@ def cull_data(camera, screen_width, screen_height, draw_count, draw_distance=200
     return out
 
 
+def projection(camera, screen_width, screen_height):
+    """The infinite reverse-Z projection of niagara.cpp:424-432 for this camera / aspect, column-major float32[16]."""
+    opts = layout.CullOptions(200.0, 1, 1, 1, 1, 1, 0)
+    out = layout.CullData()
+    proj = (ctypes.c_float * 16)()
+    load_library().nvc_host_cull_data(ctypes.byref(camera), int(screen_width), int(screen_height), 0, ctypes.byref(opts), ctypes.byref(out), proj)
+    return np.array(proj, dtype=np.float32)
+
+
 def quat_from_axis_angle(axis, angle):
     ax = np.asarray(axis, dtype=np.float64)
     ax = ax / np.linalg.norm(ax)

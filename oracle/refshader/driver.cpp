@@ -27,9 +27,12 @@ namespace glsl
 {
 thread_local uvec3 gl_GlobalInvocationID, gl_LocalInvocationID, gl_WorkGroupID;
 thread_local uint gl_LocalInvocationIndex;
+thread_local MeshPerVertex gl_MeshVerticesEXT[256];
+thread_local uvec3 gl_PrimitiveTriangleIndicesEXT[256];
+thread_local MeshPerPrimitive gl_MeshPrimitivesEXT[256];
 } // namespace glsl
 
-extern const RsShader rs_shader_drawcull, rs_shader_tasksubmit, rs_shader_clustercull, rs_shader_clustersubmit, rs_shader_depthreduce, rs_shader_meshlet_task;
+extern const RsShader rs_shader_drawcull, rs_shader_tasksubmit, rs_shader_clustercull, rs_shader_clustersubmit, rs_shader_depthreduce, rs_shader_meshlet_task, rs_shader_meshlet_mesh;
 
 namespace
 {
@@ -48,6 +51,7 @@ thread_local ucontext_t* t_scheduler = nullptr;
 thread_local Fiber* t_current = nullptr;
 thread_local void (*t_main)() = nullptr;
 thread_local uint t_emit[3];
+thread_local uint t_mesh_outputs[2];
 
 void fiberEntry()
 {
@@ -210,6 +214,12 @@ void EmitMeshTasksEXT(uint x, uint y, uint z)
 	t_emit[2] = z;
 }
 
+void SetMeshOutputsEXT(uint vertexCount, uint primitiveCount)
+{
+	t_mesh_outputs[0] = vertexCount;
+	t_mesh_outputs[1] = primitiveCount;
+}
+
 } // namespace glsl
 
 extern "C"
@@ -219,8 +229,8 @@ extern "C"
 const char* rs_sources(void)
 {
 	static char buf[512];
-	snprintf(buf, sizeof(buf), "%s %s %s %s %s %s", rs_shader_drawcull.source, rs_shader_tasksubmit.source, rs_shader_clustercull.source,
-	    rs_shader_clustersubmit.source, rs_shader_depthreduce.source, rs_shader_meshlet_task.source);
+	snprintf(buf, sizeof(buf), "%s %s %s %s %s %s %s", rs_shader_drawcull.source, rs_shader_tasksubmit.source, rs_shader_clustercull.source,
+	    rs_shader_clustersubmit.source, rs_shader_depthreduce.source, rs_shader_meshlet_task.source, rs_shader_meshlet_mesh.source);
 	return buf;
 }
 
@@ -339,6 +349,128 @@ int rs_depth_pyramid(const float* depth, uint32_t depth_width, uint32_t depth_he
 		source.texels[0] = target.texels; // mipSource = mipTarget
 		source.width[0] = levelWidth;
 		source.height[0] = levelHeight;
+	}
+	return NVC_OK;
+}
+
+// ---- the consumer: meshlet.mesh.glsl (TASK = false) over the grid of vkCmdDrawMeshTasksIndirectEXT(ccb, 4) -------------
+// (niagara.cpp:1655-1664: bindings dcb, db, mlb, mdb, vb, cib; push constants = Globals).  Per slot (= workgroup)
+// x + 256 * y + 16 * z:   records[slot] = { vertexCount, triangleCount, out_drawId[0] (or ~0), 0 },
+// positions[slot][v] = gl_MeshVerticesEXT[v].gl_Position (64 x vec4), triangles[slot][t] = gl_PrimitiveTriangleIndicesEXT[t] (96 x 3 bytes).
+int rs_mesh_clusters(const float* projection16, const NvcCullData* pass, float screen_width, float screen_height, const void* task_commands,
+    size_t commands_bytes, const void* draws, size_t draws_bytes, const void* meshlets, size_t meshlets_bytes, const void* meshletdata, size_t meshletdata_bytes,
+    const void* vertices, size_t vertices_bytes, const uint32_t* cluster_indices, size_t cib_bytes, const uint32_t* cluster_count4, uint32_t* records, float* positions,
+    uint8_t* triangles, int threads)
+{
+	TaskGlobals globals = {};
+	memcpy(globals.projection, projection16, sizeof(globals.projection));
+	globals.cullData = *pass;
+	globals.screenWidth = screen_width;
+	globals.screenHeight = screen_height;
+
+	const RsShader& s = rs_shader_meshlet_mesh;
+	s.spec(1, 0); // TASK = false: cluster indices come from cib
+	s.bind(0, const_cast<void*>(task_commands), commands_bytes);
+	s.bind(1, const_cast<void*>(draws), draws_bytes);
+	s.bind(2, const_cast<void*>(meshlets), meshlets_bytes);
+	s.bind(3, const_cast<void*>(meshletdata), meshletdata_bytes); // uint / uint16_t / uint8_t views alias binding 3
+	s.bind(4, const_cast<void*>(vertices), vertices_bytes);
+	s.bind(5, const_cast<uint32_t*>(cluster_indices), cib_bytes);
+	s.push(&globals, sizeof(globals));
+	dispatch(s, cluster_count4[1], cluster_count4[2], cluster_count4[3], threads, [&](uint x, uint y, uint z) {
+		size_t slot = size_t(x) + size_t(y) * 256 + size_t(z) * 16; // meshlet.mesh.glsl:94
+		uint vc = t_mesh_outputs[0], tc = t_mesh_outputs[1];
+		const uint* drawId = static_cast<const uint*>(s.output(0));
+		records[slot * 4 + 0] = vc;
+		records[slot * 4 + 1] = tc;
+		records[slot * 4 + 2] = vc ? drawId[0] : ~0u;
+		records[slot * 4 + 3] = 0;
+		for (uint v = 0; v < vc && v < 64; ++v)
+			for (int c = 0; c < 4; ++c)
+				positions[(slot * 64 + v) * 4 + c] = glsl::gl_MeshVerticesEXT[v].gl_Position[c];
+		for (uint t = 0; t < tc && t < 96; ++t)
+		{
+			triangles[(slot * 96 + t) * 3 + 0] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].x);
+			triangles[(slot * 96 + t) * 3 + 1] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].y);
+			triangles[(slot * 96 + t) * 3 + 2] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].z);
+		}
+	});
+	return NVC_OK;
+}
+
+// ---- a small reference rasteriser for end-to-end tests (OURS, not the reference's: Vulkan's fixed function) --------------
+// Facing as the mesh shader's own MESH_CULL code decides it (meshlet.mesh.glsl:154,175-181): in the y-up screen space
+// (clip.xy / clip.w * 0.5 + 0.5) * screen a triangle is front facing iff eb.x * ec.y > eb.y * ec.x (= the pipeline's
+// COUNTER_CLOCKWISE front face + BACK culling, shaders.cpp:687-688).  Pixels are placed with the reference's flipped
+// viewport {0, height, width, -height} (niagara.cpp:1641): row = (0.5 - 0.5 * ndc.y) * height, which is also the uv
+// convention of projectSphere's aabb (math.h:19).  A triangle with a corner at w <= 0 is skipped (no near clipping);
+// samples at pixel centres, inclusive edges; depth = clip.z / clip.w interpolated affinely, test GREATER (reverse Z, clear 0).
+// mode 0: depth[] = max(depth[], triangle depth).   mode 1: depth[] is read-only; slot_hit[slot] = 1 when some covered sample of
+// the slot has exactly the stored depth (i.e. the slot owns or ties a pixel of the final image).
+int rs_rasterize(const float* positions, const uint8_t* triangles, const uint32_t* records, uint32_t slots, uint32_t width, uint32_t height, float* depth,
+    uint8_t* slot_hit, int mode)
+{
+	for (uint32_t slot = 0; slot < slots; ++slot)
+	{
+		uint32_t vc = records[slot * 4 + 0], tc = records[slot * 4 + 1];
+		for (uint32_t t = 0; t < tc && t < 96; ++t)
+		{
+			double sx[3], sy[3], sz[3];
+			bool behind = false;
+			for (int c = 0; c < 3; ++c)
+			{
+				uint32_t v = triangles[(size_t(slot) * 96 + t) * 3 + c];
+				if (v >= vc)
+					return NVC_ERROR_INVALID_ARGUMENT;
+				const float* p = positions + (size_t(slot) * 64 + v) * 4;
+				if (!(p[3] > 0.0f))
+				{
+					behind = true;
+					break;
+				}
+				float fx = (p[0] / p[3] * 0.5f + 0.5f) * float(width), fy = (p[1] / p[3] * 0.5f + 0.5f) * float(height);
+				sx[c] = fx;
+				sy[c] = fy;
+				sz[c] = double(p[2] / p[3]);
+			}
+			if (behind)
+				continue;
+			double ebx = sx[1] - sx[0], eby = sy[1] - sy[0], ecx = sx[2] - sx[0], ecy = sy[2] - sy[0];
+			double area = ebx * ecy - eby * ecx;
+			if (!(area > 0.0))
+				continue; // back facing or zero area
+			// flipped viewport: rows count from the top; swapping two corners keeps the edge functions positive inside
+			for (int c = 0; c < 3; ++c)
+				sy[c] = double(height) - sy[c];
+			std::swap(sx[1], sx[2]);
+			std::swap(sy[1], sy[2]);
+			std::swap(sz[1], sz[2]);
+			double minx = std::min(sx[0], std::min(sx[1], sx[2])), maxx = std::max(sx[0], std::max(sx[1], sx[2]));
+			double miny = std::min(sy[0], std::min(sy[1], sy[2])), maxy = std::max(sy[0], std::max(sy[1], sy[2]));
+			if (!(maxx >= 0.0 && maxy >= 0.0 && minx <= double(width) && miny <= double(height)))
+				continue;
+			int x0 = int(std::max(0.0, floor(minx - 0.5))), x1 = int(std::min(double(width) - 1.0, ceil(maxx - 0.5)));
+			int y0 = int(std::max(0.0, floor(miny - 0.5))), y1 = int(std::min(double(height) - 1.0, ceil(maxy - 0.5)));
+			for (int y = y0; y <= y1; ++y)
+				for (int x = x0; x <= x1; ++x)
+				{
+					double px = x + 0.5, py = y + 0.5;
+					double w0 = (sx[1] - px) * (sy[2] - py) - (sy[1] - py) * (sx[2] - px);
+					double w1 = (sx[2] - px) * (sy[0] - py) - (sy[2] - py) * (sx[0] - px);
+					double w2 = (sx[0] - px) * (sy[1] - py) - (sy[0] - py) * (sx[1] - px);
+					if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0)
+						continue;
+					float z = float((w0 * sz[0] + w1 * sz[1] + w2 * sz[2]) / (w0 + w1 + w2));
+					float& d = depth[size_t(y) * width + x];
+					if (mode == 0)
+					{
+						if (z > d)
+							d = z;
+					}
+					else if (z == d)
+						slot_hit[slot] = 1;
+				}
+		}
 	}
 	return NVC_OK;
 }

@@ -11,11 +11,12 @@ Only declarations C++ cannot parse are rewritten; every statement inside a funct
   out T name  (parameters)                   T& name
   layout(constant_id = N) const bool X = v   static bool X = v        (+ rs_spec)
   layout(local_size_x = ..) in               static const uint rs_local[3]
-  layout(push_constant) uniform block {..}   static struct rs_pc;  members reachable by name
-  layout(binding = N) buffer B { T a[]; }    RobustArray<T> (zero on out-of-range reads, writes discarded)
-  layout(binding = N) buffer B { uint a; ..} pointer to the block
+  layout(push_constant) uniform block {..}   static struct rs_pc + a reference per member
+  layout(binding = N) buffer B { T a[]; }    static RobustArray<T> a  (zero on out-of-range reads, writes discarded)
+  layout(binding = N) buffer B { uint a; ..} pointer to the block, members reachable through macros
   layout(binding = N) uniform texture2D / sampler / image2D    static objects (+ rs_bind)
   shared T x / taskPayloadSharedEXT T x      static thread_local   (one workgroup runs on one host thread)
+  layout(triangles, ...) out                 dropped;  layout(location = N) out T x[]  ->  static thread_local T x[256]
   void main()                                static void rs_main()
 """
 import os
@@ -29,7 +30,7 @@ def common_rewrites(text, src_dir):
     text = re.sub(r"^[ \t]*#(version|extension)[^\n]*\n", "", text, flags=re.M)
     text = text.replace('#include "../config.h"', '#include "%s"' % os.path.normpath(os.path.join(src_dir, "..", "config.h")))
     text = FLOAT_LIT.sub(lambda m: m.group(1) + "f", text)
-    text = re.sub(r"\bout\s+(\w+)\s+(\w+)", r"\1& \2", text)
+    text = re.sub(r"([(,]\s*)out\s+(\w+)\s+(\w+)", r"\1\2& \3", text)  # only inside parameter lists
     return text
 
 
@@ -70,9 +71,8 @@ def rewrite_shader(text, name):
     def push(m):
         state["pc"] = True
         mem = members_of(m.group(2))
-        for _, member, _ in mem:
-            defines.append("#define %s rs_pc.%s" % (member, member))
-        return "static struct rs_pc_t {%s} rs_pc;" % m.group(2)
+        refs = "".join("\nstatic %s& %s = rs_pc.%s;" % (typ, member, member) for typ, member, _ in mem)
+        return "static struct rs_pc_t {%s} rs_pc;%s" % (m.group(2), refs)
 
     text = re.sub(r"layout\s*\(\s*push_constant\s*\)\s*uniform\s+(\w+)\s*\{(.*?)\}\s*;", push, text, flags=re.S)
 
@@ -82,9 +82,8 @@ def rewrite_shader(text, name):
         if all(unsized for _, _, unsized in mem):
             assert len(mem) == 1
             typ, member, _ = mem[0]
-            defines.append("#define %s rs_b_%s.%s" % (member, block, member))
-            binds.append((binding, "rs_b_%s.%s.bind(p, bytes);" % (block, member)))
-            return "static struct %s_block { RobustArray<%s> %s; } rs_b_%s;" % (block, typ, member, block)
+            binds.append((binding, "%s.bind(p, bytes);" % member))
+            return "static RobustArray<%s> %s; // block %s" % (typ, member, block)
         assert not any(unsized for _, _, unsized in mem), "mixed block %s" % block
         for _, member, _ in mem:
             defines.append("#define %s rs_b_%s->%s" % (member, block, member))
@@ -102,6 +101,16 @@ def rewrite_shader(text, name):
         return "static %s %s;" % (typ, var)
 
     text = re.sub(r"layout\s*\(\s*binding\s*=\s*(\d+)\s*(?:,\s*\w+\s*)?\)\s*uniform\s+(writeonly\s+|readonly\s+)?(texture2D|sampler|image2D)\s+(\w+)\s*;", resource, text)
+
+    # mesh stage: the output topology declaration carries no code; per-vertex outputs become plain arrays
+    text = re.sub(r"layout\s*\(\s*triangles\s*,[^)]*\)\s*out\s*;", "", text)
+    outputs = []
+
+    def output(m):
+        outputs.append((int(m.group(1)), m.group(3)))
+        return "static thread_local %s %s[256];" % (m.group(2), m.group(3))
+
+    text = re.sub(r"layout\s*\(\s*location\s*=\s*(\d+)\s*\)\s*out\s+(?:flat\s+)?(\w+)\s+(\w+)\s*\[\s*\]\s*;", output, text)
 
     def payload(m):
         state["payload"] = m.group(2)
@@ -129,6 +138,10 @@ def rewrite_shader(text, name):
         tail.append("\tif (id == %d) %s = value != 0;" % (sid, var))
     tail += ["}", ""]
     tail.append("static void* rs_payload() { return %s; }" % ("&" + state["payload"] if state["payload"] else "nullptr"))
+    tail += ["", "static void* rs_output(int location)", "{", "\t(void)location;"]
+    for loc, var in outputs:
+        tail.append("\tif (location == %d) return %s;" % (loc, var))
+    tail += ["\treturn nullptr;", "}"]
     # the member macros must touch neither the declarations above them nor the glue: both go right before rs_main
     text = text.replace("static void rs_main()", "\n".join(tail) + "\n\n" + "\n".join(defines) + "\n\nstatic void rs_main()", 1)
     return text, state
@@ -152,7 +165,7 @@ def main():
             f.write('#include "glsl_shim.h"\n#include "rs_shader.h"\n\nnamespace glsl\n{\nnamespace rs_%s\n{\n\n' % name)
             f.write(text)
             f.write("\n} // namespace rs_%s\n} // namespace glsl\n\n" % name)
-            f.write('extern const RsShader rs_shader_%s = { "%s", glsl::rs_%s::rs_local, glsl::rs_%s::rs_main, glsl::rs_%s::rs_bind, glsl::rs_%s::rs_push, glsl::rs_%s::rs_spec, glsl::rs_%s::rs_payload, %d };\n' % (name, shader, name, name, name, name, name, name, 1 if state["barrier"] else 0))
+            f.write('extern const RsShader rs_shader_%s = { "%s", glsl::rs_%s::rs_local, glsl::rs_%s::rs_main, glsl::rs_%s::rs_bind, glsl::rs_%s::rs_push, glsl::rs_%s::rs_spec, glsl::rs_%s::rs_payload, glsl::rs_%s::rs_output, %d };\n' % (name, shader, name, name, name, name, name, name, name, 1 if state["barrier"] else 0))
 
 
 if __name__ == "__main__":

@@ -411,6 +411,21 @@ struct RobustArray
 extern thread_local uvec3 gl_GlobalInvocationID, gl_LocalInvocationID, gl_WorkGroupID;
 extern thread_local uint gl_LocalInvocationIndex;
 
+// ---- mesh stage outputs (GL_EXT_mesh_shader) of the workgroup running on this host thread ------------------------------
+struct MeshPerVertex
+{
+	vec4 gl_Position;
+};
+struct MeshPerPrimitive
+{
+	bool gl_CullPrimitiveEXT;
+};
+extern thread_local MeshPerVertex gl_MeshVerticesEXT[256];
+extern thread_local uvec3 gl_PrimitiveTriangleIndicesEXT[256];
+extern thread_local MeshPerPrimitive gl_MeshPrimitivesEXT[256];
+void SetMeshOutputsEXT(uint vertexCount, uint primitiveCount);
+inline float round(float a) { return roundf(a); }
+
 void barrier();                              // yields to the other invocations of the workgroup (fibers), see driver.cpp
 void EmitMeshTasksEXT(uint x, uint y, uint z); // records the workgroup's emit count
 

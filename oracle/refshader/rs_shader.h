@@ -11,5 +11,6 @@ struct RsShader
 	void (*push)(const void* p, size_t bytes);        // push constants
 	void (*spec)(int constant_id, int value);         // specialisation constants
 	void* (*payload)();                               // taskPayloadSharedEXT object of the calling host thread, or NULL
+	void* (*output)(int location);                    // layout(location = N) out array of the calling host thread, or NULL
 	int uses_barrier;
 };

@@ -44,6 +44,10 @@ def load():
     lib.rs_taskcull.argtypes = [cd, ctypes.c_int, vp, sz, vp, vp, sz, vp, sz, vp, sz, vp, vp, hz, ctypes.c_int]
     lib.rs_depth_pyramid.restype = ctypes.c_int
     lib.rs_depth_pyramid.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, hz, ctypes.c_int]
+    lib.rs_mesh_clusters.restype = ctypes.c_int
+    lib.rs_mesh_clusters.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, ctypes.c_int]
+    lib.rs_rasterize.restype = ctypes.c_int
+    lib.rs_rasterize.argtypes = [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp, ctypes.c_int]
     lib.rs_project_sphere.restype = ctypes.c_int
     lib.rs_project_sphere.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp]
     lib.rs_occlusion_mip.restype = ctypes.c_float
@@ -96,3 +100,40 @@ class RefShaderPath(oracle_lib.OraclePath):
         depth = np.ascontiguousarray(depth, dtype=np.float32)
         s = self.rs.rs_depth_pyramid(_p(depth), self.depth_width, self.depth_height, ctypes.byref(self.hiz), self.threads)
         assert s == 0, s
+
+
+class MeshStage:
+    """meshlet.mesh.glsl (the reference's consumer of cib / ccb / dcb) + a small rasteriser, for end-to-end tests."""
+
+    def __init__(self, path, vertices, meshletdata, projection16, threads=8):
+        self.p, self.rs, self.threads = path, load(), threads
+        self.vertices = np.ascontiguousarray(vertices)
+        self.meshletdata = np.ascontiguousarray(meshletdata, dtype=np.uint32)
+        self.projection = np.ascontiguousarray(projection16, dtype=np.float32)
+
+    def run(self, cull_data, cib=None, ccb=None, dcb=None):
+        """Runs the mesh stage over (cib, ccb) (default: the path's own buffers).  Returns records[slots, 4]
+        (vertexCount, triangleCount, drawId or ~0, 0), positions[slots, 64, 4], triangles[slots, 96, 3]."""
+        p = self.p
+        cib = p.cib if cib is None else np.ascontiguousarray(cib, dtype=np.uint32)
+        ccb = p.ccb if ccb is None else np.ascontiguousarray(ccb, dtype=np.uint32)
+        dcb = p.dcb if dcb is None else dcb
+        slots = int(ccb[1]) * int(ccb[2]) * int(ccb[3])
+        rec = np.zeros((max(slots, 1), 4), np.uint32)
+        pos = np.zeros((max(slots, 1), 64, 4), np.float32)
+        tri = np.zeros((max(slots, 1), 96, 3), np.uint8)
+        pd = p._pass_data(cull_data, 0, 0)
+        w, h = p.depth_width, p.depth_height
+        s = self.rs.rs_mesh_clusters(_p(self.projection), ctypes.byref(pd), float(w), float(h), _p(dcb), _n(dcb), _p(p.draws), _n(p.draws), _p(p.meshlets), _n(p.meshlets), _p(self.meshletdata), _n(self.meshletdata), _p(self.vertices), _n(self.vertices), _p(cib), _n(cib), _p(ccb), _p(rec), _p(pos), _p(tri), self.threads)
+        assert s == 0, s
+        return rec[:slots], pos[:slots], tri[:slots]
+
+    def rasterize(self, rec, pos, tri, depth):
+        s = self.rs.rs_rasterize(_p(pos), _p(tri), _p(rec), len(rec), depth.shape[1], depth.shape[0], _p(depth), None, 0)
+        assert s == 0, s
+
+    def owners(self, rec, pos, tri, depth):
+        hit = np.zeros(max(len(rec), 1), np.uint8)
+        s = self.rs.rs_rasterize(_p(pos), _p(tri), _p(rec), len(rec), depth.shape[1], depth.shape[0], _p(depth), _p(hit), 1)
+        assert s == 0, s
+        return hit[: len(rec)].astype(bool)

@@ -1,0 +1,142 @@
+"""CPU-only end-to-end check on REAL geometry: the two-phase visibility path (oracle), the reference's own mesh shader
+(meshlet.mesh.glsl compiled through oracle/refshader) as the consumer of cib / ccb / dcb, and a small rasteriser that
+turns its output into the depth buffer the next pass culls against — no synthetic depth anywhere.
+
+Properties checked every frame, with a moving camera (why the two-phase scheme is correct):
+  * the mesh stage decodes exactly what nvc_decode_clusters / the oracle say is in cib (N1), and nothing else;
+  * no cluster is drawn twice (early and late sets are disjoint);
+  * the image rendered from early + late clusters equals the brute-force image of ALL clusters of the selected LODs
+    (nothing visible was culled), up to the reference's own fp16 rounding of meshlet bounds — the tolerance is stated;
+  * every cluster owning a pixel of the brute-force image was emitted."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import refshader_lib
+from niagara_b200 import host, layout, scenes
+
+pytestmark = pytest.mark.skipif(not refshader_lib.available(), reason="needs /root/reference or a prebuilt oracle/_ref/librefshader.so")
+
+
+def _kitten_scene(golden_dir, n, screen):
+    meshes, meshlets, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten.nvcg"))
+    z = np.load(os.path.join(golden_dir, "kitten_cook.npz"))
+    positions, meshletdata = z["positions"], z["meshletdata"]
+    vertices = np.zeros((len(positions), 8), dtype=np.uint16)
+    vertices[:, :3] = positions
+    rng = np.random.default_rng(4)
+    draws = np.zeros(n, dtype=layout.MESHDRAW_DTYPE)
+    draws["position"] = np.stack([rng.uniform(-14, 14, n), rng.uniform(-9, 9, n), -rng.uniform(6, 60, n)], 1)  # the camera looks down -Z (niagara.cpp:1492).astype(np.float32)
+    draws["scale"] = rng.uniform(1.5, 4.5, n).astype(np.float32)
+    q = rng.standard_normal((n, 4))
+    draws["orientation"] = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    bits, _ = host.visibility_offsets(draws, meshes)
+    cam = host.make_camera()
+    s = scenes.Scene("kitten-field", meshes, meshlets, draws, np.zeros((screen[1], screen[0]), np.float32), cam, screen, bits)
+    return s, vertices.view(np.uint8).reshape(-1), meshletdata
+
+
+def _all_clusters(cmds, count):
+    """cib / ccb listing every (command, lane) of the first `count` task commands — the brute-force draw list."""
+    live = np.nonzero(cmds["taskCount"][:count] > 0)[0]
+    tc = cmds["taskCount"][live].astype(np.int64)
+    cid = np.repeat(live, tc)
+    lane = np.arange(int(tc.sum())) - np.repeat(np.cumsum(tc) - tc, tc)
+    ci = (cid | (lane << 24)).astype(np.uint32)
+    pad = (len(ci) + 255) // 256 * 256
+    cib = np.full(max(pad, 256), 0xFFFFFFFF, np.uint32)
+    cib[: len(ci)] = ci
+    return cib, np.array([len(ci), 16, max(pad // 256, 0), 16], np.uint32), ci
+
+
+@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+def test_two_phase_frames_on_rasterised_depth(golden_dir, culler):
+    """culler = who runs drawcull / clustercull / depthreduce: our oracle, or the reference's own shaders."""
+    screen = (512, 384)
+    s, vertices, meshletdata = _kitten_scene(golden_dir, 300, screen)
+    o = (oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    o.set_visibility_bits(s.visibility_bits)
+    # brute-force lister: the early drawcull with every draw marked visible and every test but LOD selection switched off
+    gt = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    gt.set_visibility_bits(s.visibility_bits)
+    cams = [
+        host.make_camera((0, 0, 0)),
+        host.make_camera((0, 0, 0)),
+        host.make_camera((3.5, -1.0, 2.0), host.quat_from_axis_angle((0, 1, 0), 0.18)),
+        host.make_camera((7.0, 1.5, 5.0), host.quat_from_axis_angle((0.1, 1, 0), 0.42)),
+        host.make_camera((7.0, 1.5, 5.0), host.quat_from_axis_angle((0.1, 1, 0), 0.42)),
+    ]
+    late_added, mismatching_pixels, total_pixels, missed_owners, owners_total = 0, 0, 0, 0, 0
+    for f, cam in enumerate(cams):
+        s.camera = cam
+        cd = s.cull_data()
+        ms = refshader_lib.MeshStage(o, vertices, meshletdata, host.projection(cam, *screen))
+        depth = np.zeros((screen[1], screen[0]), np.float32)  # reverse Z: cleared to 0 = infinitely far (niagara.cpp:1744)
+
+        def draw_pass(late):
+            o.cull(cd, late)
+            o.render_clusters(cd, late)  # the reference's own wiring of clusterBackfaceEnabled
+            n = int(o.ccb[0])
+            rec, pos, tri = ms.run(cd)
+            # N1: the reference's mesh shader sees exactly the clusters the decoder reports
+            drec, dstats = o.decode_clusters()
+            assert int(dstats[0]) == n and int(dstats[2]) == 0
+            live = rec[:, 0] > 0
+            assert live.sum() == n and np.array_equal(live, drec[:, 0] != 0xFFFFFFFF)
+            assert np.array_equal(rec[live, 2], drec[live, 0]) and np.array_equal(rec[live, 0], drec[live, 2]) and np.array_equal(rec[live, 1], drec[live, 3])
+            ms.rasterize(rec, pos, tri, depth)
+            cmds = o.read_task_commands(int(o.dccb[1]) * 64)
+            return oracle_lib.cluster_pairs(o.read_cluster_indices(n), cmds), cmds
+
+        early, _ = draw_pass(False)
+        o.pyramid(depth)
+        late, cmds = draw_pass(True)
+        assert len(np.intersect1d(early, late)) == 0
+        late_added += len(late)
+
+        # brute force: every meshlet of the LOD drawcull selects for every draw, no culling at all
+        gt.dvb[:] = 1
+        gt.cull(s.cull_data(culling=False, occlusion=False, cluster_occlusion=False), late=False)
+        assert int(gt.dccb[0]) >= len(s.draws)
+        all_cmds = gt.read_task_commands(int(gt.dccb[1]) * 64)
+        cib, ccb, ci = _all_clusters(all_cmds, int(gt.dccb[0]))
+        rec, pos, tri = ms.run(cd, cib=cib, ccb=ccb, dcb=gt.dcb)
+        truth = np.zeros_like(depth)
+        ms.rasterize(rec, pos, tri, truth)
+        diff = truth != depth
+        mismatching_pixels += int(diff.sum())
+        total_pixels += diff.size
+        assert (truth >= depth).all()  # the path can only lose pixels, never invent them
+        # owners of the brute-force image must have been emitted
+        own = ms.owners(rec, pos, tri, truth)
+        owner_pairs = oracle_lib.cluster_pairs(ci[own[: len(ci)]], all_cmds)
+        emitted = np.union1d(early, late)
+        missed = ~np.isin(owner_pairs, emitted)
+        missed_owners += int(missed.sum())
+        owners_total += len(owner_pairs)
+        print("frame %d: early %d late %d clusters, brute force %d; coverage %.2f; pixels differing %d; owners %d missed %d" % (f, len(early), len(late), len(ci), (truth > 0).mean(), int(diff.sum()), len(owner_pairs), int(missed.sum())))
+        assert (truth > 0).mean() > 0.2, "the scene should cover a good part of the screen"
+    assert late_added > 0 and owners_total > 5000
+    # In general exactness is not guaranteed by the reference (meshlet spheres are stored rounded to nearest fp16,
+    # scene.cpp:71-74, cones quantised to 8 bits); on this scene the result IS exact, and the run is deterministic.
+    print("frames %d: %d/%d pixels differ from brute force, %d/%d pixel-owning clusters not emitted" % (len(cams), mismatching_pixels, total_pixels, missed_owners, owners_total))
+    assert mismatching_pixels == 0 and missed_owners == 0
+
+    # sensitivity of the check itself: cull against a vertically flipped depth (the wrong viewport convention) and the late
+    # pass rejects clusters that own pixels
+    s.camera = cams[-1]
+    cd = s.cull_data()
+    o.pyramid(np.ascontiguousarray(truth[::-1]))
+    o.cull(cd, True)
+    o.render_clusters(cd, True)
+    cmds = o.read_task_commands(int(o.dccb[1]) * 64)
+    live = cmds[cmds["taskCount"] > 0]
+    rejected = 0
+    for c in live:
+        mvi = int(c["meshletVisibilityOffset"]) + np.arange(int(c["taskCount"]))
+        bits = (o.mvb[mvi >> 5] >> (mvi & 31).astype(np.uint32)) & 1
+        pairs = (np.uint64(c["drawId"]) << np.uint64(32)) | (int(c["taskOffset"]) + np.nonzero(bits == 0)[0]).astype(np.uint64)
+        rejected += int(np.isin(pairs, owner_pairs).sum())
+    assert rejected > 20
