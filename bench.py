@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-shaders"])
     ap.add_argument("--workload", default="C4", choices=["C4", "C2"])
     ap.add_argument("--draws", type=int, default=1_000_000)
     ap.add_argument("--meshlets-per-draw", type=int, default=10)
@@ -173,9 +173,12 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(args, scene, threads, repeats=5):
+def cpu_baseline(args, scene, threads, repeats=5, shaders=False):
     """The CPU restatement (oracle/, `kind: port` — the reference has no CPU cull path) on a bounded sample:
-    the first `cpu_sample_draws` draws of the same scene, one steady-state frame, all host threads."""
+    the first `cpu_sample_draws` draws of the same scene, one steady-state frame, all host threads.
+    shaders=True times the reference's own GLSL compiled for the host instead (oracle/_ref/librefshader.so, `kind:
+    reference`): same results bit for bit, ~4x slower than the port (64-lane workgroups with idle lanes, robust-buffer
+    checks), which is why the FASTER port stays the reported baseline and this one is only attached for information."""
     import oracle_lib
 
     n = min(args.cpu_sample_draws, len(scene.draws))
@@ -184,7 +187,12 @@ def cpu_baseline(args, scene, threads, repeats=5):
 
     bits, _ = host.visibility_offsets(draws, scene.meshes)
     cd = host.cull_data(scene.camera, scene.screen[0], scene.screen[1], n)
-    o = oracle_lib.OraclePath(scene.meshes, scene.meshlets, draws, *scene.screen, threads=threads, cmd_capacity=max(64, (n * 2 + 63) // 64 * 64))
+    cls = oracle_lib.OraclePath
+    if shaders:
+        import refshader_lib
+
+        cls = refshader_lib.RefShaderPath
+    o = cls(scene.meshes, scene.meshlets, draws, *scene.screen, threads=threads, cmd_capacity=max(64, (n * 2 + 63) // 64 * 64))
     o.set_visibility_bits(bits)
     o.frame(cd, scene.depth, cluster_backface=True)  # warm-up frame: establishes dvb / mvb
 
@@ -214,6 +222,8 @@ def cpu_baseline(args, scene, threads, repeats=5):
         tested = n_tested
         best = dt if best is None else min(best, dt)
     dt = best
+    if shaders:
+        return {"value": tested / dt, "unit": "meshlets/s", "cores": threads, "kind": "reference", "seconds": dt, "what": "the reference's own GLSL shaders compiled for the host (oracle/_ref/librefshader.so), best of %d frames" % frames}
     return {
         "value": tested / dt,
         "unit": "meshlets/s",
@@ -246,6 +256,17 @@ def run_reference(args):
             t_steps.append(r)
         res = r
     value = float(np.mean([r["value"] for r in t_steps]))
+    # informational: the reference's own shaders compiled for the host, timed in a child process so that nothing it does can
+    # take this arm down (it is ~4x slower than the port, which therefore stays the reported baseline)
+    shaders = None
+    try:
+        import subprocess
+
+        child = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-shaders", "--cpu-sample-draws", str(sample_args.draws), "--draws", str(sample_args.draws),
+                                "--meshlets-per-draw", str(args.meshlets_per_draw), "--depth", str(args.depth)], capture_output=True, text=True, timeout=240)
+        shaders = json.loads(child.stdout.strip().splitlines()[-1]) if child.returncode == 0 and child.stdout.strip() else {"unavailable": "exit %d" % child.returncode}
+    except Exception as e:
+        shaders = {"unavailable": str(e)[:120]}
     line = {
         "impl": "reference",
         "metric": "meshlets culled/sec",
@@ -261,7 +282,7 @@ def run_reference(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "C4 sample: %d draws x %d meshlets, %dx%d depth; CPU restatement of the GLSL (the reference has no CPU cull path)" % (sample_args.draws, args.meshlets_per_draw, args.depth, args.depth)},
-        "cpu_baseline": {"value": value, "unit": "meshlets/s", "cores": threads, "kind": "port", "sample": res["sample"]},
+        "cpu_baseline": {"value": value, "unit": "meshlets/s", "cores": threads, "kind": "port", "sample": res["sample"], **({"reference_shaders": shaders} if shaders else {})},
         "e2e": {"value": value, "unit": "meshlets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "draws_per_s": float(np.mean([r["draws_per_s"] for r in t_steps])),
         "gpu_launches": 0,
@@ -273,6 +294,16 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "reference-shaders":  # child of the reference arm, see run_reference
+        import oracle_lib
+        import refshader_lib
+
+        if not refshader_lib.available():
+            print(json.dumps({"unavailable": "oracle/_ref/librefshader.so not built"}))
+            return
+        threads = oracle_lib.load().orc_hardware_threads() or os.cpu_count() or 1
+        print(json.dumps(cpu_baseline(args, build_scene(args, 0), threads, repeats=2, shaders=True)))
         return
 
     import torch
