@@ -17,8 +17,11 @@
  *   - plain C, no CUDA or torch types in signatures: streams are passed as void* (a cudaStream_t),
  *     device buffers as plain pointers to the structs below.
  *   - every pass call only ENQUEUES work on `stream`; no allocation, no synchronisation, safe to capture
- *     into a CUDA graph.  A context is not re-entrant (the reference's frame loop is single threaded) and its
- *     device must be the calling thread's current CUDA device (else NVC_ERROR_INVALID_ARGUMENT).
+ *     into a CUDA graph.  A context is not re-entrant (the reference's frame loop is single threaded): its passes
+ *     share device-side ticket counters, so the passes of ONE context must be ordered — same stream, or streams
+ *     ordered by events; use one context per concurrently running frame.  The context's device must be the calling
+ *     thread's current CUDA device for pass calls (else NVC_ERROR_INVALID_ARGUMENT); nvc_create makes `device` current
+ *     and leaves it so, the other lifetime calls restore the caller's device.
  *   - return value: 0 = NVC_OK, negative = NvcStatus error.  Capacity overflow (TASK_WGLIMIT /
  *     CLUSTER_LIMIT) is NOT an error: it is the reference's defined drop-and-clamp behaviour.
  *   - all struct layouts below are asserted (size/offset) against src/shaders/mesh.h + src/scene.h.

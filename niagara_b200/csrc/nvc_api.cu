@@ -49,6 +49,26 @@ void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_tex
 namespace
 {
 
+// Lifetime calls (destroy / prepare / staging) work on the context's device and put the caller's device back afterwards.
+struct DeviceGuard
+{
+	int previous = -1;
+	explicit DeviceGuard(int device)
+	{
+		if (cudaGetDevice(&previous) != cudaSuccess)
+			previous = -1;
+		if (previous != device)
+			cudaSetDevice(device);
+		else
+			previous = -1; // nothing to restore
+	}
+	~DeviceGuard()
+	{
+		if (previous >= 0)
+			cudaSetDevice(previous);
+	}
+};
+
 // Pass calls launch on the caller's stream, which lives on the context's device: that device must be current
 // (the reference drives one VkDevice from one thread; nothing here switches devices behind the caller's back).
 bool device_is_current(NvcContext* ctx)
@@ -183,7 +203,7 @@ NVC_API void nvc_destroy(NvcContext* ctx)
 {
 	if (!ctx)
 		return;
-	cudaSetDevice(ctx->device);
+	DeviceGuard guard(ctx->device);
 	nvc::gather_destroy(ctx);
 	nvc::nccl_destroy(ctx);
 	if (ctx->scratch)
@@ -199,7 +219,7 @@ NVC_API int nvc_prepare_meshes(NvcContext* ctx, void* stream, const NvcMesh* mes
 {
 	if (!ctx)
 		return NVC_ERROR_INVALID_ARGUMENT;
-	cudaSetDevice(ctx->device);
+	DeviceGuard guard(ctx->device);
 	if (ctx->mesh_heads)
 	{
 		cudaDeviceSynchronize();
@@ -234,7 +254,7 @@ NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels)
 {
 	if (!ctx)
 		return NVC_ERROR_INVALID_ARGUMENT;
-	cudaSetDevice(ctx->device);
+	DeviceGuard guard(ctx->device);
 	ctx->hiz_stage_budget = texels > 11264 ? 11264 : texels; // 44 KB: stays under the 48 KB dynamic shared memory default
 	int early = 0, late = 0;
 	cudaError_t e = nvc::clustercull_occupancy(&early, &late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
