@@ -93,6 +93,48 @@ def test_kitten_4096_two_phase(golden_dir):
     assert o.read_counts()[0][0] > 0
 
 
+def test_cuda_reproduces_committed_vectors(golden_dir):
+    """The CUDA path against the COMMITTED expected outputs of BASELINE configs[0] + its two-phase variant
+    (tests/golden/c1_kitten_expected.npz, reproduced byte for byte by the oracle and by the reference's own shaders on the
+    CPU side): counters, dvb, mvb, pyramid digest exactly; command lists and cluster indices as sets."""
+    torch = _torch()
+    from niagara_b200.path import VisibilityPath
+
+    want = np.load(os.path.join(golden_dir, "c1_kitten_expected.npz"))
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten.nvcg"), 4096)
+
+    # (a) frustum + LOD only, draw-command path, every draw visible last frame
+    cd = s.cull_data(occlusion=False, cluster_occlusion=False, mesh_shading=False)
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen, mesh_shading=False)
+    g.dvb.fill_(1)
+    g.cull(cd, late=False, task=False)
+    torch.cuda.synchronize()
+    n = int(g.read_counts()[0][0])
+    assert n == int(want["a_count"])
+    got = g.read_draw_commands(n).view(np.uint32).reshape(n, 6)
+    order = lambda a: a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(order(got), order(want["a_commands"]))
+
+    # (b) two frames of the full two-phase path with cone culling
+    cd = s.cull_data()
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen)
+    g.set_visibility_bits(s.visibility_bits)
+    depth = torch.from_numpy(s.depth).cuda()
+    crc = lambda v: np.uint64(int(np.bitwise_xor.reduce(v.astype(np.uint64) * np.arange(1, len(v) + 1, dtype=np.uint64)))) if len(v) else np.uint64(0)
+    for f in range(2):
+        g.frame(cd, depth, cluster_backface=True)
+        torch.cuda.synchronize()
+        dccb, ccb = g.read_counts()
+        assert np.array_equal(dccb, want["b%d_dccb" % f]) and np.array_equal(ccb, want["b%d_ccb" % f])
+        assert np.array_equal(np.packbits(g.dvb.cpu().numpy()[: len(s.draws)].astype(np.uint8)), want["b%d_dvb" % f])
+        assert np.array_equal(g.mvb.cpu().numpy().astype(np.uint32), want["b%d_mvb" % f])
+        cmds = g.read_task_commands(int(dccb[1]) * 64).view(np.uint32).reshape(-1, 5)
+        assert np.array_equal(order(cmds), order(want["b%d_commands" % f]))
+    pyr = g.depthPyramid.cpu().numpy()
+    assert np.array_equal(pyr[-341:].view(np.uint32), want["b_pyramid_top"].view(np.uint32))
+    assert crc(pyr.view(np.uint32)) == want["b_pyramid_crc"]
+
+
 def test_cuda_vs_reference_shaders(golden_dir):
     """The CUDA path against the reference's OWN GLSL shaders run on the host (oracle/_ref/librefshader.so: the text of
     src/shaders/*.glsl compiled through oracle/refshader/glsl_shim.h by build(); the prebuilt library travels to the
