@@ -235,3 +235,23 @@ def test_cache_scene_runs_through_the_oracle():
     host.animate(s.animations, s.keyframes, 1.7, s.draws)
     o.draws[...] = s.draws
     o.frame(cd, s.depth, post_passes=True)
+
+
+def test_cpp_host_example_reads_the_same(tmp_path):
+    """examples/scene_cache_info.cpp (plain g++, host only): the C ABI used from C++ the way niagara's main() uses
+    loadSceneCache and its animation block — same meshlet data digest and same animated transforms as through ctypes."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples"), "scene_cache_info"], check=True)
+    path = os.path.join(GOLDEN, "animated.z.cache")
+    out = subprocess.run([os.path.join(ROOT, "examples", "scene_cache_info"), path, "0.2", "1.7"], check=True, capture_output=True, text=True).stdout
+    c = scene_cache.SceneCache(path)
+    digest = 1469598103934665603
+    for w in c.section("meshletdata").tolist():
+        digest = ((digest ^ w) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert "meshletdata: ok, %d words, fnv %016x" % (c.header.meshletdataCount, digest) in out
+    assert "t = 0.2: 0 draws move" in out
+    draws = c.section("draws").copy()
+    idx, val = host.animate(c.section("animations"), c.section("keyframes"), 1.7, draws)
+    line = [l for l in out.splitlines() if l.startswith("t = 1.7")][0]
+    assert line.startswith("t = 1.7: %d draws move" % len(idx))
+    for i, v in zip(idx, val):
+        assert "[%d] -> (%.9g %.9g %.9g) scale %.9g" % (i, v["position"][0], v["position"][1], v["position"][2], v["scale"]) in line
