@@ -339,9 +339,9 @@ NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push);
  * Replaces loadSceneCache (src/scenecache.cpp:273-370) for the arrays the visibility path consumes.  Host-only, no
  * CUDA calls: the caller maps the file, parses it once and copies Meshlet[] / Mesh[] / MeshDraw[] / Animation[] /
  * Keyframe[] straight from the mapping to the device (they are stored raw, scenecache.cpp:170,181-186).  The
- * meshopt-compressed sections are located by the header's byte counts; the per-meshlet stream ("meshlet codec",
- * scenecache.cpp:84-117,256-271) has a decoder here, the vertex / index / RT-position streams (rendering data, not
- * read by the visibility path) are reported with their extents and NVC_ERROR_UNSUPPORTED on read. */
+ * meshopt-compressed sections are located by the header's byte counts and decoded by nvc_scene_cache_read: the
+ * per-meshlet stream ("meshlet codec", scenecache.cpp:84-117,256-271), the vertex codec (vertices and RT positions) and
+ * the index codec.  Every stream is bounds-checked (NVC_ERROR_CORRUPT), nothing is written outside dst. */
 
 #define NVC_SCENE_CACHE_MAGIC 0x434E4353u /* 'SCNC', scenecache.cpp:12 */
 #define NVC_SCENE_CACHE_VERSION 7u        /* scenecache.cpp:13 */
@@ -418,7 +418,7 @@ typedef struct NvcAnimation
  * stream's size chain adds up to compressedMeshletDataBytes), fills the section table.  The caller decides about
  * hashMeta / meshlet limits / clrtMode / ommStates (loadSceneCache's other rejections, scenecache.cpp:283-290). */
 NVC_API int nvc_scene_cache_parse(const void* file, size_t file_size, NvcSceneCacheInfo* out);
-/* Copies (raw sections) or decodes (compressed NVC_CACHE_MESHLETDATA) one section into dst[decoded_bytes]. */
+/* Copies (raw sections) or decodes (compressed sections) one section into dst[decoded_bytes]. */
 NVC_API int nvc_scene_cache_read(const void* file, size_t file_size, const NvcSceneCacheInfo* info, int section,
     void* dst, size_t dst_bytes);
 

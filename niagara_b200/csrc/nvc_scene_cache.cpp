@@ -1,4 +1,6 @@
 // nvc_scene_cache.cpp — reader of the reference's scene cache (.cache v7), SURVEY §8(f) row N2.  Host only.
+// (The vertex / index codec streams are decoded by nvc_meshopt_decode.cpp; loadSceneCache's normalizeIndicesForOMM step,
+// scenecache.cpp:344-353, belongs to the ray-tracing feature and is not applied.)
 //
 // Follows src/scenecache.cpp: SceneHeader (16-55), the section order of saveSceneCache (158-197) and, for the
 // per-meshlet compressed stream, the layout written by writeMeshletDataCompressed (84-117): for every Meshlet, in
@@ -19,6 +21,13 @@
 #include "../../include/niagara_cull.h"
 
 #include <string.h>
+
+namespace nvc
+{
+// nvc_meshopt_decode.cpp
+int decode_vertex_stream(const uint8_t* stream, size_t stream_size, uint32_t vertex_count, uint32_t stride, uint8_t* out);
+int decode_index_stream(const uint8_t* stream, size_t stream_size, uint32_t index_count, uint32_t* out);
+} // namespace nvc
 
 namespace
 {
@@ -200,8 +209,14 @@ extern "C" NVC_API int nvc_scene_cache_read(const void* file, size_t file_size, 
 			memcpy(dst, base + sec.offset, sec.decoded_bytes);
 		return NVC_OK;
 	}
+	if (section == NVC_CACHE_VERTICES) // readVertexCompressed, scenecache.cpp:244-248, Vertex stride
+		return nvc::decode_vertex_stream(base + sec.offset, sec.stored_bytes, sec.count, 16, static_cast<uint8_t*>(dst));
+	if (section == NVC_CACHE_MESHLETVTX0) // uint16 x 4 per element of the stream (scenecache.cpp:329)
+		return sec.count % 4 ? NVC_ERROR_CORRUPT : nvc::decode_vertex_stream(base + sec.offset, sec.stored_bytes, sec.count / 4, 8, static_cast<uint8_t*>(dst));
+	if (section == NVC_CACHE_INDICES) // readIndexCompressed, scenecache.cpp:250-254
+		return nvc::decode_index_stream(base + sec.offset, sec.stored_bytes, sec.count, static_cast<uint32_t*>(dst));
 	if (section != NVC_CACHE_MESHLETDATA)
-		return NVC_ERROR_UNSUPPORTED; // meshopt vertex / index codec streams: rendering data, not on the visibility path
+		return NVC_ERROR_UNSUPPORTED;
 
 	// readMeshletDataCompressed, scenecache.cpp:256-271
 	memset(dst, 0, sec.decoded_bytes);

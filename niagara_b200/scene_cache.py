@@ -22,8 +22,8 @@ _DTYPES = {
 
 
 class SceneCache:
-    """A parsed cache file.  `section(name)` returns a numpy array (a copy; compressed meshlet data is decoded, the
-    meshopt vertex / index streams raise NvcError: they are rendering data the visibility path never reads)."""
+    """A parsed cache file.  `section(name)` returns a numpy array (a copy; the meshopt streams of a compressed cache —
+    vertices, indices, meshlet data, RT positions — are decoded)."""
 
     def __init__(self, path):
         self.path = path

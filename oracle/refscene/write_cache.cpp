@@ -10,6 +10,7 @@
 //                          (the meshlet codec rotates triangles, so this — not the raw cache — is what a reader of the
 //                          compressed cache must reproduce; bytes past triangleCount * 3 in a meshlet's last word are
 //                          whatever the reference's SIMD decoder left there)
+//     <prefix>.z.indices       geometry.indices (uint32[]) as the reference's loadSceneCache decodes <prefix>.z.cache
 //     <prefix>.nvca        animation golden: the frame loop's update (niagara.cpp:1362-1390, glm::mix / glm::slerp) applied
 //                          at a list of animationTime values; format below
 //
@@ -121,6 +122,12 @@ int main(int argc, char** argv)
 			return 1;
 		fwrite(g2.meshletdata.data(), sizeof(uint32_t), g2.meshletdata.size(), mf);
 		fclose(mf);
+		// the index codec rotates triangles as well: what the reference's loader returns is the golden, not the raw cache
+		FILE* xf = fopen((prefix + ".z.indices").c_str(), "wb");
+		if (!xf)
+			return 1;
+		fwrite(g2.indices.data(), sizeof(uint32_t), g2.indices.size(), xf);
+		fclose(xf);
 	}
 
 	// animation golden

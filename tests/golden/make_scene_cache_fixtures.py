@@ -43,8 +43,14 @@ def main():
     c = scene_cache.SceneCache(os.path.join(HERE, "kitten.z.cache"))
     ref = np.fromfile(os.path.join(tmp, "kitten.z.meshletdata"), dtype="<u4")
     mask = meaningful_bytes(c.section("meshlets"), len(ref))
+    def digest(path):
+        return hashlib.sha256(np.fromfile(path, dtype="<u4").tobytes()).hexdigest()
+
     expected = {
+        "animated": {"indices_sha256": digest(os.path.join(tmp, "animated.z.indices"))},
         "kitten": {
+            "indices_sha256": digest(os.path.join(tmp, "kitten.z.indices")),
+            "vertices_sha256": hashlib.sha256(scene_cache.SceneCache(os.path.join(tmp, "kitten.raw.cache")).section("vertices").tobytes()).hexdigest(),
             "meshletdata_words": int(len(ref)),
             "meshletdata_sha256_masked": hashlib.sha256((ref.view(np.uint8) * mask).tobytes()).hexdigest(),
             "meshlets": int(c.header.meshletCount),
