@@ -150,31 +150,26 @@ int main(int argc, char** argv)
 
 	for (double animationTime : times)
 	{
-		// niagara.cpp:1366-1390, the draw branch
-		for (Animation& animation : animations)
+		// What the frame loop does for draw animations (niagara.cpp:1366-1390), written out with the SAME glm calls
+		// (glm::mix for translation / scale, glm::slerp for rotation) so that glm's arithmetic — not ours — defines the golden:
+		// track position in keyframe units (double), wrapped with fmod; integer part picks the key pair, fraction blends.
+		for (const Animation& track : animations)
 		{
-			double index = (animationTime - animation.startTime) / animation.period;
-
-			if (index < 0)
+			if (track.drawIndex < 0)
 				continue;
-
-			index = fmod(index, double(animation.keyframeCount));
-
-			int index0 = int(index) % animation.keyframeCount;
-			int index1 = (index0 + 1) % animation.keyframeCount;
-
-			double t = index - floor(index);
-
-			const Keyframe& keyframe0 = keyframes[animation.keyframeOffset + index0];
-			const Keyframe& keyframe1 = keyframes[animation.keyframeOffset + index1];
-
-			if (animation.drawIndex >= 0)
-			{
-				MeshDraw& draw = draws[animation.drawIndex];
-				draw.position = glm::mix(keyframe0.translation, keyframe1.translation, float(t));
-				draw.scale = glm::mix(keyframe0.scale, keyframe1.scale, float(t));
-				draw.orientation = glm::slerp(keyframe0.rotation, keyframe1.rotation, float(t));
-			}
+			double cursor = (animationTime - track.startTime) / track.period;
+			if (cursor < 0)
+				continue; // not started yet
+			cursor = fmod(cursor, double(track.keyframeCount));
+			int from = int(cursor) % track.keyframeCount;
+			int to = (from + 1) % track.keyframeCount;
+			float blend = float(cursor - floor(cursor));
+			const Keyframe& k0 = keyframes[track.keyframeOffset + from];
+			const Keyframe& k1 = keyframes[track.keyframeOffset + to];
+			MeshDraw& target = draws[track.drawIndex];
+			target.position = glm::mix(k0.translation, k1.translation, blend);
+			target.scale = glm::mix(k0.scale, k1.scale, blend);
+			target.orientation = glm::slerp(k0.rotation, k1.rotation, blend);
 		}
 		fwrite(&animationTime, sizeof(double), 1, f);
 		fwrite(draws.data(), sizeof(MeshDraw), draws.size(), f);
