@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: produces golden vectors for the host-side helpers (niagara_b200/csrc/nvc_host.cpp) with the
 // reference's own math library (glm, compiled from /root/reference/extern/glm with the reference's defines).
-// niagara.cpp's main() cannot be compiled here (Vulkan/GLFW), so the few lines involved are restated verbatim in
-// spirit: PCG32 + random scene (niagara.cpp:449-481, 969-998) and the CullData fill (niagara.cpp:424-437, 1487-1516).
+// niagara.cpp's main() cannot be compiled here (Vulkan/GLFW), so what its few lines involved compute is written out
+// again, in our own terms, around the same glm calls: PCG32 + random scene (niagara.cpp:449-481, 969-998) and the CullData fill (niagara.cpp:424-437, 1487-1516).
 //
 // Output "NVCH" v1: u32 magic, u32 version, u32 drawCountA, u32 meshCountA, u32 drawCountB, u32 meshCountB, u32 cameraCount, u32 pad
 //   MeshDraw[drawCountA], MeshDraw[drawCountB], then per camera: {float pos[3], quat xyzw[4], fovY, znear, u32 w, u32 h, u32 drawCount, u32 lodStep} + CullData(144 B)
@@ -38,58 +38,45 @@ struct alignas(16) CullData
 static_assert(sizeof(CullData) == 144, "CullData");
 static_assert(sizeof(MeshDraw) == 48, "MeshDraw");
 
-struct pcg32_random_t
+// PCG32 (pcg-random.org minimal generator) with the stream constant niagara.cpp:449-466 seeds it with
+struct Pcg32
 {
-	uint64_t state, inc;
-};
-static pcg32_random_t rngstate = { 0x853c49e6748fea9bULL, 0xda3e39cb94b95bdbULL };
+	uint64_t state = 0x853c49e6748fea9bULL;
+	uint64_t stream = 0xda3e39cb94b95bdbULL;
 
-static uint32_t pcg32_random_r(pcg32_random_t* rng)
-{
-	uint64_t oldstate = rng->state;
-	rng->state = oldstate * 6364136223846793005ULL + (rng->inc | 1);
-	uint32_t xorshifted = uint32_t(((oldstate >> 18u) ^ oldstate) >> 27u);
-	uint32_t rot = oldstate >> 59u;
-	return (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
-}
-static double rand01() { return pcg32_random_r(&rngstate) / double(1ull << 32); }
-static uint32_t rand32() { return pcg32_random_r(&rngstate); }
-
-static std::vector<MeshDraw> randomScene(uint32_t drawCount, size_t meshCount)
-{
-	rngstate.state = 0x42;
-	std::vector<MeshDraw> draws(drawCount);
-	float sceneRadius = 300;
-	for (uint32_t i = 0; i < drawCount; ++i)
+	uint32_t next()
 	{
-		MeshDraw& draw = draws[i];
-		memset(&draw, 0, sizeof(draw));
-		size_t meshIndex = rand32() % meshCount;
-		draw.position[0] = float(rand01()) * sceneRadius * 2 - sceneRadius;
-		draw.position[1] = float(rand01()) * sceneRadius * 2 - sceneRadius;
-		draw.position[2] = float(rand01()) * sceneRadius * 2 - sceneRadius;
-		draw.scale = float(rand01()) + 1;
-		draw.scale *= 2;
-		vec3 axis = normalize(vec3(float(rand01()) * 2 - 1, float(rand01()) * 2 - 1, float(rand01()) * 2 - 1));
-		float angle = glm::radians(float(rand01()) * 90.f);
-		draw.orientation = quat(cosf(angle * 0.5f), axis * sinf(angle * 0.5f));
-		draw.meshIndex = uint32_t(meshIndex);
+		uint64_t s0 = state;
+		state = s0 * 6364136223846793005ULL + (stream | 1);
+		uint32_t x = uint32_t(((s0 >> 18u) ^ s0) >> 27u), r = uint32_t(s0 >> 59u);
+		return (x >> r) | (x << ((32 - r) & 31));
 	}
-	return draws;
-}
+	double unit() { return next() / double(1ull << 32); }
+};
+static Pcg32 g_rng;
+static double rand01() { return g_rng.unit(); }
 
-static mat4 perspectiveProjection(float fovY, float aspectWbyH, float zNear)
+// The random scene of niagara.cpp:969-998: per draw one mesh pick, a position in a 600^3 cube, scale in [2, 4), a rotation
+// of up to 90 degrees about a random axis.  The three-argument vec3(...) below must stay ONE expression: the reference
+// relies on the compiler's argument evaluation order there (GCC: right to left), and so does the golden.
+static std::vector<MeshDraw> randomScene(uint32_t count, size_t meshes)
 {
-	float f = 1.0f / tanf(fovY / 2.0f);
-	return mat4(f / aspectWbyH, 0.0f, 0.0f, 0.0f, 0.0f, f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, zNear, 0.0f);
-}
-static vec4 normalizePlane(vec4 p) { return p / length(vec3(p)); }
-static uint32_t previousPow2(uint32_t v)
-{
-	uint32_t r = 1;
-	while (r * 2 < v)
-		r *= 2;
-	return r;
+	g_rng.state = 0x42;
+	const float extent = 300;
+	std::vector<MeshDraw> out(count);
+	for (MeshDraw& d : out)
+	{
+		memset(&d, 0, sizeof(d));
+		d.meshIndex = uint32_t(g_rng.next() % meshes);
+		for (int c = 0; c < 3; ++c)
+			d.position[c] = float(rand01()) * extent * 2 - extent;
+		d.scale = float(rand01()) + 1;
+		d.scale *= 2;
+		vec3 axis = normalize(vec3(float(rand01()) * 2 - 1, float(rand01()) * 2 - 1, float(rand01()) * 2 - 1));
+		float half = glm::radians(float(rand01()) * 90.f) * 0.5f;
+		d.orientation = quat(cosf(half), axis * sinf(half));
+	}
+	return out;
 }
 
 struct CameraCase
@@ -100,39 +87,44 @@ struct CameraCase
 	uint32_t width, height, drawCount, lodStep;
 };
 
+// CullData as the frame loop fills it (niagara.cpp:1487-1516) from: the view matrix (camera transform inverted, Z flipped),
+// the infinite reverse-Z projection (niagara.cpp:424-432) and its two symmetric frustum planes — all through glm.
 static CullData fillCullData(const CameraCase& c)
 {
-	quat orientation(c.q[3], c.q[0], c.q[1], c.q[2]); // (w, x, y, z) scalar-first constructor is unaffected by GLM_FORCE_QUAT_CTOR_XYZW? no: use named init below
-	orientation.x = c.q[0], orientation.y = c.q[1], orientation.z = c.q[2], orientation.w = c.q[3];
-	mat4 view = glm::mat4_cast(orientation);
-	view[3] = vec4(vec3(c.pos[0], c.pos[1], c.pos[2]), 1.0f);
-	view = inverse(view);
-	view = glm::scale(glm::identity<glm::mat4>(), vec3(1, 1, -1)) * view;
+	quat rotation;
+	rotation.x = c.q[0], rotation.y = c.q[1], rotation.z = c.q[2], rotation.w = c.q[3];
+	mat4 camera = glm::mat4_cast(rotation);
+	camera[3] = vec4(vec3(c.pos[0], c.pos[1], c.pos[2]), 1.0f);
+	mat4 view = glm::scale(glm::identity<glm::mat4>(), vec3(1, 1, -1)) * inverse(camera);
 
-	mat4 projection = perspectiveProjection(c.fovY, float(c.width) / float(c.height), c.znear);
-	mat4 projectionT = transpose(projection);
-	vec4 frustumX = normalizePlane(projectionT[3] + projectionT[0]);
-	vec4 frustumY = normalizePlane(projectionT[3] + projectionT[1]);
+	float f = 1.0f / tanf(c.fovY / 2.0f), aspect = float(c.width) / float(c.height);
+	mat4 projection(f / aspect, 0.0f, 0.0f, 0.0f, 0.0f, f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, c.znear, 0.0f);
+	mat4 rows = transpose(projection);
+	vec4 planeX = rows[3] + rows[0], planeY = rows[3] + rows[1];
+	planeX = planeX / length(vec3(planeX));
+	planeY = planeY / length(vec3(planeY));
 
-	CullData cullData = {};
-	cullData.view = view;
-	cullData.P00 = projection[0][0];
-	cullData.P11 = projection[1][1];
-	cullData.znear = c.znear;
-	cullData.zfar = 200;
-	cullData.frustum[0] = frustumX.x;
-	cullData.frustum[1] = frustumX.z;
-	cullData.frustum[2] = frustumY.y;
-	cullData.frustum[3] = frustumY.z;
-	cullData.drawCount = c.drawCount;
-	cullData.cullingEnabled = 1;
-	cullData.lodEnabled = 1;
-	cullData.occlusionEnabled = 1;
-	cullData.lodTarget = (2 / cullData.P11) * (1.f / float(c.height)) * (1 << c.lodStep);
-	cullData.pyramidWidth = float(previousPow2(c.width));
-	cullData.pyramidHeight = float(previousPow2(c.height));
-	cullData.clusterOcclusionEnabled = 1;
-	return cullData;
+	auto pow2_below = [](uint32_t v) {
+		uint32_t r = 1;
+		while (r * 2 < v)
+			r *= 2;
+		return r;
+	};
+
+	CullData cd = {};
+	cd.view = view;
+	cd.P00 = projection[0][0];
+	cd.P11 = projection[1][1];
+	cd.znear = c.znear;
+	cd.zfar = 200;
+	cd.frustum[0] = planeX.x, cd.frustum[1] = planeX.z;
+	cd.frustum[2] = planeY.y, cd.frustum[3] = planeY.z;
+	cd.drawCount = c.drawCount;
+	cd.cullingEnabled = cd.lodEnabled = cd.occlusionEnabled = cd.clusterOcclusionEnabled = 1;
+	cd.lodTarget = (2 / cd.P11) * (1.f / float(c.height)) * (1 << c.lodStep);
+	cd.pyramidWidth = float(pow2_below(c.width));
+	cd.pyramidHeight = float(pow2_below(c.height));
+	return cd;
 }
 
 int main(int argc, char** argv)
