@@ -6,14 +6,9 @@
 // File format "NVCG" v1 (little endian):
 //   u32 magic 'NVCG', u32 version, u32 meshCount, u32 meshletCount, u32 drawCount, u32 reserved[3]
 //   Mesh[meshCount] (208 B), Meshlet[meshletCount] (24 B), MeshDraw[drawCount] (48 B)
-#include "common.h"
-#include "scene.h"
+#include "scene_arrays.h"
 
 #include <stdio.h>
-#include <string.h>
-
-// scene.cpp references this from textures.cpp only inside buildSceneOmm (ray-tracing feature, out of scope)
-unsigned char* decodeImageRGBA(const char*, int, unsigned int&, unsigned int&, unsigned int&) { return nullptr; }
 
 static_assert(sizeof(Mesh) == 208, "Mesh layout");
 static_assert(sizeof(Meshlet) == 24, "Meshlet layout");
@@ -28,33 +23,15 @@ int main(int argc, char** argv)
 		return 2;
 	}
 
-	Geometry geometry;
-	std::vector<Material> materials;
-	std::vector<MeshDraw> draws;
-	std::vector<Light> lights;
-	std::vector<std::string> texturePaths;
-	std::vector<Animation> animations;
-	std::vector<Keyframe> keyframes;
-	Camera camera = {};
-	vec3 sun(0.f);
-
-	// the reference's main() seeds a dummy material before loadScene (niagara.cpp: 'materials' index 0 = dummy)
-	materials.push_back(Material());
-
+	SceneArrays in;
 	for (int i = 2; i < argc; ++i)
-	{
-		const char* ext = strrchr(argv[i], '.');
-		bool ok;
-		if (ext && (strcmp(ext, ".gltf") == 0 || strcmp(ext, ".glb") == 0))
-			ok = loadScene(geometry, materials, draws, lights, texturePaths, animations, keyframes, camera, sun, argv[i]);
-		else
-			ok = loadMesh(geometry, argv[i]);
-		if (!ok)
+		if (!in.load(argv[i]))
 		{
 			fprintf(stderr, "failed to load %s\n", argv[i]);
 			return 1;
 		}
-	}
+	Geometry& geometry = in.geo;
+	std::vector<MeshDraw>& draws = in.draws;
 
 	FILE* f = fopen(argv[1], "wb");
 	if (!f)

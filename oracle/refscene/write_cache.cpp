@@ -17,14 +17,10 @@
 // NVCA v1 (little endian): u32 magic 'NVCA', u32 version, u32 animationCount, u32 keyframeCount, u32 drawCount, u32 timeCount,
 //   u32 reserved[2]; Animation[animationCount] (24 B); Keyframe[keyframeCount] (32 B); MeshDraw[drawCount] (initial);
 //   then timeCount records { f64 animationTime; MeshDraw[drawCount] (draws after the update at that time) }
-#include "common.h"
-#include "scene.h"
+#include "scene_arrays.h"
 
 #include <math.h>
 #include <stdio.h>
-#include <string.h>
-
-unsigned char* decodeImageRGBA(const char*, int, unsigned int&, unsigned int&, unsigned int&) { return nullptr; }
 
 static_assert(sizeof(Animation) == 24 && sizeof(Keyframe) == 32 && sizeof(MeshDraw) == 48, "layouts");
 
@@ -36,42 +32,39 @@ int main(int argc, char** argv)
 		return 2;
 	}
 
-	Geometry geometry;
-	std::vector<Material> materials;
-	std::vector<MeshDraw> draws;
-	std::vector<Light> lights;
-	std::vector<std::string> texturePaths;
-	std::vector<Animation> animations;
-	std::vector<Keyframe> keyframes;
-	Camera camera = {};
-	camera.orientation = quat(1, 0, 0, 0);
-	camera.fovY = glm::radians(70.f);
-	camera.znear = 0.1f;
-	vec3 sun = normalize(vec3(1.0f, 1.0f, 1.0f));
-
-	materials.push_back(Material()); // index 0 = dummy material, as niagara.cpp does before loadScene
-
+	SceneArrays in;
+	in.cam.orientation = quat(1, 0, 0, 0);
+	in.cam.fovY = glm::radians(70.f);
+	in.cam.znear = 0.1f;
+	in.sun = normalize(vec3(1.0f, 1.0f, 1.0f));
 	for (int i = 2; i < argc; ++i)
 	{
-		const char* ext = strrchr(argv[i], '.');
-		bool scene = ext && (strcmp(ext, ".gltf") == 0 || strcmp(ext, ".glb") == 0);
-		size_t firstMesh = geometry.meshes.size();
-		bool ok = scene ? loadScene(geometry, materials, draws, lights, texturePaths, animations, keyframes, camera, sun, argv[i]) : loadMesh(geometry, argv[i]);
-		if (!ok)
+		size_t firstMesh = in.geo.meshes.size();
+		bool scene = false;
+		if (!in.load(argv[i], &scene))
 		{
 			fprintf(stderr, "failed to load %s\n", argv[i]);
 			return 1;
 		}
-		if (!scene) // one identity draw per mesh
-			for (size_t m = firstMesh; m < geometry.meshes.size(); ++m)
+		if (!scene) // a bare mesh: one identity draw per mesh
+			for (size_t m = firstMesh; m < in.geo.meshes.size(); ++m)
 			{
 				MeshDraw draw = {};
 				draw.scale = 1.f;
 				draw.orientation = quat(1, 0, 0, 0);
 				draw.meshIndex = uint32_t(m);
-				draws.push_back(draw);
+				in.draws.push_back(draw);
 			}
 	}
+	Geometry& geometry = in.geo;
+	std::vector<Material>& materials = in.mats;
+	std::vector<MeshDraw>& draws = in.draws;
+	std::vector<Light>& lights = in.lights;
+	std::vector<std::string>& texturePaths = in.textures;
+	std::vector<Animation>& animations = in.tracks;
+	std::vector<Keyframe>& keyframes = in.keys;
+	Camera& camera = in.cam;
+	vec3& sun = in.sun;
 
 	// meshletVisibilityOffset as niagara.cpp:1003-1020 assigns it
 	uint32_t meshletVisibilityCount = 0;
