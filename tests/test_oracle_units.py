@@ -1,6 +1,7 @@
 """CPU-only: pins the oracle's scalar pieces with hand-computed / analytic cases, exhaustive conversions and the
 independent numpy restatement (tests/numpy_ref.py).  The reference holds no golden vectors for this path
-(SURVEY F3), so these are the anchors the oracle has; see DESIGN.md "parity unpinned"."""
+(SURVEY F3); the strongest anchor is tests/test_refshader.py (the reference's own shaders run on the host), these are
+the independent ones; see DESIGN.md §2."""
 import ctypes
 import math
 import os
