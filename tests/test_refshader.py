@@ -270,3 +270,36 @@ def test_hostile_inputs_against_reference_shaders(golden_dir):
         # culling off: draws with NaN / inf centres pass the frustum stage and reach projectSphere and the sampler
         total += _lockstep(s, s.cull_data(culling=False), frames=2)
     assert total > 1000
+
+
+def test_full_size_c4_against_reference_shaders():
+    """BASELINE configs[3] at FULL size (1M draws x 10 unique meshlets, 4096^2 depth): two frames in lock step, the oracle
+    (the checker of the GPU suite's full-size run) against the reference's own shaders — 28M meshlet tests, bit for bit."""
+    s = scenes.config4_scene()
+    threads = os.cpu_count() or 8
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=threads, cmd_capacity=2 * len(s.draws))
+    r = refshader_lib.RefShaderPath(s.meshes, s.meshlets, s.draws, *s.screen, threads=threads, cmd_capacity=2 * len(s.draws))
+    for p in (o, r):
+        p.set_visibility_bits(s.visibility_bits)
+    cd = s.cull_data()
+    tested = 0
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                o.pyramid(s.depth)
+                r.pyramid(s.depth)
+                assert np.array_equal(o.pyramid_texels, r.pyramid_texels)
+            _sync(r, o)
+            o.cull(cd, late)
+            r.cull(cd, late)
+            assert np.array_equal(o.dvb, r.dvb) and np.array_equal(o.dccb, r.dccb)
+            n = int(o.dccb[1]) * 64
+            assert np.array_equal(oracle_lib.sorted_commands(o.read_task_commands(n)), oracle_lib.sorted_commands(r.read_task_commands(n)))
+            _sync(r, o)
+            o.render_clusters(cd, late, cluster_backface=True)
+            r.render_clusters(cd, late, cluster_backface=True)
+            assert np.array_equal(o.ccb, r.ccb) and np.array_equal(o.mvb, r.mvb)
+            count = int(o.ccb[0])
+            assert np.array_equal(np.sort(o.read_cluster_indices(count)), np.sort(r.read_cluster_indices(count)))
+            tested += int(o.read_task_commands(n)["taskCount"].sum())
+    assert tested > 25_000_000
