@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -340,6 +341,7 @@ inline bool drawDecision(const NvcCullData& cd, bool late, const NvcMeshDraw& dr
 struct Emit
 {
 	uint32_t di, lod, dv;
+	uint32_t groups; // task groups of the selected LOD (drawcull.comp.glsl:122)
 };
 
 // drawcull.comp.glsl:54-156 over draws [begin, end) in ascending di (= one legal order of the GLSL atomics).
@@ -359,7 +361,10 @@ void drawcullRange(const NvcCullData& cd, bool late, const NvcMeshDraw* draws, c
 		if (!reached)
 			continue;
 		if (r.emit)
-			emitted.push_back(Emit{ di, r.lodIndex, dv }); // dv = drawVisibility[di] before the :154 write
+		{
+			const NvcMeshLod& lod = mesh.lods[r.lodIndex];
+			emitted.push_back(Emit{ di, r.lodIndex, dv, (lod.meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE }); // dv = drawVisibility[di] before the :154 write
+		}
 		if (late)
 			dvb[di] = r.visible ? 1 : 0; // :154-155
 	}
@@ -381,6 +386,12 @@ inline bool clusterLane(const NvcCullData& cd, bool late, const NvcMeshTaskComma
 
 	uint32_t mi = mgi + command.taskOffset;
 	uint32_t mvi = mgi + command.meshletVisibilityOffset;
+
+	// early pass: a meshlet whose bit is clear cannot become visible (:91-92) and nothing else of the lane is observable,
+	// so the arithmetic below is skipped for it (the CPU baseline should not do work the result cannot depend on)
+	if (!late && cd.clusterOcclusionEnabled == 1 && cd.postPass == 0 && (__atomic_load_n(&mvb[mvi >> 5], __ATOMIC_RELAXED) & (1u << (mvi & 31))) == 0)
+		return false;
+
 	const NvcMeshlet& ml = meshlets[mi];
 
 	vec3 lc = { halfToFloat(ml.center[0]), halfToFloat(ml.center[1]), halfToFloat(ml.center[2]) };
@@ -434,7 +445,8 @@ void clusterRange(const NvcCullData& cd, bool late, const NvcMeshTaskCommand* cm
 		if (command.taskCount == 0)
 			continue; // padding command (tasksubmit.comp.glsl:42-46): no lane is valid
 		const NvcMeshDraw& meshDraw = draws[command.drawId];
-		for (uint32_t mgi = 0; mgi < NVC_TASK_WGSIZE; ++mgi)
+		const uint32_t lanes = std::min(command.taskCount, NVC_TASK_WGSIZE); // lanes >= taskCount are invalid (:84)
+		for (uint32_t mgi = 0; mgi < lanes; ++mgi)
 			if (clusterLane(cd, late, command, meshDraw, meshlets, mvb, hiz, mgi))
 				out.push_back(commandId | (mgi << 24)); // :138
 	}
@@ -518,6 +530,34 @@ private:
 	bool stop_ = false;
 };
 
+// Over-decomposed variant: `chunks` contiguous ranges handed out dynamically (an atomic counter), so that a slow or late
+// worker does not hold the pass back; fn(chunk, begin, end).  Results stay deterministic as long as the caller keeps
+// per-CHUNK outputs and concatenates them in chunk order.
+template <typename F>
+void parallelChunks(uint32_t n, int threads, uint32_t chunks, F&& fn)
+{
+	chunks = std::max(1u, std::min(chunks, std::max(1u, n)));
+	int nt = int(std::min<uint32_t>(uint32_t(std::max(1, threads)), chunks));
+	auto range = [&](uint32_t c) { fn(c, uint32_t(uint64_t(n) * c / chunks), uint32_t(uint64_t(n) * (c + 1) / chunks)); };
+	if (nt == 1)
+	{
+		for (uint32_t c = 0; c < chunks; ++c)
+			range(c);
+		return;
+	}
+	std::atomic<uint32_t> next{ 0 };
+	Pool::get().run(nt, [&](int) {
+		for (uint32_t c = next.fetch_add(1); c < chunks; c = next.fetch_add(1))
+			range(c);
+	});
+}
+
+inline uint32_t chunkCount(uint32_t n, int threads)
+{
+	// ~8 chunks per worker, at least 1024 items each
+	return std::max(1u, std::min(uint32_t(std::max(1, threads)) * 8u, (n + 1023u) / 1024u));
+}
+
 template <typename F>
 void parallelRanges(uint32_t n, int threads, F&& fn)
 {
@@ -557,8 +597,8 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 
 	uint32_t n = cd.drawCount;
 	int nt = std::max(1, threads);
-	std::vector<std::vector<Emit>> parts(size_t(std::max(1, nt)));
-	parallelRanges(n, nt, [&](int t, uint32_t b, uint32_t e) { drawcullRange(cd, late != 0, draws, meshes, draw_visibility, hiz ? &hv : nullptr, b, e, parts[size_t(t)], lod_out); });
+	std::vector<std::vector<Emit>> parts(size_t(nt == 1 ? 1u : chunkCount(n, nt)));
+	parallelChunks(n, nt, uint32_t(parts.size()), [&](uint32_t c, uint32_t b, uint32_t e) { drawcullRange(cd, late != 0, draws, meshes, draw_visibility, hiz ? &hv : nullptr, b, e, parts[c], lod_out); });
 
 	// commandCount starts at 0 (vkCmdFillBuffer(dccb, 0, 4, 0) niagara.cpp:1541).  Slot of every emitted draw = exclusive
 	// prefix sum in ascending di order (= the serial atomicAdd sequence); the per-thread lists are written in parallel.
@@ -569,10 +609,7 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 		uint64_t units = 0;
 		if (task)
 			for (const Emit& e : parts[t])
-			{
-				const NvcMeshLod& lod = meshes[draws[e.di].meshIndex].lods[e.lod];
-				units += (lod.meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
-			}
+				units += e.groups; // :122
 		else
 			units = parts[t].size();
 		part_base[t + 1] = uint32_t(part_base[t] + units);
@@ -582,7 +619,7 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 	if (task)
 	{
 		NvcMeshTaskCommand* out = static_cast<NvcMeshTaskCommand*>(commands);
-		parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+		parallelChunks(uint32_t(np), nt, uint32_t(np), [&](uint32_t, uint32_t pb, uint32_t pe) {
 			for (uint32_t t = pb; t < pe; ++t)
 			{
 				uint32_t dci = part_base[t]; // :123 atomicAdd
@@ -619,7 +656,7 @@ int orc_drawcull(const NvcCullData* cull, int late, int task, const NvcMeshDraw*
 	else
 	{
 		NvcMeshDrawCommand* out = static_cast<NvcMeshDrawCommand*>(commands);
-		parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+		parallelChunks(uint32_t(np), nt, uint32_t(np), [&](uint32_t, uint32_t pb, uint32_t pe) {
 			for (uint32_t t = pb; t < pe; ++t)
 			{
 				uint32_t dci = part_base[t];
@@ -660,8 +697,8 @@ int orc_clustercull(const NvcCullData* cull, int late, const NvcMeshTaskCommand*
 
 	uint32_t ncmd = command_count4[1] * 64;
 	int nt = std::max(1, threads);
-	std::vector<std::vector<uint32_t>> parts(static_cast<size_t>(nt));
-	parallelRanges(ncmd, nt, [&](int t, uint32_t b, uint32_t e) { clusterRange(cd, late != 0, task_commands, draws, meshlets, meshlet_visibility, hiz ? &hv : nullptr, b, e, parts[size_t(t)]); });
+	std::vector<std::vector<uint32_t>> parts(size_t(nt == 1 ? 1u : chunkCount(ncmd, nt)));
+	parallelChunks(ncmd, nt, uint32_t(parts.size()), [&](uint32_t c, uint32_t b, uint32_t e) { clusterRange(cd, late != 0, task_commands, draws, meshlets, meshlet_visibility, hiz ? &hv : nullptr, b, e, parts[c]); });
 
 	// clusterCount starts at 0 (vkCmdFillBuffer(ccb, 0, 4, 0) niagara.cpp:1586); index = position in ascending
 	// (commandId, mgi) order (:135 atomicAdd), entries past CLUSTER_LIMIT are dropped (:137)
@@ -670,7 +707,7 @@ int orc_clustercull(const NvcCullData* cull, int late, const NvcMeshTaskCommand*
 	for (size_t t = 0; t < np; ++t)
 		part_base[t + 1] = part_base[t] + parts[t].size();
 	const uint32_t count = uint32_t(part_base[np]);
-	parallelRanges(uint32_t(np), int(np), [&](int, uint32_t pb, uint32_t pe) {
+	parallelChunks(uint32_t(np), nt, uint32_t(np), [&](uint32_t, uint32_t pb, uint32_t pe) {
 		for (uint32_t t = pb; t < pe; ++t)
 		{
 			uint64_t index = part_base[t];
