@@ -29,6 +29,24 @@ def test_no_torch_types_in_abi():
     assert "torch" not in code and "at::" not in code and "cudaStream_t" not in code and "#include <cuda" not in code
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/niagara_cull.h compiles as strict C99 (the boundary a cgo / FFI binding would consume) and links against
+    the library from a C program that calls host-only entry points."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "niagara_cull.h"\n#include <stdio.h>\n'
+        "int main(void) { NvcHiZ h; if (nvc_hiz_layout(1920, 1080, &h) != NVC_OK) return 1;\n"
+        '  printf("%u %u %u %s\\n", h.width, h.height, h.levels, nvc_status_string(NVC_ERROR_CORRUPT)); return sizeof(NvcMeshlet) == 24 ? 0 : 2; }\n'
+    )
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(ROOT, "niagara_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir, "-lniagara_cull", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:3] == ["1024", "1024", "11"] and " ".join(out[3:]) == "corrupt scene cache"
+
+
 def test_layout_sizes():
     assert layout.MESHLET_DTYPE.itemsize == 24 and layout.MESHLET_DTYPE.fields["cone_axis"][1] == 8
     assert layout.MESH_DTYPE.itemsize == 208 and layout.MESH_DTYPE.fields["lods"][1] == 48 and layout.MESH_DTYPE.fields["lodCount"][1] == 32
