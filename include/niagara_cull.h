@@ -399,6 +399,17 @@ typedef struct NvcSceneCacheInfo
 	NvcSceneCacheSection sections[NVC_CACHE_SECTION_COUNT];
 } NvcSceneCacheInfo;
 
+/* The three meshopt stream decoders on their own (the same streams appear in glTF EXT_meshopt_compression buffers):
+ *   vertex codec v0 / v1   -> dst[vertex_count * vertex_size], vertex_size a multiple of 4, <= 256
+ *   index codec v0 / v1    -> dst[index_count] uint32, index_count a multiple of 3 (triangles come back rotated)
+ *   meshlet codec          -> vertex references (reference_size 2 or 4 bytes each) and triangle_count * 3 index bytes
+ * Return NVC_OK, NVC_ERROR_CORRUPT (malformed stream; nothing is written outside the destinations),
+ * NVC_ERROR_UNSUPPORTED (a newer codec version) or NVC_ERROR_INVALID_ARGUMENT. */
+NVC_API int nvc_decode_vertex_stream(void* dst, uint32_t vertex_count, uint32_t vertex_size, const void* stream, size_t stream_size);
+NVC_API int nvc_decode_index_stream(uint32_t* dst, uint32_t index_count, const void* stream, size_t stream_size);
+NVC_API int nvc_decode_meshlet_stream(void* references, uint32_t vertex_count, uint32_t reference_size, uint8_t* triangles,
+    uint32_t triangle_count, const void* stream, size_t stream_size);
+
 /* scene.h:141-161 */
 typedef struct NvcKeyframe
 {

@@ -240,3 +240,26 @@ extern "C" NVC_API int nvc_scene_cache_read(const void* file, size_t file_size, 
 	}
 	return NVC_OK;
 }
+
+extern "C" NVC_API int nvc_decode_vertex_stream(void* dst, uint32_t vertex_count, uint32_t vertex_size, const void* stream, size_t stream_size)
+{
+	if ((!dst && vertex_count) || !stream)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	return nvc::decode_vertex_stream(static_cast<const uint8_t*>(stream), stream_size, vertex_count, vertex_size, static_cast<uint8_t*>(dst));
+}
+
+extern "C" NVC_API int nvc_decode_index_stream(uint32_t* dst, uint32_t index_count, const void* stream, size_t stream_size)
+{
+	if ((!dst && index_count) || !stream)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	return nvc::decode_index_stream(static_cast<const uint8_t*>(stream), stream_size, index_count, dst);
+}
+
+extern "C" NVC_API int nvc_decode_meshlet_stream(void* references, uint32_t vertex_count, uint32_t reference_size, uint8_t* triangles, uint32_t triangle_count,
+    const void* stream, size_t stream_size)
+{
+	if (!stream || (reference_size != 2 && reference_size != 4) || vertex_count > 256 || triangle_count > 256 || (!references && vertex_count) || (!triangles && triangle_count))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	return decodeMeshletBlock(static_cast<const uint8_t*>(stream), stream_size, vertex_count, triangle_count, reference_size, static_cast<uint8_t*>(references), triangles) ? NVC_OK
+	                                                                                                                                                                     : NVC_ERROR_CORRUPT;
+}
