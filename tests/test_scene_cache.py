@@ -306,3 +306,45 @@ def test_decoders_under_address_and_ub_sanitizers(tmp_path):
         run = subprocess.run([exe, os.path.join(GOLDEN, cache), "1500"], capture_output=True, text=True)
         assert run.returncode == 0, run.stderr[-2000:]
         assert "mutations 1500" in run.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libanim_ref.so")), reason="needs glm from the reference (oracle/_ref/libanim_ref.so)")
+def test_animation_blend_against_glm_on_random_keyframes():
+    """Property test of nvc_host_animate's blend against glm::mix / glm::slerp themselves (oracle/refscene/anim_ref.cpp):
+    random unit and non-unit quaternions, nearly identical ones (glm's lerp shortcut), opposite ones (sign flip), exact 0 / 1
+    and tiny blend factors — bit for bit."""
+    if os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    glm = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libanim_ref.so"))
+    glm.anim_ref_blend.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]
+    rng = np.random.default_rng(8)
+    n = 4000
+    keys = np.zeros(2 * n, dtype=layout.KEYFRAME_DTYPE)
+    keys["translation"] = rng.uniform(-50, 50, (2 * n, 3)).astype(np.float32)
+    keys["scale"] = rng.uniform(0.1, 5, 2 * n).astype(np.float32)
+    q = rng.standard_normal((2 * n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[1::8] = q[0::8] + rng.standard_normal((len(q[0::8]), 4)) * 1e-5  # nearly the same rotation -> dot > 1 - eps
+    q[3::8] = -q[2::8] + rng.standard_normal((len(q[2::8]), 4)) * 0.3  # far side of the sphere -> dot < 0
+    q[5::8] = q[4::8]  # identical
+    q[7::16] *= 3.0  # not normalised
+    keys["rotation"] = q.astype(np.float32)
+    anims = np.zeros(n, dtype=layout.ANIMATION_DTYPE)
+    anims["drawIndex"] = np.arange(n)
+    anims["lightIndex"] = -1
+    anims["startTime"] = 0.0
+    anims["period"] = 1.0
+    anims["keyframeOffset"] = 2 * np.arange(n)
+    anims["keyframeCount"] = 2
+    out = np.zeros(8, np.float32)
+    for t in (0.0, 1.0 / 3.0, 0.5, 0.999999, 1e-7, 0.25):
+        draws = np.zeros(n, dtype=layout.MESHDRAW_DTYPE)
+        idx, val = host.animate(anims, keys, t, draws)  # index = t in [0, 1): keyframe 0 -> 1, blend factor float(t)
+        assert len(idx) == n
+        a = np.float32(t - np.floor(t))
+        for i in range(0, n, 1):
+            k0, k1 = keys[2 * i], keys[2 * i + 1]
+            glm.anim_ref_blend(k0["translation"].ctypes.data, float(k0["scale"]), k0["rotation"].ctypes.data, k1["translation"].ctypes.data, float(k1["scale"]), k1["rotation"].ctypes.data, float(a), out.ctypes.data)
+            got = np.concatenate([draws["position"][i], [draws["scale"][i]], draws["orientation"][i]]).astype(np.float32)
+            same = (got.view(np.uint32) == out.view(np.uint32)) | (np.isnan(got) & np.isnan(out))
+            assert same.all(), (t, i, got, out)
