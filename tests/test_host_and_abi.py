@@ -189,3 +189,40 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in src and "oracle_lib" not in src and "orc_" not in src, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libanim_ref.so")), reason="needs glm from the reference (oracle/_ref/libanim_ref.so)")
+def test_cull_data_against_glm_on_random_cameras():
+    """Property test of nvc_host_cull_data (glm-free: quaternion -> matrix, general 4x4 inverse, Z flip, projection, frustum
+    planes, lodTarget, pyramid size) against the same computation through glm (oracle/refscene/host_golden.h): 3000 random
+    cameras incl. non-unit and axis-aligned quaternions, extreme positions, fields of view and aspect ratios — all 136 bytes."""
+    import ctypes
+    import subprocess
+
+    if os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    glm = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libanim_ref.so"))
+    glm.cull_data_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+    rng = np.random.default_rng(31)
+    want = np.zeros(144, np.uint8)
+    for i in range(3000):
+        pos = (rng.standard_normal(3) * 10.0 ** rng.integers(-2, 5)).astype(np.float32)
+        q = rng.standard_normal(4)
+        kind = i % 5
+        if kind == 0:
+            q /= np.linalg.norm(q)
+        elif kind == 1:
+            q = np.eye(4)[rng.integers(0, 4)] * rng.choice([-1.0, 1.0])  # axis aligned: exact zeros and signed zeros in the matrix
+        elif kind == 2:
+            q = q / np.linalg.norm(q) * rng.uniform(0.5, 2.0)  # not normalised
+        elif kind == 3:
+            q = np.array([0, 0, 0, 1.0]) + rng.standard_normal(4) * 1e-4
+        q = q.astype(np.float32)
+        fov = float(np.float32(rng.uniform(0.05, 3.0)))
+        znear = float(np.float32(10.0 ** rng.uniform(-3, 1)))
+        w, h = int(rng.integers(1, 8192)), int(rng.integers(1, 8192))
+        n, step = int(rng.integers(0, 1 << 31)), int(rng.integers(0, 8))
+        glm.cull_data_ref(pos.ctypes.data, q.ctypes.data, fov, znear, w, h, n, step, want.ctypes.data)
+        cam = host.make_camera(tuple(float(x) for x in pos), tuple(float(x) for x in q), fov, znear)
+        cd = host.cull_data(cam, w, h, n, debug_lod_step=step)
+        assert bytes(cd)[:136] == want.tobytes()[:136], (i, kind, pos, q, fov, znear, w, h)
