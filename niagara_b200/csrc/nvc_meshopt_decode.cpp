@@ -63,22 +63,34 @@ bool read_byte_group(ByteReader& r, int width, uint8_t* out)
 	}
 	if (!r.take(size_t(2 * width), packed))
 		return false;
-	const uint32_t escape = (1u << width) - 1u;
-	const int per_byte = 8 / width;
+	// unpack without escapes first; a value equal to the all-ones code is then replaced by the next escape byte, in order
+	const uint8_t escape = uint8_t((1u << width) - 1u);
+	if (width == 4)
+		for (int i = 0; i < 8; ++i)
+		{
+			out[2 * i] = packed[i] >> 4;
+			out[2 * i + 1] = packed[i] & 15u;
+		}
+	else if (width == 2)
+		for (int i = 0; i < 4; ++i)
+		{
+			uint8_t b = packed[i];
+			out[4 * i] = b >> 6;
+			out[4 * i + 1] = (b >> 4) & 3u;
+			out[4 * i + 2] = (b >> 2) & 3u;
+			out[4 * i + 3] = b & 3u;
+		}
+	else // width 1: least significant bit first
+		for (int i = 0; i < 16; ++i)
+			out[i] = (packed[i >> 3] >> (i & 7)) & 1u;
 	for (int i = 0; i < 16; ++i)
-	{
-		uint32_t byte = packed[i / per_byte];
-		int slot = i % per_byte;
-		uint32_t v = width == 1 ? (byte >> slot) & 1u : (byte >> (8 - width * (slot + 1))) & escape;
-		if (v == escape)
+		if (out[i] == escape)
 		{
 			const uint8_t* e;
 			if (!r.take(1, e))
 				return false;
-			v = *e;
+			out[i] = *e;
 		}
-		out[i] = uint8_t(v);
-	}
 	return true;
 }
 
