@@ -398,6 +398,78 @@ int rs_mesh_clusters(const float* projection16, const NvcCullData* pass, float s
 	return NVC_OK;
 }
 
+// ---- the same consumer in task-shading mode (TASK = true, niagara.cpp:1666-1679): vkCmdDrawMeshTasksIndirectEXT(dccb, 4) runs
+// meshlet.task per command; EmitMeshTasksEXT(n, 1, 1) then launches n mesh workgroups that read payload.clusterIndices[gl_WorkGroupID.x].
+// Here the task stage's results are given (payloads[c], emit_counts[c] — from rs_taskcull, the oracle or the CUDA path) and the
+// mesh stage runs over them.  Output slot s = first_slot[c] + i for the i-th mesh workgroup of command c (first_slot = exclusive
+// prefix sum of emit_counts, which the caller computes); records / positions / triangles as in rs_mesh_clusters.
+int rs_mesh_payloads(const float* projection16, const NvcCullData* pass, float screen_width, float screen_height, const void* task_commands,
+    size_t commands_bytes, uint32_t command_count, const void* draws, size_t draws_bytes, const void* meshlets, size_t meshlets_bytes, const void* meshletdata,
+    size_t meshletdata_bytes, const void* vertices, size_t vertices_bytes, const NvcMeshTaskPayload* payloads, const uint32_t* emit_counts, const uint32_t* first_slot,
+    uint32_t* records, float* positions, uint8_t* triangles, int threads)
+{
+	TaskGlobals globals = {};
+	memcpy(globals.projection, projection16, sizeof(globals.projection));
+	globals.cullData = *pass;
+	globals.screenWidth = screen_width;
+	globals.screenHeight = screen_height;
+
+	const RsShader& s = rs_shader_meshlet_mesh;
+	s.spec(1, 1); // TASK = true: cluster indices come from the task payload
+	s.bind(0, const_cast<void*>(task_commands), commands_bytes);
+	s.bind(1, const_cast<void*>(draws), draws_bytes);
+	s.bind(2, const_cast<void*>(meshlets), meshlets_bytes);
+	s.bind(3, const_cast<void*>(meshletdata), meshletdata_bytes);
+	s.bind(4, const_cast<void*>(vertices), vertices_bytes);
+	s.bind(5, nullptr, 0);
+	s.push(&globals, sizeof(globals));
+
+	// one "dispatch" per task command: x = emitted mesh workgroups; the payload is the calling thread's taskPayloadSharedEXT object
+	std::atomic<uint32_t> next{ 0 };
+	auto worker = [&]() {
+		for (uint32_t c = next.fetch_add(1); c < command_count; c = next.fetch_add(1))
+		{
+			uint32_t n = emit_counts[c];
+			if (n > NVC_TASK_WGSIZE)
+				n = NVC_TASK_WGSIZE;
+			memcpy(s.payload(), &payloads[c], sizeof(NvcMeshTaskPayload));
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				runGroup(s, i, 0, 0);
+				size_t slot = size_t(first_slot[c]) + i;
+				uint vc = t_mesh_outputs[0], tc = t_mesh_outputs[1];
+				const uint* drawId = static_cast<const uint*>(s.output(0));
+				records[slot * 4 + 0] = vc;
+				records[slot * 4 + 1] = tc;
+				records[slot * 4 + 2] = vc ? drawId[0] : ~0u;
+				records[slot * 4 + 3] = c;
+				for (uint v = 0; v < vc && v < 64; ++v)
+					for (int k = 0; k < 4; ++k)
+						positions[(slot * 64 + v) * 4 + k] = glsl::gl_MeshVerticesEXT[v].gl_Position[k];
+				for (uint t = 0; t < tc && t < 96; ++t)
+				{
+					triangles[(slot * 96 + t) * 3 + 0] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].x);
+					triangles[(slot * 96 + t) * 3 + 1] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].y);
+					triangles[(slot * 96 + t) * 3 + 2] = uint8_t(glsl::gl_PrimitiveTriangleIndicesEXT[t].z);
+				}
+			}
+		}
+	};
+	int nt = std::max(1, std::min(threads, int(command_count)));
+	if (nt <= 1)
+		worker();
+	else
+	{
+		std::vector<std::thread> pool;
+		for (int t = 0; t < nt; ++t)
+			pool.emplace_back(worker);
+		for (std::thread& t : pool)
+			t.join();
+	}
+	s.spec(1, 0);
+	return NVC_OK;
+}
+
 // ---- a small reference rasteriser for end-to-end tests (OURS, not the reference's: Vulkan's fixed function) --------------
 // Facing as the mesh shader's own MESH_CULL code decides it (meshlet.mesh.glsl:154,175-181): in the y-up screen space
 // (clip.xy / clip.w * 0.5 + 0.5) * screen a triangle is front facing iff eb.x * ec.y > eb.y * ec.x (= the pipeline's

@@ -46,6 +46,8 @@ def load():
     lib.rs_depth_pyramid.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, hz, ctypes.c_int]
     lib.rs_mesh_clusters.restype = ctypes.c_int
     lib.rs_mesh_clusters.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, ctypes.c_int]
+    lib.rs_mesh_payloads.restype = ctypes.c_int
+    lib.rs_mesh_payloads.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, ctypes.c_uint32, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, ctypes.c_int]
     lib.rs_rasterize.restype = ctypes.c_int
     lib.rs_rasterize.argtypes = [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp, ctypes.c_int]
     lib.rs_project_sphere.restype = ctypes.c_int
@@ -125,6 +127,24 @@ class MeshStage:
         pd = p._pass_data(cull_data, 0, 0)
         w, h = p.depth_width, p.depth_height
         s = self.rs.rs_mesh_clusters(_p(self.projection), ctypes.byref(pd), float(w), float(h), _p(dcb), _n(dcb), _p(p.draws), _n(p.draws), _p(p.meshlets), _n(p.meshlets), _p(self.meshletdata), _n(self.meshletdata), _p(self.vertices), _n(self.vertices), _p(cib), _n(cib), _p(ccb), _p(rec), _p(pos), _p(tri), self.threads)
+        assert s == 0, s
+        return rec[:slots], pos[:slots], tri[:slots]
+
+    def run_payloads(self, cull_data, payloads, emit_counts, dcb=None):
+        """Task-shading mode: the mesh stage (TASK = true) over task payloads.  Returns records (…, command id in column 3),
+        positions, triangles with one slot per emitted mesh workgroup, in command order."""
+        p = self.p
+        dcb = p.dcb if dcb is None else dcb
+        ncmd = len(emit_counts)
+        emit = np.minimum(np.ascontiguousarray(emit_counts, dtype=np.uint32), 64)
+        first = (np.cumsum(emit) - emit).astype(np.uint32)
+        slots = int(emit.sum())
+        rec = np.zeros((max(slots, 1), 4), np.uint32)
+        pos = np.zeros((max(slots, 1), 64, 4), np.float32)
+        tri = np.zeros((max(slots, 1), 96, 3), np.uint8)
+        payloads = np.ascontiguousarray(payloads, dtype=np.uint32)
+        pd = p._pass_data(cull_data, 0, 0)
+        s = self.rs.rs_mesh_payloads(_p(self.projection), ctypes.byref(pd), float(p.depth_width), float(p.depth_height), _p(dcb), _n(dcb), ncmd, _p(p.draws), _n(p.draws), _p(p.meshlets), _n(p.meshlets), _p(self.meshletdata), _n(self.meshletdata), _p(self.vertices), _n(self.vertices), _p(payloads), _p(emit), _p(first), _p(rec), _p(pos), _p(tri), self.threads)
         assert s == 0, s
         return rec[:slots], pos[:slots], tri[:slots]
 

@@ -140,3 +140,58 @@ def test_two_phase_frames_on_rasterised_depth(golden_dir, culler):
         pairs = (np.uint64(c["drawId"]) << np.uint64(32)) | (int(c["taskOffset"]) + np.nonzero(bits == 0)[0]).astype(np.uint64)
         rejected += int(np.isin(pairs, owner_pairs).sum())
     assert rejected > 20
+
+
+@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+def test_task_shading_mode_on_rasterised_depth(golden_dir, culler):
+    """The other submission mode (niagara.cpp:1666-1679): drawcull -> meshlet.task (payload + emit count per command, the
+    contract of nvc_taskcull) -> the reference's mesh shader with TASK = true reading the payloads.  Same closed loop, same
+    properties: disjoint early / late sets, image == brute force, every pixel owner emitted."""
+    screen = (512, 384)
+    s, vertices, meshletdata = _kitten_scene(golden_dir, 200, screen)
+    o = (oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    o.set_visibility_bits(s.visibility_bits)
+    gt = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    gt.set_visibility_bits(s.visibility_bits)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((0, 0, 0)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25))]
+    owners_total, late_total = 0, 0
+    for cam in cams:
+        s.camera = cam
+        cd = s.cull_data()
+        ms = refshader_lib.MeshStage(o, vertices, meshletdata, host.projection(cam, *screen))
+        depth = np.zeros((screen[1], screen[0]), np.float32)
+
+        def draw_pass(late):
+            o.cull(cd, late)
+            n = int(o.dccb[1]) * 64
+            payloads, emit = np.zeros((max(n, 1), 64), np.uint32), np.zeros(max(n, 1), np.uint32)
+            o.task_shading(cd, late, payloads, emit)
+            cmds = o.read_task_commands(n)
+            rec, pos, tri = ms.run_payloads(cd, payloads[:n], emit[:n])
+            assert len(rec) == int(emit[:n].sum()) and (rec[:, 0] > 0).all()
+            # what the mesh stage decoded == what the payloads say: (drawId, meshlet) per slot
+            ci = np.concatenate([payloads[c, : emit[c]] for c in range(n)]) if n else np.zeros(0, np.uint32)
+            assert np.array_equal(ci & 0xFFFFFF, rec[:, 3])
+            assert np.array_equal(rec[:, 2], cmds["drawId"][ci & 0xFFFFFF])
+            assert np.array_equal(rec[:, 1], s.meshlets["triangleCount"][cmds["taskOffset"][ci & 0xFFFFFF] + (ci >> 24)])
+            ms.rasterize(rec, pos, tri, depth)
+            return oracle_lib.cluster_pairs(ci, cmds)
+
+        early = draw_pass(False)
+        o.pyramid(depth)
+        late = draw_pass(True)
+        assert len(np.intersect1d(early, late)) == 0
+        late_total += len(late)
+        gt.dvb[:] = 1
+        gt.cull(s.cull_data(culling=False, occlusion=False, cluster_occlusion=False), late=False)
+        all_cmds = gt.read_task_commands(int(gt.dccb[1]) * 64)
+        cib, ccb, ci = _all_clusters(all_cmds, int(gt.dccb[0]))
+        rec, pos, tri = ms.run(cd, cib=cib, ccb=ccb, dcb=gt.dcb)
+        truth = np.zeros_like(depth)
+        ms.rasterize(rec, pos, tri, truth)
+        assert np.array_equal(truth, depth)
+        own = ms.owners(rec, pos, tri, truth)
+        owner_pairs = oracle_lib.cluster_pairs(ci[own[: len(ci)]], all_cmds)
+        assert np.isin(owner_pairs, np.union1d(early, late)).all()
+        owners_total += len(owner_pairs)
+    assert owners_total > 3000 and late_total > 0
