@@ -30,9 +30,11 @@ thread_local uint gl_LocalInvocationIndex;
 thread_local MeshPerVertex gl_MeshVerticesEXT[256];
 thread_local uvec3 gl_PrimitiveTriangleIndicesEXT[256];
 thread_local MeshPerPrimitive gl_MeshPrimitivesEXT[256];
+thread_local int gl_VertexIndex, gl_DrawIDARB;
+thread_local vec4 gl_Position;
 } // namespace glsl
 
-extern const RsShader rs_shader_drawcull, rs_shader_tasksubmit, rs_shader_clustercull, rs_shader_clustersubmit, rs_shader_depthreduce, rs_shader_meshlet_task, rs_shader_meshlet_mesh;
+extern const RsShader rs_shader_drawcull, rs_shader_tasksubmit, rs_shader_clustercull, rs_shader_clustersubmit, rs_shader_depthreduce, rs_shader_meshlet_task, rs_shader_meshlet_mesh, rs_shader_mesh_vert;
 
 namespace
 {
@@ -229,8 +231,8 @@ extern "C"
 const char* rs_sources(void)
 {
 	static char buf[512];
-	snprintf(buf, sizeof(buf), "%s %s %s %s %s %s %s", rs_shader_drawcull.source, rs_shader_tasksubmit.source, rs_shader_clustercull.source,
-	    rs_shader_clustersubmit.source, rs_shader_depthreduce.source, rs_shader_meshlet_task.source, rs_shader_meshlet_mesh.source);
+	snprintf(buf, sizeof(buf), "%s %s %s %s %s %s %s %s", rs_shader_drawcull.source, rs_shader_tasksubmit.source, rs_shader_clustercull.source,
+	    rs_shader_clustersubmit.source, rs_shader_depthreduce.source, rs_shader_meshlet_task.source, rs_shader_meshlet_mesh.source, rs_shader_mesh_vert.source);
 	return buf;
 }
 
@@ -479,6 +481,69 @@ int rs_mesh_payloads(const float* projection16, const NvcCullData* pass, float s
 // samples at pixel centres, inclusive edges; depth = clip.z / clip.w interpolated affinely, test GREATER (reverse Z, clear 0).
 // mode 0: depth[] = max(depth[], triangle depth).   mode 1: depth[] is read-only; slot_hit[slot] = 1 when some covered sample of
 // the slot has exactly the stored depth (i.e. the slot owns or ties a pixel of the final image).
+} // extern "C"
+
+namespace
+{
+
+// one triangle given as three clip-space corners; returns true when (mode 1) a covered sample has exactly the stored depth
+bool rasterTriangle(const float* const corner[3], uint32_t width, uint32_t height, float* depth, int mode)
+{
+	double sx[3], sy[3], sz[3];
+	for (int c = 0; c < 3; ++c)
+	{
+		const float* p = corner[c];
+		if (!(p[3] > 0.0f))
+			return false;
+		float fx = (p[0] / p[3] * 0.5f + 0.5f) * float(width), fy = (p[1] / p[3] * 0.5f + 0.5f) * float(height);
+		sx[c] = fx;
+		sy[c] = fy;
+		sz[c] = double(p[2] / p[3]);
+	}
+	double ebx = sx[1] - sx[0], eby = sy[1] - sy[0], ecx = sx[2] - sx[0], ecy = sy[2] - sy[0];
+	double area = ebx * ecy - eby * ecx;
+	if (!(area > 0.0))
+		return false; // back facing or zero area
+	// flipped viewport: rows count from the top; swapping two corners keeps the edge functions positive inside
+	for (int c = 0; c < 3; ++c)
+		sy[c] = double(height) - sy[c];
+	std::swap(sx[1], sx[2]);
+	std::swap(sy[1], sy[2]);
+	std::swap(sz[1], sz[2]);
+	double minx = std::min(sx[0], std::min(sx[1], sx[2])), maxx = std::max(sx[0], std::max(sx[1], sx[2]));
+	double miny = std::min(sy[0], std::min(sy[1], sy[2])), maxy = std::max(sy[0], std::max(sy[1], sy[2]));
+	if (!(maxx >= 0.0 && maxy >= 0.0 && minx <= double(width) && miny <= double(height)))
+		return false;
+	int x0 = int(std::max(0.0, floor(minx - 0.5))), x1 = int(std::min(double(width) - 1.0, ceil(maxx - 0.5)));
+	int y0 = int(std::max(0.0, floor(miny - 0.5))), y1 = int(std::min(double(height) - 1.0, ceil(maxy - 0.5)));
+	bool hit = false;
+	for (int y = y0; y <= y1; ++y)
+		for (int x = x0; x <= x1; ++x)
+		{
+			double px = x + 0.5, py = y + 0.5;
+			double w0 = (sx[1] - px) * (sy[2] - py) - (sy[1] - py) * (sx[2] - px);
+			double w1 = (sx[2] - px) * (sy[0] - py) - (sy[2] - py) * (sx[0] - px);
+			double w2 = (sx[0] - px) * (sy[1] - py) - (sy[0] - py) * (sx[1] - px);
+			if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0)
+				continue;
+			float z = float((w0 * sz[0] + w1 * sz[1] + w2 * sz[2]) / (w0 + w1 + w2));
+			float& d = depth[size_t(y) * width + x];
+			if (mode == 0)
+			{
+				if (z > d)
+					d = z;
+			}
+			else if (z == d)
+				hit = true;
+		}
+	return hit;
+}
+
+} // namespace
+
+extern "C"
+{
+
 int rs_rasterize(const float* positions, const uint8_t* triangles, const uint32_t* records, uint32_t slots, uint32_t width, uint32_t height, float* depth,
     uint8_t* slot_hit, int mode)
 {
@@ -487,62 +552,65 @@ int rs_rasterize(const float* positions, const uint8_t* triangles, const uint32_
 		uint32_t vc = records[slot * 4 + 0], tc = records[slot * 4 + 1];
 		for (uint32_t t = 0; t < tc && t < 96; ++t)
 		{
-			double sx[3], sy[3], sz[3];
-			bool behind = false;
+			const float* corner[3];
 			for (int c = 0; c < 3; ++c)
 			{
 				uint32_t v = triangles[(size_t(slot) * 96 + t) * 3 + c];
 				if (v >= vc)
 					return NVC_ERROR_INVALID_ARGUMENT;
-				const float* p = positions + (size_t(slot) * 64 + v) * 4;
-				if (!(p[3] > 0.0f))
-				{
-					behind = true;
-					break;
-				}
-				float fx = (p[0] / p[3] * 0.5f + 0.5f) * float(width), fy = (p[1] / p[3] * 0.5f + 0.5f) * float(height);
-				sx[c] = fx;
-				sy[c] = fy;
-				sz[c] = double(p[2] / p[3]);
+				corner[c] = positions + (size_t(slot) * 64 + v) * 4;
 			}
-			if (behind)
-				continue;
-			double ebx = sx[1] - sx[0], eby = sy[1] - sy[0], ecx = sx[2] - sx[0], ecy = sy[2] - sy[0];
-			double area = ebx * ecy - eby * ecx;
-			if (!(area > 0.0))
-				continue; // back facing or zero area
-			// flipped viewport: rows count from the top; swapping two corners keeps the edge functions positive inside
-			for (int c = 0; c < 3; ++c)
-				sy[c] = double(height) - sy[c];
-			std::swap(sx[1], sx[2]);
-			std::swap(sy[1], sy[2]);
-			std::swap(sz[1], sz[2]);
-			double minx = std::min(sx[0], std::min(sx[1], sx[2])), maxx = std::max(sx[0], std::max(sx[1], sx[2]));
-			double miny = std::min(sy[0], std::min(sy[1], sy[2])), maxy = std::max(sy[0], std::max(sy[1], sy[2]));
-			if (!(maxx >= 0.0 && maxy >= 0.0 && minx <= double(width) && miny <= double(height)))
-				continue;
-			int x0 = int(std::max(0.0, floor(minx - 0.5))), x1 = int(std::min(double(width) - 1.0, ceil(maxx - 0.5)));
-			int y0 = int(std::max(0.0, floor(miny - 0.5))), y1 = int(std::min(double(height) - 1.0, ceil(maxy - 0.5)));
-			for (int y = y0; y <= y1; ++y)
-				for (int x = x0; x <= x1; ++x)
-				{
-					double px = x + 0.5, py = y + 0.5;
-					double w0 = (sx[1] - px) * (sy[2] - py) - (sy[1] - py) * (sx[2] - px);
-					double w1 = (sx[2] - px) * (sy[0] - py) - (sy[2] - py) * (sx[0] - px);
-					double w2 = (sx[0] - px) * (sy[1] - py) - (sy[0] - py) * (sx[1] - px);
-					if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0)
-						continue;
-					float z = float((w0 * sz[0] + w1 * sz[1] + w2 * sz[2]) / (w0 + w1 + w2));
-					float& d = depth[size_t(y) * width + x];
-					if (mode == 0)
-					{
-						if (z > d)
-							d = z;
-					}
-					else if (z == d)
-						slot_hit[slot] = 1;
-				}
+			if (rasterTriangle(corner, width, height, depth, mode) && slot_hit)
+				slot_hit[slot] = 1;
 		}
+	}
+	return NVC_OK;
+}
+
+// ---- the draw path's consumer: vkCmdDrawIndexedIndirectCount(dcb + 4, dccb, drawCount, 24) with mesh.vert.glsl (niagara.cpp:1680-1694) --
+// For command i < command_count: indexCount indices from firstIndex, each + vertexOffset = gl_VertexIndex, gl_DrawIDARB = i; the vertex
+// shader's gl_Position is rasterised as above.  mode 0: depth = max; mode 1: command_hit[i] = 1 when the command owns / ties a pixel.
+int rs_draw_indexed(const float* projection16, const NvcCullData* pass, float screen_width, float screen_height, const void* draw_commands, size_t commands_bytes,
+    uint32_t command_count, const void* draws, size_t draws_bytes, const void* vertices, size_t vertices_bytes, const uint32_t* indices, size_t index_count,
+    uint32_t width, uint32_t height, float* depth, uint8_t* command_hit, int mode)
+{
+	TaskGlobals globals = {};
+	memcpy(globals.projection, projection16, sizeof(globals.projection));
+	globals.cullData = *pass;
+	globals.screenWidth = screen_width;
+	globals.screenHeight = screen_height;
+
+	const RsShader& s = rs_shader_mesh_vert;
+	s.bind(0, const_cast<void*>(draw_commands), commands_bytes);
+	s.bind(1, const_cast<void*>(draws), draws_bytes);
+	s.bind(2, const_cast<void*>(vertices), vertices_bytes);
+	s.push(&globals, sizeof(globals));
+
+	const NvcMeshDrawCommand* cmds = static_cast<const NvcMeshDrawCommand*>(draw_commands);
+	if (size_t(command_count) * sizeof(NvcMeshDrawCommand) > commands_bytes)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	for (uint32_t i = 0; i < command_count; ++i)
+	{
+		const NvcMeshDrawCommand& c = cmds[i];
+		if (uint64_t(c.firstIndex) + c.indexCount > index_count)
+			return NVC_ERROR_INVALID_ARGUMENT;
+		for (uint32_t inst = 0; inst < c.instanceCount; ++inst)
+			for (uint32_t t = 0; t + 2 < c.indexCount; t += 3)
+			{
+				float clip[3][4];
+				const float* corner[3];
+				for (int k = 0; k < 3; ++k)
+				{
+					glsl::gl_DrawIDARB = int(i);
+					glsl::gl_VertexIndex = int(indices[c.firstIndex + t + k] + c.vertexOffset);
+					s.main();
+					for (int q = 0; q < 4; ++q)
+						clip[k][q] = glsl::gl_Position[q];
+					corner[k] = clip[k];
+				}
+				if (rasterTriangle(corner, width, height, depth, mode) && command_hit)
+					command_hit[i] = 1;
+			}
 	}
 	return NVC_OK;
 }

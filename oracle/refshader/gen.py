@@ -17,6 +17,7 @@ Only declarations C++ cannot parse are rewritten; every statement inside a funct
   layout(binding = N) uniform texture2D / sampler / image2D    static objects (+ rs_bind)
   shared T x / taskPayloadSharedEXT T x      static thread_local   (one workgroup runs on one host thread)
   layout(triangles, ...) out                 dropped;  layout(location = N) out T x[]  ->  static thread_local T x[256]
+  layout(location = N) out T x  (vertex stage)   static thread_local T x
   void main()                                static void rs_main()
 """
 import os
@@ -66,7 +67,8 @@ def rewrite_shader(text, name):
         return "static const uint rs_local[3] = { %s, %s, %s };" % (m.group(1), m.group(2), m.group(3))
 
     text, n = re.subn(r"layout\s*\(\s*local_size_x\s*=\s*([^,]+?)\s*,\s*local_size_y\s*=\s*([^,]+?)\s*,\s*local_size_z\s*=\s*([^)]+?)\s*\)\s*in\s*;", local, text)
-    assert n == 1, "local size of %s" % name
+    assert n <= 1, "local size of %s" % name
+    has_local = n == 1
 
     def push(m):
         state["pc"] = True
@@ -112,6 +114,12 @@ def rewrite_shader(text, name):
 
     text = re.sub(r"layout\s*\(\s*location\s*=\s*(\d+)\s*\)\s*out\s+(?:flat\s+)?(\w+)\s+(\w+)\s*\[\s*\]\s*;", output, text)
 
+    def output_scalar(m):  # vertex stage: one value per invocation
+        outputs.append((int(m.group(1)), "&" + m.group(3)))
+        return "static thread_local %s %s;" % (m.group(2), m.group(3))
+
+    text = re.sub(r"layout\s*\(\s*location\s*=\s*(\d+)\s*\)\s*out\s+(?:flat\s+)?(\w+)\s+(\w+)\s*;", output_scalar, text)
+
     def payload(m):
         state["payload"] = m.group(2)
         return "static thread_local %s %s;" % (m.group(1), m.group(2))
@@ -123,7 +131,8 @@ def rewrite_shader(text, name):
     if "layout" in re.sub(r"//[^\n]*", "", text):
         raise SystemExit("gen.py: unhandled layout declaration left in %s" % name)
 
-    tail = ["", "static void rs_bind(int binding, void* p, size_t bytes)", "{", "\t(void)bytes;", "\tswitch (binding)", "\t{"]
+    tail = ["", "" if has_local else "static const uint rs_local[3] = { 1, 1, 1 }; // not a compute-like stage: one invocation per dispatch element",
+            "static void rs_bind(int binding, void* p, size_t bytes)", "{", "\t(void)bytes;", "\tswitch (binding)", "\t{"]
     for b in sorted(set(x[0] for x in binds)):
         tail.append("\tcase %d:" % b)
         for bb, stmt in binds:

@@ -424,6 +424,10 @@ extern thread_local MeshPerVertex gl_MeshVerticesEXT[256];
 extern thread_local uvec3 gl_PrimitiveTriangleIndicesEXT[256];
 extern thread_local MeshPerPrimitive gl_MeshPrimitivesEXT[256];
 void SetMeshOutputsEXT(uint vertexCount, uint primitiveCount);
+
+// ---- vertex stage (mesh.vert.glsl): one invocation per vertex of an indexed indirect draw ------------------------------
+extern thread_local int gl_VertexIndex, gl_DrawIDARB; // GL_ARB_shader_draw_parameters
+extern thread_local vec4 gl_Position;
 inline float round(float a) { return roundf(a); }
 
 void barrier();                              // yields to the other invocations of the workgroup (fibers), see driver.cpp

@@ -48,6 +48,8 @@ def load():
     lib.rs_mesh_clusters.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, ctypes.c_int]
     lib.rs_mesh_payloads.restype = ctypes.c_int
     lib.rs_mesh_payloads.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, ctypes.c_uint32, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+    lib.rs_draw_indexed.restype = ctypes.c_int
+    lib.rs_draw_indexed.argtypes = [vp, cd, ctypes.c_float, ctypes.c_float, vp, sz, ctypes.c_uint32, vp, sz, vp, sz, vp, sz, ctypes.c_uint32, ctypes.c_uint32, vp, vp, ctypes.c_int]
     lib.rs_rasterize.restype = ctypes.c_int
     lib.rs_rasterize.argtypes = [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp, ctypes.c_int]
     lib.rs_project_sphere.restype = ctypes.c_int
@@ -157,3 +159,23 @@ class MeshStage:
         s = self.rs.rs_rasterize(_p(pos), _p(tri), _p(rec), len(rec), depth.shape[1], depth.shape[0], _p(depth), _p(hit), 1)
         assert s == 0, s
         return hit[: len(rec)].astype(bool)
+
+
+class VertexStage:
+    """mesh.vert.glsl (the draw path's consumer of dcb / dccb under vkCmdDrawIndexedIndirectCount) + the same rasteriser."""
+
+    def __init__(self, path, vertices, indices, projection16):
+        self.p, self.rs = path, load()
+        self.vertices = np.ascontiguousarray(vertices)
+        self.indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        self.projection = np.ascontiguousarray(projection16, dtype=np.float32)
+
+    def draw(self, cull_data, depth, dcb=None, count=None, owners=False):
+        p = self.p
+        dcb = p.dcb if dcb is None else dcb
+        count = int(p.dccb[0]) if count is None else int(count)
+        hit = np.zeros(max(count, 1), np.uint8)
+        pd = p._pass_data(cull_data, 0, 0)
+        s = self.rs.rs_draw_indexed(_p(self.projection), ctypes.byref(pd), float(p.depth_width), float(p.depth_height), _p(dcb), _n(dcb), count, _p(p.draws), _n(p.draws), _p(self.vertices), _n(self.vertices), _p(self.indices), len(self.indices), depth.shape[1], depth.shape[0], _p(depth), _p(hit), 1 if owners else 0)
+        assert s == 0, s
+        return hit[:count].astype(bool)

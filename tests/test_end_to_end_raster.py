@@ -195,3 +195,56 @@ def test_task_shading_mode_on_rasterised_depth(golden_dir, culler):
         assert np.isin(owner_pairs, np.union1d(early, late)).all()
         owners_total += len(owner_pairs)
     assert owners_total > 3000 and late_total > 0
+
+
+@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+def test_draw_path_on_rasterised_depth(golden_dir, culler):
+    """The third submission mode (mesh shading off, niagara.cpp:1680-1694): drawcull writes MeshDrawCommand[] + a count, consumed by
+    vkCmdDrawIndexedIndirectCount with mesh.vert.glsl.  Geometry comes out of the reference-written compressed cache through OUR
+    codecs (vertices + indices of kitten.z.cache).  Closed loop as above: early / late draw sets disjoint, image == brute force of
+    every draw at its selected LOD, every pixel-owning draw emitted."""
+    from niagara_b200 import scene_cache
+
+    screen = (512, 384)
+    cache = scene_cache.SceneCache(os.path.join(golden_dir, "kitten.z.cache"))
+    vertices, indices, meshes, meshlets = cache.section("vertices"), cache.section("indices"), cache.section("meshes"), cache.section("meshlets")
+    s, _, _ = _kitten_scene(golden_dir, 160, screen)
+    assert np.array_equal(s.meshes, meshes)
+    cls = oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath
+    o = cls(meshes, meshlets, s.draws, *screen, mesh_shading=False, threads=8)
+    gt = oracle_lib.OraclePath(meshes, meshlets, s.draws, *screen, mesh_shading=False, threads=8)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((0, 0, 0)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25))]
+    toggles = dict(mesh_shading=False, cluster_occlusion=False)
+    owners_total, late_total, lods = 0, 0, set()
+    for cam in cams:
+        s.camera = cam
+        cd = s.cull_data(**toggles)
+        vs = refshader_lib.VertexStage(o, vertices, indices, host.projection(cam, *screen))
+        depth = np.zeros((screen[1], screen[0]), np.float32)
+
+        def draw_pass(late):
+            o.cull(cd, late, task=False)
+            n = int(o.dccb[0])
+            vs.draw(cd, depth)
+            cmds = o.read_draw_commands(n)
+            lods.update(cmds["indexCount"].tolist())
+            return np.sort(cmds["drawId"])
+
+        early = draw_pass(False)
+        o.pyramid(depth)
+        late = draw_pass(True)
+        assert len(np.intersect1d(early, late)) == 0 and len(np.unique(early)) == len(early)
+        late_total += len(late)
+        gt.dvb[:] = 1
+        gt.cull(s.cull_data(culling=False, occlusion=False, **toggles), late=False, task=False)
+        assert int(gt.dccb[0]) == len(s.draws)
+        vg = refshader_lib.VertexStage(gt, vertices, indices, host.projection(cam, *screen))
+        truth = np.zeros_like(depth)
+        vg.draw(cd, truth)
+        assert np.array_equal(truth, depth)
+        own = vg.draw(cd, truth, owners=True)
+        owner_draws = gt.read_draw_commands(len(s.draws))["drawId"][own]
+        assert np.isin(owner_draws, np.union1d(early, late)).all()
+        owners_total += len(owner_draws)
+        assert (truth > 0).mean() > 0.2
+    assert owners_total > 200 and late_total > 0 and len(lods) >= 2

@@ -34,7 +34,7 @@ def _bits_equal(a, b):
 
 def test_library_is_built_from_the_reference_shaders():
     names = refshader_lib.load().rs_sources().decode().split()
-    assert names == ["drawcull.comp.glsl", "tasksubmit.comp.glsl", "clustercull.comp.glsl", "clustersubmit.comp.glsl", "depthreduce.comp.glsl", "meshlet.task.glsl", "meshlet.mesh.glsl"]
+    assert names == ["drawcull.comp.glsl", "tasksubmit.comp.glsl", "clustercull.comp.glsl", "clustersubmit.comp.glsl", "depthreduce.comp.glsl", "meshlet.task.glsl", "meshlet.mesh.glsl", "mesh.vert.glsl"]
 
 
 def test_math_h_functions_random():
