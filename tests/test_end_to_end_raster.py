@@ -248,3 +248,68 @@ def test_draw_path_on_rasterised_depth(golden_dir, culler):
         owners_total += len(owner_draws)
         assert (truth > 0).mean() > 0.2
     assert owners_total > 200 and late_total > 0 and len(lods) >= 2
+
+
+def test_animated_cache_scene_with_post_pass(golden_dir):
+    """Everything at once on the scene the reference's importer made from tests/golden/animated.gltf: cache reader (N2) -> keyframe
+    animation between frames (N3) -> early / late / POST passes (postPass = 1 draws: the alpha-blended primitives) -> the reference's
+    mesh shader -> rasteriser -> pyramid.  Image == brute force of all 14 draws, every pixel-owning cluster emitted by exactly one pass."""
+    from niagara_b200 import scene_cache
+
+    screen = (512, 384)
+    path = os.path.join(golden_dir, "animated.z.cache")
+    s = scene_cache.load_scene(path, screen=screen)
+    cache = scene_cache.SceneCache(path)
+    vertices, meshletdata = cache.section("vertices"), cache.section("meshletdata")
+    assert set(s.draws["postPass"].tolist()) == {0, 1}
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=4)
+    o.set_visibility_bits(s.visibility_bits)
+    gt = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=4)
+    gt.set_visibility_bits(s.visibility_bits)
+    s.camera = host.make_camera((0.0, 1.0, 16.0), (0.0, 0.0, 0.0, 1.0), s.camera.fovY, s.camera.znear)
+    owners_total, post_total, moved = 0, 0, 0
+    for t in (0.0, 0.0, 0.7, 0.95, 1.6, 1.6):
+        idx, _ = host.animate(s.animations, s.keyframes, t, s.draws)
+        moved += len(idx)
+        o.draws[...] = s.draws
+        gt.draws[...] = s.draws
+        cd = s.cull_data()
+        ms = refshader_lib.MeshStage(o, vertices, meshletdata, host.projection(s.camera, *screen), threads=4)
+        depth = np.zeros((screen[1], screen[0]), np.float32)
+
+        def draw_pass(late, post):
+            o.cull(cd, late, post_pass=post)
+            o.render_clusters(cd, late, post_pass=post)
+            n = int(o.ccb[0])
+            rec, pos, tri = ms.run(cd)
+            assert int((rec[:, 0] > 0).sum()) == n
+            ms.rasterize(rec, pos, tri, depth)
+            return oracle_lib.cluster_pairs(o.read_cluster_indices(n), o.read_task_commands(int(o.dccb[1]) * 64))
+
+        early = draw_pass(False, 0)
+        o.pyramid(depth)
+        late = draw_pass(True, 0)
+        post = draw_pass(True, 1)
+        assert len(np.intersect1d(early, late)) == 0 and len(np.intersect1d(np.union1d(early, late), post)) == 0
+        post_total += len(post)
+
+        truth = np.zeros_like(depth)
+        everything = []
+        for pp in (0, 1):
+            gt.dvb[:] = 1
+            gt.cull(s.cull_data(culling=False, occlusion=False, cluster_occlusion=False), late=False, post_pass=pp)
+            cmds = gt.read_task_commands(int(gt.dccb[1]) * 64)
+            cib, ccb, ci = _all_clusters(cmds, int(gt.dccb[0]))
+            mg = refshader_lib.MeshStage(gt, vertices, meshletdata, host.projection(s.camera, *screen), threads=4)
+            rec, pos, tri = mg.run(cd, cib=cib, ccb=ccb)
+            mg.rasterize(rec, pos, tri, truth)
+            everything.append((mg, rec, pos, tri, ci, cmds.copy()))
+        assert np.array_equal(truth, depth)
+        emitted = np.union1d(np.union1d(early, late), post)
+        for mg, rec, pos, tri, ci, cmds in everything:
+            own = mg.owners(rec, pos, tri, truth)
+            owner_pairs = oracle_lib.cluster_pairs(ci[own[: len(ci)]], cmds)
+            assert np.isin(owner_pairs, emitted).all()
+            owners_total += len(owner_pairs)
+        assert (truth > 0).mean() > 0.02
+    assert moved >= 9 and post_total > 0 and owners_total > 100
