@@ -22,12 +22,19 @@ struct Pk // run-time constants that keep ptxas from contracting (see above)
 	f2 one, neg_one;
 };
 
+#if defined(NVC_EMU) // CPU emulation of the kernels (tests/cuda_emu): each half is one IEEE operation
+__device__ __forceinline__ f2 pk(float a, float b)
+{
+	return f2(__float_as_uint(a)) | (f2(__float_as_uint(b)) << 32);
+}
+#else
 __device__ __forceinline__ f2 pk(float a, float b)
 {
 	f2 r;
 	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
 	return r;
 }
+#endif
 
 __device__ __forceinline__ float lo(f2 v)
 {
@@ -44,6 +51,10 @@ __device__ __forceinline__ f2 bc(float s) // broadcast a scalar to both halves
 	return pk(s, s);
 }
 
+#if defined(NVC_EMU)
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return pk(__fmul_rn(lo(a), lo(b)), __fmul_rn(hi(a), hi(b))); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return pk(__fmaf_rn(lo(a), lo(b), lo(c)), __fmaf_rn(hi(a), hi(b), hi(c))); }
+#else
 __device__ __forceinline__ f2 mul2(f2 a, f2 b)
 {
 	f2 d;
@@ -57,6 +68,7 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) // a genuine fused multiply
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
 	return d;
 }
+#endif
 
 __device__ __forceinline__ f2 add2(const Pk& k, f2 a, f2 b)
 {

@@ -7,6 +7,13 @@
 namespace nvc
 {
 
+#if defined(NVC_EMU) // CPU emulation of the kernels (tests/cuda_emu): the bulk copy is a memcpy that is complete on return
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { memcpy(dst_smem, src_gmem, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+#else
+
 __device__ __forceinline__ uint32_t smem_addr(const void* p)
 {
 	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -45,5 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	    "r"(parity)
 	    : "memory");
 }
+
+#endif // NVC_EMU
 
 } // namespace nvc

@@ -1,0 +1,7 @@
+// TEST INFRASTRUCTURE — the parts of the library that are not emulated (multi-GPU transports)
+#include "nvc_internal.h"
+namespace nvc
+{
+void nccl_destroy(NvcContext*) {}
+void gather_destroy(NvcContext*) {}
+} // namespace nvc

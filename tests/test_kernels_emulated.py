@@ -1,0 +1,255 @@
+"""CPU-only: the PRODUCT's CUDA kernels executed under the SIMT emulation of tests/cuda_emu (nvc_kernels.cu + nvc_api.cu compiled
+by g++, same C ABI, host pointers) against the oracle — the -m gpu parity suite in miniature for a machine without a GPU.  It checks
+kernel logic (indexing, block / warp scans, flattening, compaction, staging, epilogues, arithmetic order); what only hardware can
+show (memory model, timing) stays with the GPU tests.  Build-time variants of the cluster kernels are covered too."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib
+from niagara_b200 import host, layout, scenes
+
+
+def _pair(s, defines=(), threads=4, **kw):
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=threads, **kw)
+    e = emu_lib.EmuPath(s.meshes, s.meshlets, s.draws, *s.screen, defines=defines, **kw)
+    o.set_visibility_bits(s.visibility_bits)
+    e.set_visibility_bits(s.visibility_bits)
+    return o, e
+
+
+def _compare_draw(o, e, task, what):
+    assert np.array_equal(o.dccb, e.dccb), (what, o.dccb, e.dccb)
+    if task:
+        n = int(o.dccb[1]) * 64
+        assert np.array_equal(oracle_lib.sorted_commands(o.read_task_commands(n)), oracle_lib.sorted_commands(e.read_task_commands(n))), what
+    else:
+        n = int(o.dccb[0])
+        assert np.array_equal(oracle_lib.sorted_commands(o.read_draw_commands(n)), oracle_lib.sorted_commands(e.read_draw_commands(n))), what
+    assert np.array_equal(o.dvb, e.dvb), what
+
+
+def _compare_clusters(o, e, what):
+    assert np.array_equal(o.ccb, e.ccb), (what, o.ccb, e.ccb)
+    n = int(o.ccb[0])
+    oc, ec = o.read_task_commands(int(o.dccb[1]) * 64), e.read_task_commands(int(e.dccb[1]) * 64)
+    assert np.array_equal(oracle_lib.cluster_pairs(o.read_cluster_indices(n), oc), oracle_lib.cluster_pairs(e.read_cluster_indices(n), ec)), what
+    pad = (n + 255) // 256 * 256
+    assert (e.cib[n:pad] == 0xFFFFFFFF).all(), what
+    assert np.array_equal(o.mvb, e.mvb), what
+
+
+def _frames(s, frames=2, toggles=None, cluster_backface=True, cameras=None, post_passes=False, defines=(), **kw):
+    o, e = _pair(s, defines=defines, **kw)
+    emitted = 0
+    for f in range(frames):
+        if cameras:
+            s.camera = cameras[f % len(cameras)]
+        cd = s.cull_data(**(toggles or {}))
+        passes = [(False, 0), (True, 0)] + ([(True, 1)] if post_passes else [])
+        for late, post in passes:
+            if late and post == 0:
+                o.pyramid(s.depth)
+                e.pyramid(s.depth)
+                assert np.array_equal(o.pyramid_texels.view(np.uint32), e.pyramid_texels.view(np.uint32)), ("pyramid", f)
+            o.cull(cd, late, post_pass=post)
+            e.cull(cd, late, post_pass=post)
+            _compare_draw(o, e, o.mesh_shading, ("cull", f, late, post))
+            if o.mesh_shading:
+                o.render_clusters(cd, late, post_pass=post, cluster_backface=cluster_backface)
+                e.render_clusters(cd, late, post_pass=post, cluster_backface=cluster_backface)
+                _compare_clusters(o, e, ("clusters", f, late, post))
+                emitted += int(o.ccb[0])
+            else:
+                emitted += int(o.dccb[0])
+    e.close()
+    return emitted
+
+
+def _kp(golden_dir, n, screen=(640, 480)):
+    return scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), n, screen=screen)
+
+
+@pytest.mark.parametrize("toggles", [dict(), dict(lod=False), dict(culling=False), dict(occlusion=False), dict(cluster_occlusion=False), dict(debug_lod_step=3)])
+def test_two_phase_frames(golden_dir, toggles):
+    assert _frames(_kp(golden_dir, 5000), frames=2, toggles=toggles) > 500
+
+
+@pytest.mark.parametrize("backface", [False, None])
+def test_cluster_backface_wiring(golden_dir, backface):
+    _frames(_kp(golden_dir, 3000), cluster_backface=backface)
+
+
+def test_moving_camera_and_post_pass(golden_dir):
+    s = _kp(golden_dir, 6000, screen=(800, 600))
+    s.draws["postPass"][::5] = 1
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((12, -4, 9), host.quat_from_axis_angle((0, 1, 0), 0.35)), host.make_camera((25, 3, -14), host.quat_from_axis_angle((0.1, 1, 0), 0.9))]
+    assert _frames(s, frames=3, cameras=cams, post_passes=True) > 500
+
+
+def test_draw_path(golden_dir):
+    assert _frames(_kp(golden_dir, 8000), frames=2, toggles=dict(mesh_shading=False, cluster_occlusion=False), mesh_shading=False) > 100
+
+
+def test_without_prepared_mesh_heads(golden_dir):
+    _frames(_kp(golden_dir, 3000), prepare_meshes=False) if False else None
+    s = _kp(golden_dir, 3000)
+    o, _ = _pair(s)
+    e = emu_lib.EmuPath(s.meshes, s.meshlets, s.draws, *s.screen, prepare_meshes=False)
+    e.set_visibility_bits(s.visibility_bits)
+    cd = s.cull_data()
+    for late in (False, True):
+        if late:
+            o.pyramid(s.depth)
+            e.pyramid(s.depth)
+        o.cull(cd, late)
+        e.cull(cd, late)
+        _compare_draw(o, e, True, late)
+
+
+def test_synthetic_c4_and_c2():
+    """uniform meshlet counts (the multiply-high flatten), 4-LOD meshes with several task groups per draw"""
+    assert _frames(scenes.config4_scene(draw_count=20000, screen=(1024, 1024)), frames=2, cmd_capacity=40000) > 10000
+    assert _frames(scenes.config2_scene(draw_count=30000, num_meshes=128, screen=(512, 512)), frames=2) > 100
+
+
+@pytest.mark.parametrize("size", [(64, 64), (100, 60), (30, 17), (129, 257), (2, 2), (1, 1), (256, 8), (1920, 1080), (1000, 3)])
+def test_pyramid_sizes(size):
+    w, h = size
+    depth = np.random.default_rng(w * 7 + h).random((h, w), dtype=np.float32)
+    blank = (np.zeros(1, layout.MESH_DTYPE), np.zeros(1, layout.MESHLET_DTYPE), np.zeros(1, layout.MESHDRAW_DTYPE))
+    o = oracle_lib.OraclePath(*blank, w, h)
+    e = emu_lib.EmuPath(*blank, w, h, prepare_meshes=False)
+    o.pyramid(depth)
+    e.pyramid(depth)
+    assert np.array_equal(o.pyramid_texels.view(np.uint32), e.pyramid_texels.view(np.uint32))
+
+
+def test_tiny_and_empty_inputs(golden_dir):
+    _frames(_kp(golden_dir, 1))
+    s = _kp(golden_dir, 3)
+    o, e = _pair(s)
+    cd = s.cull_data()
+    cd.drawCount = 0
+    for late in (False, True):
+        o.cull(cd, late)
+        e.cull(cd, late)
+        _compare_draw(o, e, True, late)
+        o.render_clusters(cd, late)
+        e.render_clusters(cd, late)
+        _compare_clusters(o, e, late)
+
+
+def test_overflow_limits(golden_dir):
+    """TASK_WGLIMIT / CLUSTER_LIMIT drop-and-clamp: counters keep counting, writes stop, group counts clamp"""
+    s = _kp(golden_dir, 4000)
+    cd = s.cull_data(occlusion=False, cluster_occlusion=False)
+    o, e = _pair(s, task_wglimit=64, cluster_limit=512)
+    o.dvb[:] = 1
+    e.dvb[:] = 1
+    o.cull(cd, False)
+    e.cull(cd, False)
+    assert np.array_equal(o.dccb, e.dccb) and int(o.dccb[0]) > 64
+    o.render_clusters(cd, False)
+    e.render_clusters(cd, False)
+    assert np.array_equal(o.ccb, e.ccb)
+
+
+def test_taskcull_payloads(golden_dir):
+    s = _kp(golden_dir, 3000)
+    o, e = _pair(s)
+    cd = s.cull_data()
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                o.pyramid(s.depth)
+                e.pyramid(s.depth)
+            o.cull(cd, late)
+            e.cull(cd, late)
+            n = int(o.dccb[1]) * 64
+            op, oe = np.zeros((max(n, 1), 64), np.uint32), np.zeros(max(n, 1), np.uint32)
+            ep, ee = np.zeros((max(n, 1), 64), np.uint32), np.zeros(max(n, 1), np.uint32)
+            o.task_shading(cd, late, op, oe, cluster_backface=True)
+            e.task_shading(cd, late, ep, ee, cluster_backface=True)
+            ot, et = o.read_task_commands(n), e.read_task_commands(n)
+
+            def table(cmds, payloads, counts):
+                return {tuple(cmds[i].tolist()): tuple(int(v) >> 24 for v in payloads[i][: counts[i]]) for i in range(n) if cmds["taskCount"][i]}
+
+            assert table(ot, op, oe) == table(et, ep, ee)
+            assert np.array_equal(o.mvb, e.mvb)
+
+
+def test_hostile_inputs(golden_dir):
+    import warnings
+
+    import hostile
+
+    s = hostile.hostile_scene(golden_dir, 6000)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((5, 2, -3), host.quat_from_axis_angle((0.3, 1, 0), 0.9))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _frames(s, frames=2, cameras=cams)
+        _frames(s, frames=2, toggles=dict(culling=False))
+
+
+@pytest.mark.parametrize("defines", [("NVC_PACKED=1",), ("NVC_ALIVE_FLATTEN=0",), ("NVC_UNIFORM_FLATTEN=0",), ("NVC_ALIVE_FLATTEN=0", "NVC_UNIFORM_FLATTEN=0")])
+def test_build_time_variants(golden_dir, defines):
+    """the compile-time variants of the cluster kernels (packed FP32x2 arithmetic, the flatten strategies)"""
+    assert _frames(_kp(golden_dir, 3000), defines=defines) > 300
+    assert _frames(scenes.config4_scene(draw_count=6000, screen=(512, 512)), defines=defines, cmd_capacity=12000) > 3000
+
+
+def test_tma_staged_hiz(golden_dir):
+    """nvc_set_hiz_staging: the late cluster pass reads the coarse mips from the staged shared-memory copy"""
+    s = _kp(golden_dir, 3000)
+    o, e = _pair(s)
+    assert e.emu.nvc_set_hiz_staging(e.ctx, 5461) == 0
+    cd = s.cull_data()
+    for late in (False, True):
+        if late:
+            o.pyramid(s.depth)
+            e.pyramid(s.depth)
+        o.cull(cd, late)
+        e.cull(cd, late)
+        o.render_clusters(cd, late, cluster_backface=True)
+        e.render_clusters(cd, late, cluster_backface=True)
+        _compare_clusters(o, e, late)
+
+
+def test_decode_update_and_cook(golden_dir):
+    """the smaller kernels: consumer walk, animated-draw scatter, meshlet bounds"""
+    s = _kp(golden_dir, 2500)
+    o, e = _pair(s)
+    cd = s.cull_data()
+    o.frame(cd, s.depth, cluster_backface=True)
+    e.frame(cd, s.depth, cluster_backface=True)
+    slots = int(e.ccb[2]) * 256
+    rec, stats = np.zeros((max(slots, 1), 4), np.uint32), np.zeros(4, np.uint32)
+    assert e.emu.nvc_decode_clusters(e.ctx, None, e.cib.ctypes.data, e.ccb.ctypes.data, e.dcb.ctypes.data, e.meshlets.ctypes.data, rec.ctypes.data, stats.ctypes.data) == 0
+    _, ostats = o.decode_clusters()
+    assert np.array_equal(stats, ostats) and stats[2] == 0
+
+    draws = s.draws.copy()
+    idx = np.array([5, 17, 2400, 99999], np.uint32)
+    val = np.zeros(4, layout.MESHDRAW_DTYPE)
+    val["scale"] = [1.5, 2.5, 3.5, 4.5]
+    assert e.emu.nvc_update_draws(e.ctx, None, draws.ctypes.data, len(draws), idx.ctypes.data, val.ctypes.data, 4) == 0
+    want = s.draws.copy()
+    want[idx[:3]] = val[:3]
+    assert np.array_equal(draws, want)
+
+    z = np.load(os.path.join(golden_dir, "kitten_cook.npz"))
+    positions, data = z["positions"], z["meshletdata"]
+    _, want_ml, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten.nvcg"))
+    vertices = np.zeros((len(positions), 8), np.uint16)
+    vertices[:, :3] = positions
+    got = want_ml.copy()
+    got.view(np.uint8).reshape(len(got), 24)[:, :12] = 0xCD
+    rej = np.full(1, 9, np.uint32)
+    assert e.emu.nvc_cook_meshlet_bounds(e.ctx, None, vertices.ctypes.data, len(vertices), data.ctypes.data, len(data), got.ctypes.data, len(got), rej.ctypes.data) == 0
+    assert rej[0] == 0 and np.array_equal(got, want_ml)
+    e.close()
