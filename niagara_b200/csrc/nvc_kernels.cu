@@ -72,6 +72,12 @@ typedef NvcCullData ClusterConsts;
 #ifndef NVC_UNIFORM_FLATTEN
 #define NVC_UNIFORM_FLATTEN 1
 #endif
+// NVC_SMEM_ITEMS=1 (early pass with visibility tracking): instead of re-deriving item -> (command, lane) per chunk with redux / ballot /
+// select_bit64, every command lane scatters its set visibility bits ONCE per batch into a per-warp shared-memory table; chunks then
+// read one 16-bit entry per item.  Validated under the CPU emulation (tests/test_kernels_emulated.py); not yet timed on B200.
+#ifndef NVC_SMEM_ITEMS
+#define NVC_SMEM_ITEMS 0
+#endif
 #ifndef NVC_CLUSTER_MIN_BLOCKS
 #define NVC_CLUSTER_MIN_BLOCKS 6
 #endif
@@ -709,6 +715,7 @@ __device__ __forceinline__ void update_visibility_bits(uint32_t* mvb, bool activ
 constexpr int kClusterBlock = 256;
 constexpr int kClusterWarps = kClusterBlock / 32;
 constexpr int kStage = 256; // staged cluster indices per warp before one global atomicAdd + coalesced write-out
+constexpr uint32_t kItems = 512; // NVC_SMEM_ITEMS: items of one batch that fit the per-warp table (larger batches take the generic path)
 
 __device__ __forceinline__ void flush_stage(const ClusterParams& p, uint32_t* stage, uint32_t& nst)
 {
@@ -732,6 +739,9 @@ template <bool LATE, bool STAGED>
 __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) clustercull_kernel(const ClusterParams p)
 {
 	__shared__ uint32_t s_stage[kClusterWarps][kStage];
+#if NVC_SMEM_ITEMS
+	__shared__ uint16_t s_items[LATE ? 1 : kClusterWarps][LATE ? 1 : kItems];
+#endif
 	__shared__ uint32_t s_is_last;
 	__shared__ __align__(8) uint64_t s_hiz_bar;
 	extern __shared__ __align__(16) float s_hiz[]; // coarse Hi-Z mips (STAGED only)
@@ -746,6 +756,11 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	uint32_t* stage = s_stage[warp];
 	uint32_t nst = 0;
+#if NVC_SMEM_ITEMS
+	uint16_t* const item_table = s_items[LATE ? 0 : warp];
+#else
+	uint16_t* const item_table = nullptr;
+#endif
 
 	// the reference dispatches (X,64,1) groups from dccb+4 (niagara.cpp:1599): commandId < X * 64
 	const uint32_t ncmd = p.command_count4[1] * 64u;
@@ -818,11 +833,31 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 		const bool uniform = NVC_UNIFORM_FLATTEN && count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0); // (count 1: the reciprocal would not fit)
 		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u; // ceil(2^32 / count0)
 
+		// NVC_SMEM_ITEMS: item table of this batch, entry = (command lane << 6) | meshlet lane, in flattened order
+		const bool use_table = NVC_SMEM_ITEMS && !LATE && alive_flatten && total <= kItems;
+		if (use_table)
+		{
+			uint16_t* tbl = item_table;
+			__syncwarp(); // the previous batch's readers are done
+			uint32_t k = excl;
+			for (uint32_t m = amask_lo; m; m &= m - 1u)
+				tbl[k++] = uint16_t((lane << 6) | uint32_t(__ffs(int(m)) - 1));
+			for (uint32_t m = amask_hi; m; m &= m - 1u)
+				tbl[k++] = uint16_t((lane << 6) | uint32_t(32 + __ffs(int(m)) - 1));
+			__syncwarp();
+		}
+
 		// item -> command mapping of the chunk starting at `base` (executed by all lanes)
 		auto map_chunk = [&](uint32_t base) -> ItemRef {
 			const uint32_t item = base + lane;
 			uint32_t j;
-			if (uniform)
+			uint32_t table_entry = 0;
+			if (use_table)
+			{
+				table_entry = item < total ? uint32_t(item_table[item]) : 0u;
+				j = table_entry >> 6;
+			}
+			else if (uniform)
 				j = __umulhi(item, recip);
 			else if (nz_prefix)
 			{
@@ -850,8 +885,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 			r.active = item < total;
 			r.drawId = __shfl_sync(0xffffffffu, c_draw, j);
 			r.lateVis = __shfl_sync(0xffffffffu, c_late, j);
-			uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j); // rank of the item inside its command
-			if (alive_flatten)
+			uint32_t mgi = use_table ? (table_entry & 63u) : item - __shfl_sync(0xffffffffu, excl, j); // rank of the item inside its command
+			if (alive_flatten && !use_table)
 			{
 				// the rank-th SET bit of the command's visibility window is the meshlet's lane index
 				const uint32_t mlo = __shfl_sync(0xffffffffu, amask_lo, j), mhi = __shfl_sync(0xffffffffu, amask_hi, j);

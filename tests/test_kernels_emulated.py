@@ -196,11 +196,14 @@ def test_hostile_inputs(golden_dir):
         _frames(s, frames=2, toggles=dict(culling=False))
 
 
-@pytest.mark.parametrize("defines", [("NVC_PACKED=1",), ("NVC_ALIVE_FLATTEN=0",), ("NVC_UNIFORM_FLATTEN=0",), ("NVC_ALIVE_FLATTEN=0", "NVC_UNIFORM_FLATTEN=0")])
+@pytest.mark.parametrize("defines", [("NVC_PACKED=1",), ("NVC_ALIVE_FLATTEN=0",), ("NVC_UNIFORM_FLATTEN=0",), ("NVC_ALIVE_FLATTEN=0", "NVC_UNIFORM_FLATTEN=0"), ("NVC_SMEM_ITEMS=1",)])
 def test_build_time_variants(golden_dir, defines):
     """the compile-time variants of the cluster kernels (packed FP32x2 arithmetic, the flatten strategies)"""
     assert _frames(_kp(golden_dir, 3000), defines=defines) > 300
     assert _frames(scenes.config4_scene(draw_count=6000, screen=(512, 512)), defines=defines, cmd_capacity=12000) > 3000
+    # several frames with a moving camera: the early pass sees sparse, changing visibility masks
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((12, -4, 9), host.quat_from_axis_angle((0, 1, 0), 0.35)), host.make_camera((25, 3, -14), host.quat_from_axis_angle((0.1, 1, 0), 0.9))]
+    assert _frames(_kp(golden_dir, 2500, screen=(800, 600)), frames=4, cameras=cams, defines=defines) > 300
 
 
 def test_tma_staged_hiz(golden_dir):
