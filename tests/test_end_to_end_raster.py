@@ -13,9 +13,18 @@ import os
 import numpy as np
 import pytest
 
+import emu_lib
 import oracle_lib
 import refshader_lib
 from niagara_b200 import host, layout, scenes
+
+CULLERS = ["oracle", "reference-shaders", "cuda-kernels-emulated"]
+
+
+def _culler(name):
+    """who runs drawcull / clustercull / taskcull / the pyramid: our oracle, the reference's own shaders (oracle/refshader), or the
+    PRODUCT's CUDA kernels under the CPU SIMT emulation (tests/cuda_emu)"""
+    return {"oracle": oracle_lib.OraclePath, "reference-shaders": refshader_lib.RefShaderPath, "cuda-kernels-emulated": emu_lib.EmuPath}[name]
 
 pytestmark = pytest.mark.skipif(not refshader_lib.available(), reason="needs /root/reference or a prebuilt oracle/_ref/librefshader.so")
 
@@ -51,12 +60,12 @@ def _all_clusters(cmds, count):
     return cib, np.array([len(ci), 16, max(pad // 256, 0), 16], np.uint32), ci
 
 
-@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+@pytest.mark.parametrize("culler", CULLERS)
 def test_two_phase_frames_on_rasterised_depth(golden_dir, culler):
     """culler = who runs drawcull / clustercull / depthreduce: our oracle, or the reference's own shaders."""
     screen = (512, 384)
     s, vertices, meshletdata = _kitten_scene(golden_dir, 300, screen)
-    o = (oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    o = _culler(culler)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
     o.set_visibility_bits(s.visibility_bits)
     # brute-force lister: the early drawcull with every draw marked visible and every test but LOD selection switched off
     gt = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=8)
@@ -142,14 +151,14 @@ def test_two_phase_frames_on_rasterised_depth(golden_dir, culler):
     assert rejected > 20
 
 
-@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+@pytest.mark.parametrize("culler", CULLERS)
 def test_task_shading_mode_on_rasterised_depth(golden_dir, culler):
     """The other submission mode (niagara.cpp:1666-1679): drawcull -> meshlet.task (payload + emit count per command, the
     contract of nvc_taskcull) -> the reference's mesh shader with TASK = true reading the payloads.  Same closed loop, same
     properties: disjoint early / late sets, image == brute force, every pixel owner emitted."""
     screen = (512, 384)
     s, vertices, meshletdata = _kitten_scene(golden_dir, 200, screen)
-    o = (oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
+    o = _culler(culler)(s.meshes, s.meshlets, s.draws, *screen, threads=8)
     o.set_visibility_bits(s.visibility_bits)
     gt = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *screen, threads=8)
     gt.set_visibility_bits(s.visibility_bits)
@@ -197,7 +206,7 @@ def test_task_shading_mode_on_rasterised_depth(golden_dir, culler):
     assert owners_total > 3000 and late_total > 0
 
 
-@pytest.mark.parametrize("culler", ["oracle", "reference-shaders"])
+@pytest.mark.parametrize("culler", CULLERS)
 def test_draw_path_on_rasterised_depth(golden_dir, culler):
     """The third submission mode (mesh shading off, niagara.cpp:1680-1694): drawcull writes MeshDrawCommand[] + a count, consumed by
     vkCmdDrawIndexedIndirectCount with mesh.vert.glsl.  Geometry comes out of the reference-written compressed cache through OUR
@@ -210,8 +219,7 @@ def test_draw_path_on_rasterised_depth(golden_dir, culler):
     vertices, indices, meshes, meshlets = cache.section("vertices"), cache.section("indices"), cache.section("meshes"), cache.section("meshlets")
     s, _, _ = _kitten_scene(golden_dir, 160, screen)
     assert np.array_equal(s.meshes, meshes)
-    cls = oracle_lib.OraclePath if culler == "oracle" else refshader_lib.RefShaderPath
-    o = cls(meshes, meshlets, s.draws, *screen, mesh_shading=False, threads=8)
+    o = _culler(culler)(meshes, meshlets, s.draws, *screen, mesh_shading=False, threads=8)
     gt = oracle_lib.OraclePath(meshes, meshlets, s.draws, *screen, mesh_shading=False, threads=8)
     cams = [host.make_camera((0, 0, 0)), host.make_camera((0, 0, 0)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25)), host.make_camera((4.0, 0.5, 3.0), host.quat_from_axis_angle((0, 1, 0), 0.25))]
     toggles = dict(mesh_shading=False, cluster_occlusion=False)
