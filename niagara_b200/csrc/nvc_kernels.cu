@@ -78,6 +78,17 @@ typedef NvcCullData ClusterConsts;
 #ifndef NVC_SMEM_ITEMS
 #define NVC_SMEM_ITEMS 0
 #endif
+// NVC_PDL=1: programmatic dependent launch.  Every frame kernel starts with cudaGridDependencySynchronize() and is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of pass N+1 are scheduled while pass N drains (the five passes of a
+// frame are 5 launches of 30-160 us each: ramp-up / drain is a measurable share).  Compiles; not yet run on B200 (build-time variant).
+#ifndef NVC_PDL
+#define NVC_PDL 0
+#endif
+#if NVC_PDL && !defined(NVC_EMU)
+#define NVC_GRID_DEPENDENCY_SYNC() cudaGridDependencySynchronize()
+#else
+#define NVC_GRID_DEPENDENCY_SYNC() ((void)0)
+#endif
 #ifndef NVC_CLUSTER_MIN_BLOCKS
 #define NVC_CLUSTER_MIN_BLOCKS 6
 #endif
@@ -166,6 +177,7 @@ constexpr uint32_t kDrawStage = 512; // commands staged per block before the coa
 template <bool LATE, bool TASK>
 __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
 {
+	NVC_GRID_DEPENDENCY_SYNC(); // nothing of the previous pass (scratch counters, dvb, pyramid) is touched before this point
 	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
 	__shared__ uint32_t s_block_base, s_block_total;
 	__shared__ uint32_t s_is_last;
@@ -746,6 +758,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 	__shared__ __align__(8) uint64_t s_hiz_bar;
 	extern __shared__ __align__(16) float s_hiz[]; // coarse Hi-Z mips (STAGED only)
 
+	NVC_GRID_DEPENDENCY_SYNC();
 	if (STAGED)
 		hiz_stage_begin(p.hiz, s_hiz, &s_hiz_bar); // the copy overlaps the first batch's command / geometry loads
 	bool hiz_ready = !STAGED;
@@ -1082,6 +1095,7 @@ __global__ void __launch_bounds__(kPyrBlock, NVC_PYRAMID_MIN_BLOCKS) pyramid_ker
 	__shared__ float s_b[(kPyrTile / 2) * (kPyrTile / 2)]; // levels 1, 3, 5
 	__shared__ uint32_t s_is_last;
 
+	NVC_GRID_DEPENDENCY_SYNC();
 	const HiZDesc& hz = p.hiz;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t tile_x = blockIdx.x * kPyrTile, tile_y = blockIdx.y * kPyrTile;
@@ -1464,11 +1478,33 @@ cudaError_t launch_pack_meshes(const NvcMesh* meshes, uint32_t count, MeshCullHe
 	return cudaGetLastError();
 }
 
+#if NVC_PDL && !defined(NVC_EMU)
+template <typename P, typename... Extra>
+static cudaError_t launch_pdl(void (*kernel)(P, Extra...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const P& p, Extra... extra)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, p, extra...);
+}
+#endif
+
 cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
 {
 	uint32_t blocks = (p.cull.drawCount + kDrawBlock - 1) / kDrawBlock;
 	if (blocks == 0)
 		blocks = 1;
+#if NVC_PDL && !defined(NVC_EMU)
+	void (*kernel)(DrawCullParams) = late ? (task ? drawcull_kernel<true, true> : drawcull_kernel<true, false>) : (task ? drawcull_kernel<false, true> : drawcull_kernel<false, false>);
+	return launch_pdl(kernel, dim3(blocks), dim3(kDrawBlock), 0, stream, p);
+#endif
 	if (late)
 	{
 		if (task)
@@ -1494,6 +1530,10 @@ uint32_t hiz_stage_bytes(const HiZDesc& hiz)
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream)
 {
 	const uint32_t stage_bytes = late ? hiz_stage_bytes(p.hiz) : 0u;
+#if NVC_PDL && !defined(NVC_EMU)
+	void (*kernel)(ClusterParams) = late ? (stage_bytes ? clustercull_kernel<true, true> : clustercull_kernel<true, false>) : clustercull_kernel<false, false>;
+	return launch_pdl(kernel, dim3(blocks), dim3(kClusterBlock), stage_bytes, stream, p);
+#endif
 	if (late && stage_bytes)
 		clustercull_kernel<true, true><<<blocks, kClusterBlock, stage_bytes, stream>>>(p);
 	else if (late)
@@ -1520,6 +1560,9 @@ cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream)
 	// 16-byte loads of the depth rows / 8-byte stores of mip 0 need aligned bases (row pitches are multiples of 4 / 2
 	// texels whenever a full 64-texel tile exists)
 	q.vector_ok = (reinterpret_cast<uintptr_t>(p.depth) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.hiz.texels) & 7u) == 0 && (p.depth_width & 3u) == 0;
+#if NVC_PDL && !defined(NVC_EMU)
+	return launch_pdl(exact ? pyramid_kernel<true> : pyramid_kernel<false>, grid, dim3(kPyrBlock), 0, stream, q);
+#endif
 	if (exact)
 		pyramid_kernel<true><<<grid, kPyrBlock, 0, stream>>>(q);
 	else

@@ -12,6 +12,8 @@ from niagara_b200 import _build  # noqa: E402
 VARIANTS = {
     "base": [],
     "smem_items": ["NVC_SMEM_ITEMS=1"],  # early cluster pass: per-batch item table in shared memory
+    "pdl": ["NVC_PDL=1"],  # programmatic dependent launch of the five frame kernels (compiles; semantics need the GPU parity run)
+    "pdl_smem_items": ["NVC_PDL=1", "NVC_SMEM_ITEMS=1"],
 }
 
 if __name__ == "__main__":
