@@ -97,3 +97,36 @@ def pending_test_hostile_inputs_culling_off(golden_dir):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         _run_frames(s, frames=2, toggles=dict(culling=False))
+
+
+def pending_test_frame_in_cuda_graph(golden_dir):
+    """include/niagara_cull.h promises that pass calls only enqueue (no allocation, no synchronisation) and can be captured into a
+    CUDA graph: capture one frame, replay it over two frames of state, compare with the oracle."""
+    import torch
+
+    from niagara_b200.path import VisibilityPath
+    from test_gpu_parity import _compare_cluster_pass, _compare_draw_pass
+
+    s = scenes.instanced_scene(os.path.join(golden_dir, "kitten_pirate.nvcg"), 20000, screen=(1280, 720))
+    g = VisibilityPath(s.meshes, s.meshlets, s.draws, *s.screen)
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=8)
+    g.set_visibility_bits(s.visibility_bits)
+    o.set_visibility_bits(s.visibility_bits)
+    depth = torch.from_numpy(s.depth).cuda()
+    cd = s.cull_data()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        g.frame(cd, depth, cluster_backface=True)  # warm-up outside capture (lazy module loading)
+        side.synchronize()
+        # restart from the initial state so that the replays line up with the oracle's frames
+        g.dvb.zero_()
+        g.mvb.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            g.frame(cd, depth, cluster_backface=True)
+    for f in range(2):
+        graph.replay()
+        torch.cuda.synchronize()
+        o.frame(cd, s.depth, cluster_backface=True)
+        _compare_draw_pass(g, o, True, ("graph", f))
+        _compare_cluster_pass(g, o, ("graph", f))
