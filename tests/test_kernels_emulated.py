@@ -256,3 +256,71 @@ def test_decode_update_and_cook(golden_dir):
     assert e.emu.nvc_cook_meshlet_bounds(e.ctx, None, vertices.ctypes.data, len(vertices), data.ctypes.data, len(data), got.ctypes.data, len(got), rej.ctypes.data) == 0
     assert rej[0] == 0 and np.array_equal(got, want_ml)
     e.close()
+
+
+def _guarded(arr):
+    """A copy of `arr` that ends exactly at an inaccessible page: any read or write past its end faults (the CPU counterpart of
+    compute-sanitizer's memcheck for the emulated kernels)."""
+    import mmap
+
+    page = mmap.PAGESIZE
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    n = max(len(raw), 1)
+    span = (n + page - 1) // page * page
+    m = mmap.mmap(-1, span + page, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    base = ctypes.addressof(ctypes.c_char.from_buffer(m))
+    assert libc.mprotect(base + span, page, 0) == 0, ctypes.get_errno()  # PROT_NONE
+    view = np.frombuffer(m, dtype=np.uint8, count=n, offset=span - n)
+    view[: len(raw)] = raw
+    out = view[: len(raw)].view(arr.dtype).reshape(arr.shape) if len(raw) else view[:0].view(arr.dtype)
+    _guarded.keep.append(m)
+    return out
+
+
+_guarded.keep = []
+
+
+@pytest.mark.parametrize("defines", [(), ("NVC_SMEM_ITEMS=1",)])
+def test_no_access_past_buffer_ends(golden_dir, defines):
+    """Every device buffer of the passes (draws, meshes, meshlets, dvb, dcb, dccb, cib, ccb, mvb, depth, pyramid) ends at a
+    PROT_NONE page while the emulated kernels run two frames + the small kernels: an overrun would be a SIGSEGV."""
+    s = _kp(golden_dir, 2047, screen=(333, 217))  # odd sizes: ragged last blocks / tiles
+    o = oracle_lib.OraclePath(s.meshes, s.meshlets, s.draws, *s.screen, threads=4)
+    o.set_visibility_bits(s.visibility_bits)
+    e = emu_lib.EmuPath(s.meshes, s.meshlets, s.draws, *s.screen, defines=defines, prepare_meshes=False)
+    e.set_visibility_bits(s.visibility_bits)
+    for name in ("meshes", "meshlets", "draws", "dvb", "dcb", "dccb", "cib", "ccb", "mvb", "pyramid_texels"):
+        setattr(e, name, _guarded(getattr(e, name)))
+    e.hiz.texels = e.pyramid_texels.ctypes.data
+    assert e.emu.nvc_prepare_meshes(e.ctx, None, e.meshes.ctypes.data, len(e.meshes)) == 0
+    depth = _guarded(s.depth)
+    cd = s.cull_data()
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                o.pyramid(s.depth)
+                e.pyramid(depth)
+            o.cull(cd, late)
+            e.cull(cd, late)
+            _compare_draw(o, e, True, (f, late))
+            o.render_clusters(cd, late, cluster_backface=True)
+            e.render_clusters(cd, late, cluster_backface=True)
+            _compare_clusters(o, e, (f, late))
+    n = int(e.dccb[1]) * 64
+    payloads, emit = _guarded(np.zeros((max(n, 1), 64), np.uint32)), _guarded(np.zeros(max(n, 1), np.uint32))
+    e.task_shading(cd, True, payloads, emit, cluster_backface=True)
+    slots = int(e.ccb[2]) * 256
+    rec, stats = _guarded(np.zeros((max(slots, 1), 4), np.uint32)), _guarded(np.zeros(4, np.uint32))
+    assert e.emu.nvc_decode_clusters(e.ctx, None, e.cib.ctypes.data, e.ccb.ctypes.data, e.dcb.ctypes.data, e.meshlets.ctypes.data, rec.ctypes.data, stats.ctypes.data) == 0
+    idx, val = _guarded(np.array([3, 2046, 5000], np.uint32)), _guarded(np.zeros(3, layout.MESHDRAW_DTYPE))
+    assert e.emu.nvc_update_draws(e.ctx, None, e.draws.ctypes.data, len(e.draws), idx.ctypes.data, val.ctypes.data, 3) == 0
+    z = np.load(os.path.join(golden_dir, "kitten_cook.npz"))
+    _, want_ml, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten.nvcg"))
+    vertices = np.zeros((len(z["positions"]), 8), np.uint16)
+    vertices[:, :3] = z["positions"]
+    gv, gd, gm = _guarded(vertices), _guarded(z["meshletdata"]), _guarded(want_ml.copy())
+    assert e.emu.nvc_cook_meshlet_bounds(e.ctx, None, gv.ctypes.data, len(gv), gd.ctypes.data, len(gd), gm.ctypes.data, len(gm), None) == 0
+    assert np.array_equal(gm, want_ml)
+    e.close()
