@@ -294,3 +294,20 @@ def test_two_phase_invariants(golden_dir):
         both = np.union1d(early, late)
         assert np.isin(vis, both).all()
         assert len(late) > 0 or f > 0
+
+
+def test_oracle_is_race_free(tmp_path, golden_dir):
+    """The multi-threaded oracle (dynamic chunk scheduling, atomics on the shared visibility words) under ThreadSanitizer:
+    two full frames with 8 threads, no report (tests/tsan_oracle.cpp)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "tsan_oracle")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-o", exe, os.path.join(root, "tests", "tsan_oracle.cpp"),
+                            os.path.join(root, "oracle", "oracle.cpp"), os.path.join(root, "niagara_b200", "csrc", "nvc_host.cpp"), "-lpthread"], capture_output=True, text=True)
+    if build.returncode != 0 and ("tsan" in build.stderr or "sanitize" in build.stderr):
+        pytest.skip("this toolchain has no ThreadSanitizer runtime")
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe, os.path.join(golden_dir, "kitten_pirate.nvcg"), "3000"], capture_output=True, text=True, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66"))
+    assert run.returncode == 0 and "ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
+    assert "emitted" in run.stdout
