@@ -206,6 +206,11 @@ NVC_API int nvc_prepare_meshes(NvcContext* ctx, void* stream, const NvcMesh* mes
  * Results are identical either way.  Also settable with the environment variable NVC_HIZ_STAGE_TEXELS. */
 NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels);
 
+/* The cluster pass runs by default as a conservative FILTER (fused arithmetic with an error margin on every comparison,
+ * per-command transforms) whose undecided meshlets are re-evaluated by the exact strict-IEEE path: results are identical,
+ * the pass is ~2x faster.  enabled = 0 selects the exact kernel for every meshlet (A/B measurements, debugging). */
+NVC_API int nvc_set_cluster_filter(NvcContext* ctx, int enabled);
+
 /* ---- pyramid layout (host only): niagara.cpp:439-447 previousPow2, resources.cpp:280-292 getImageMipLevels,
  *      niagara.cpp:1339-1342 ------------------------------------------------------------------------- */
 NVC_API uint32_t nvc_previous_pow2(uint32_t v);

@@ -1,5 +1,6 @@
 // nvc_api.cu — the C ABI declared in include/niagara_cull.h (context, argument validation, launches).
 #include "nvc_internal.h"
+#include "nvc_filter.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -179,6 +180,10 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		e = nvc::clustercull_occupancy(&ctx->cluster_blocks_early, &ctx->cluster_blocks_late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
 	}
 	if (e == cudaSuccess)
+		e = nvc::clustercull_filter_occupancy(&ctx->cluster_filter_blocks_early, &ctx->cluster_filter_blocks_late);
+	if (const char* env = getenv("NVC_CLUSTER_FILTER"))
+		ctx->cluster_filter = atoi(env) != 0;
+	if (e == cudaSuccess)
 		e = cudaDeviceSynchronize();
 	if (e != cudaSuccess)
 	{
@@ -194,6 +199,10 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		ctx->cluster_blocks_late = 1;
 	if (ctx->cluster_blocks_late_staged < 1)
 		ctx->cluster_blocks_late_staged = 1;
+	if (ctx->cluster_filter_blocks_early < 1)
+		ctx->cluster_filter_blocks_early = 1;
+	if (ctx->cluster_filter_blocks_late < 1)
+		ctx->cluster_filter_blocks_late = 1;
 
 	*out_ctx = ctx;
 	return NVC_OK;
@@ -262,6 +271,14 @@ NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels)
 		return cuda_fail(ctx, e, "nvc_set_hiz_staging");
 	if (ctx->cluster_blocks_late_staged < 1)
 		ctx->cluster_blocks_late_staged = 1;
+	return NVC_OK;
+}
+
+NVC_API int nvc_set_cluster_filter(NvcContext* ctx, int enabled)
+{
+	if (!ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	ctx->cluster_filter = enabled != 0;
 	return NVC_OK;
 }
 
@@ -347,6 +364,14 @@ NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cu
 		staged = p.hiz.stage_level < p.hiz.levels;
 	}
 	uint32_t blocks = uint32_t(ctx->sm_count) * uint32_t(late ? (staged ? ctx->cluster_blocks_late_staged : ctx->cluster_blocks_late) : ctx->cluster_blocks_early);
+	// default: the filtered kernel (conservative filter + exact fallback, same results); TMA-staged Hi-Z and
+	// nvc_set_cluster_filter(ctx, 0) select the exact kernel
+	if (ctx->cluster_filter && !staged)
+	{
+		p.use_filter = 1;
+		p.filter = nvc::make_filter_consts(p.cull, p.hiz, late && cull->clusterOcclusionEnabled == 1);
+		blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_filter_blocks_late : ctx->cluster_filter_blocks_early);
+	}
 	cudaError_t e = nvc::launch_clustercull(p, late != 0, blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_clustercull");
 }

@@ -18,6 +18,8 @@ struct NvcContext
 	int device = 0;
 	int sm_count = 0;
 	int cluster_blocks_early = 0, cluster_blocks_late = 0, cluster_blocks_late_staged = 0;
+	int cluster_filter_blocks_early = 0, cluster_filter_blocks_late = 0;
+	bool cluster_filter = true; // nvc_set_cluster_filter / env NVC_CLUSTER_FILTER: filtered cluster kernel (default) or the exact one
 	uint32_t hiz_stage_budget = 0; // texels (24 KB) of coarse Hi-Z mips staged per CTA; 0 = off (env NVC_HIZ_STAGE_TEXELS)
 	NvcLimits limits = { NVC_TASK_WGLIMIT, NVC_CLUSTER_LIMIT };
 	nvc::Scratch* scratch = nullptr;
@@ -95,6 +97,28 @@ struct DrawCullParams
 	uint32_t task_wglimit;
 };
 
+// Per-launch constants of the conservative meshlet filter (nvc_filter.cuh; host-computed by make_filter_consts).
+struct FilterConsts
+{
+	float vrE;            // max(max row abs sum of V3, 1)
+	float mFk;            // frustum margin = mFk * E
+	float zfarLo, zfarHi; // zfar (1 -+ 2^-20)
+	float hPx, hPyn;      // 0.5 P00, -0.5 P11
+	float kGx, kGrx;      // validity cone per axis: |cx| + r kGrx <= kGx cz  (kGx = 1 / hPx, kGrx = sqrt(1 + kGx^2))
+	float kGy, kGry;
+	float sxk, syk;       // size.x * pyramidWidth = r vx icz sxk  (sxk = 2 hPx pw), same for y (positive)
+	float Kuv;            // uv error = Kuv g relE
+	float KuvP;           // max(pw, ph) Kuv 1.05  (px error in base-level texels per unit gr)
+	float Km1, Km2;       // dm = gr (Km1 + Km2 m)
+	float Kfp;            // footprint margin = Kfp whf gr  (whf = w/2)
+	float zn4u;           // 4 u znear (enters Et)
+	uint32_t lbMax;       // float bits of 2^(levels)      = ceiling of the clamped L
+	uint32_t lbLevMax;    // float bits of 2^(levels - 1)  = top mip
+	uint32_t pwBits, phBits; // float bits of (float)hiz.width, (float)hiz.height (powers of two when occ_ok)
+	uint32_t enabled;     // 0: every item is undecided (unusual view / projection: the exact path does everything)
+	uint32_t occ_ok;      // 0: the occlusion stage is never decided here (non power-of-two pyramid, ...)
+};
+
 struct ClusterParams
 {
 	NvcCullData cull;
@@ -108,6 +132,8 @@ struct ClusterParams
 	Scratch* scratch;
 	HiZDesc hiz;
 	uint32_t cluster_limit;
+	FilterConsts filter; // valid when use_filter
+	uint32_t use_filter; // 1: clustercull_filter_kernel (conservative filter + exact fallback), 0: the exact kernel
 	float one, neg_one; // 1.0f / -1.0f as run-time values: see nvc_math2.cuh (keeps ptxas from contracting packed adds)
 };
 
@@ -129,6 +155,7 @@ cudaError_t launch_cook_meshlet_bounds(const NvcVertex* vertices, uint32_t verte
 cudaError_t launch_update_draws(NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices, const NvcMeshDraw* update_values, uint32_t count, cudaStream_t stream);
 cudaError_t launch_pack_meshes(const NvcMesh* meshes, uint32_t count, MeshCullHead* heads, float* errors, cudaStream_t stream);
 cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late, int* blocks_per_sm_late_staged, uint32_t stage_bytes);
+cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late);
 uint32_t hiz_stage_bytes(const HiZDesc& hiz);
 void choose_stage_public(HiZDesc& hz, uint32_t total_texels, uint32_t budget_texels);
 

@@ -12,6 +12,7 @@
 #include "nvc_cook.cuh"
 #include "nvc_math2.cuh"
 #include "nvc_tma.cuh"
+#include "nvc_filter.cuh"
 
 #include <cuda_runtime.h>
 
@@ -1009,6 +1010,289 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 }
 
 // ------------------------------------------------------------------------------------------------------
+// clustercull, filtered: the default cluster pass.
+//
+// Same contract and the same outputs as clustercull_kernel, ~2x fewer instructions per meshlet:
+//   * the lane that owns a task command builds, ONCE per command, the command's view-space transform
+//     (M = scale * view3 * R(orientation), T = view * position) and the error scales of the filter into a shared-memory
+//     record (CmdRecord, 80 bytes); every meshlet of the command then needs 9 fused multiply-adds for its centre
+//     instead of the exact path's 54 unfused operations, and no shuffles / draw loads per item;
+//   * each meshlet goes through filter_meshlet (nvc_filter.cuh): fused arithmetic, MUFU reciprocals / roots, and a
+//     margin on every comparison.  Decided meshlets are committed at once;
+//   * undecided meshlets (a few per cent: a screen-space coordinate within its error bound of a texel / mip boundary,
+//     unusual transforms, non-finite data) are appended to a per-warp queue and re-evaluated by the EXACT
+//     meshlet_compute on full warps, 32 at a time — so the result is bit-identical to the exact kernel's.
+// ------------------------------------------------------------------------------------------------------
+
+#ifndef NVC_FILTER_MIN_BLOCKS
+#define NVC_FILTER_MIN_BLOCKS 4
+#endif
+constexpr int kFStage = 128;  // staged cluster indices per warp
+constexpr int kFQueue = 64;   // undecided items per warp (drained 32 at a time)
+
+struct FilterShared
+{
+	CmdRecord rec[kClusterWarps][32];
+	uint4 queue[kClusterWarps][kFQueue];
+	uint32_t stage[kClusterWarps][kFStage];
+};
+
+template <bool LATE>
+__global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
+{
+	__shared__ FilterShared sh;
+	__shared__ uint32_t s_is_last;
+
+	NVC_GRID_DEPENDENCY_SYNC();
+	const NvcCullData& cd = p.cull;
+	const ClusterConsts& cc = cd;
+	const FilterConsts& fc = p.filter;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = tid & 31u, warp = tid >> 5;
+	uint32_t* const stage = sh.stage[warp];
+	uint4* const queue = sh.queue[warp];
+	CmdRecord* const recs = sh.rec[warp];
+	uint32_t nst = 0, nq = 0;
+
+	const uint32_t ncmd = p.command_count4[1] * 64u; // niagara.cpp:1599: commandId < X * 64
+	const uint32_t nbatch = (ncmd + 31u) / 32u;
+	const bool track = cd.clusterOcclusionEnabled == 1 && cd.postPass == 0; // clustercull.comp.glsl:86
+	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
+	const bool bits_known = cd.postPass == 0;
+	const bool backface = cd.clusterBackfaceEnabled != 0;
+	const bool occlusion = LATE && cd.clusterOcclusionEnabled == 1;
+	const bool filter_on = fc.enabled != 0u;
+
+	// bookkeeping of one group of <= 32 verdicts: visibility bits (late, :126-131) and compaction (:133-139)
+	auto commit = [&](bool active, bool visible, bool skip, bool oldbit, uint32_t mvi, uint32_t code) {
+		if (track_late && __any_sync(0xffffffffu, active && (!bits_known || oldbit != visible)))
+			update_visibility_bits(p.meshlet_visibility, active, visible, mvi);
+		const bool out = active && visible && !skip;
+		const uint32_t omask = __ballot_sync(0xffffffffu, out);
+		const uint32_t n = __popc(omask);
+		if (n)
+		{
+			if (nst + n > uint32_t(kFStage))
+				flush_stage(p, stage, nst);
+			if (out)
+				stage[nst + __popc(omask & lanemask_lt())] = code;
+			nst += n;
+		}
+	};
+
+	// the exact path for up to 32 queued items (all lanes execute; lanes >= n are inactive)
+	auto drain = [&](uint32_t n) {
+		__syncwarp();
+		const uint4 q = queue[lane < n ? lane : 0u];
+		ItemRef r;
+		r.active = lane < n;
+		r.drawId = q.x;
+		r.mi = q.y;
+		r.mvi = q.z;
+		r.code = q.w & 0x7fffffffu;
+		r.lateVis = q.w >> 31;
+		r.alive_known = !LATE && track; // early + tracking: only meshlets whose bit is set are queued
+		ItemData d;
+		meshlet_fetch<LATE>(p, r, d);
+		bool visible, skip, oldbit;
+		meshlet_compute<LATE, false>(p, cc, nullptr, r, d, visible, skip, oldbit);
+		commit(r.active, visible, skip, oldbit, r.mvi, r.code);
+		// move the rest of the queue down
+		__syncwarp();
+		const uint32_t rest = nq - n;
+		uint4 t0 = make_uint4(0u, 0u, 0u, 0u);
+		if (lane < rest)
+			t0 = queue[n + lane];
+		__syncwarp();
+		if (lane < rest)
+			queue[lane] = t0;
+		nq = rest;
+		__syncwarp();
+	};
+
+	for (;;)
+	{
+		uint32_t batch = 0;
+		if (lane == 0)
+			batch = atomicAdd(&p.scratch->cluster_batch, 1u);
+		batch = __shfl_sync(0xffffffffu, batch, 0);
+		if (batch >= nbatch)
+			break;
+
+		// ---- per command: load, transform record ----
+		const uint32_t cid = batch * 32u + lane;
+		uint32_t c_count = 0, c_mvo = 0;
+		__syncwarp(); // the previous batch's readers of `recs` are done
+		if (cid < ncmd)
+		{
+			const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + cid);
+			const uint32_t c_draw = __ldg(cp + 0), c_task = __ldg(cp + 1);
+			c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
+			const uint32_t c_late = __ldg(cp + 3);
+			c_mvo = __ldg(cp + 4);
+			if (c_count)
+			{
+				const char* dp = reinterpret_cast<const char*>(p.draws + c_draw);
+				const float4 d0 = ldg_f4(dp), d1 = ldg_f4(dp + 16);
+				build_record(fc, cd.view, cd.znear, d0, d1, c_task, c_mvo, c_draw, c_late, recs[lane]);
+			}
+		}
+
+		// early pass with tracking: flatten only the SET visibility bits of every command (see clustercull_kernel)
+		const bool alive_flatten = !LATE && track;
+		uint32_t amask_lo = 0, amask_hi = 0;
+		uint32_t eff_count = c_count;
+		if (alive_flatten)
+		{
+			if (c_count)
+			{
+				const uint32_t sft = c_mvo & 31u;
+				const uint32_t nwords = (sft + c_count + 31u) >> 5;
+				const uint32_t* wp = p.meshlet_visibility + (c_mvo >> 5);
+				uint32_t w0 = __ldg(wp), w1 = nwords > 1 ? __ldg(wp + 1) : 0u, w2 = nwords > 2 ? __ldg(wp + 2) : 0u;
+				amask_lo = __funnelshift_r(w0, w1, sft);
+				amask_hi = __funnelshift_r(w1, w2, sft);
+				amask_lo &= c_count >= 32 ? 0xffffffffu : ((1u << c_count) - 1u);
+				amask_hi &= c_count >= 64 ? 0xffffffffu : (c_count > 32 ? ((1u << (c_count - 32)) - 1u) : 0u);
+			}
+			eff_count = __popc(amask_lo) + __popc(amask_hi);
+		}
+
+		uint32_t incl = eff_count;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= uint32_t(o))
+				incl += n;
+		}
+		const uint32_t excl = incl - eff_count;
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		const uint32_t nz = __ballot_sync(0xffffffffu, eff_count != 0);
+		const bool nz_prefix = (nz & (nz + 1u)) == 0;
+		const uint32_t count0 = __shfl_sync(0xffffffffu, eff_count, 0);
+		const bool uniform = count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0);
+		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u;
+		__syncwarp(); // records visible to the whole warp
+
+		for (uint32_t base = 0; base < total; base += 32)
+		{
+			// ---- item -> (command lane j, rank inside the command) ----
+			const uint32_t item = base + lane;
+			const bool active = item < total;
+			uint32_t j;
+			if (uniform)
+				j = __umulhi(item, recip);
+			else if (nz_prefix)
+			{
+				uint32_t rel = excl - base;
+				uint32_t hbit = (eff_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
+				uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
+				uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && incl <= base));
+				j = first + __popc(heads & lanemask_le());
+			}
+			else
+			{
+				j = 0;
+#pragma unroll
+				for (int s = 16; s >= 1; s >>= 1)
+				{
+					uint32_t v = __shfl_sync(0xffffffffu, incl, (j + s - 1) & 31u);
+					if (v <= item)
+						j += s;
+				}
+			}
+			j &= 31u;
+			uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j);
+			if (alive_flatten)
+			{
+				const uint32_t mlo = __shfl_sync(0xffffffffu, amask_lo, j), mhi = __shfl_sync(0xffffffffu, amask_hi, j);
+				mgi = active ? select_bit64(mlo, mhi, mgi) : 0u;
+			}
+			mgi &= 63u;
+
+			// ---- the command's record, the meshlet, its visibility bit ----
+			const CmdRecord& rec = recs[active ? j : (lane & 0u)];
+			const uint4 ids = rec.ids;
+			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
+			const uint32_t code = (batch * 32u + j) | (mgi << 24); // :138
+			uint2 b0 = make_uint2(0u, 0u);
+			uint32_t b1 = 0u, word = 0u;
+			if (active)
+			{
+				const char* mp = reinterpret_cast<const char*>(p.meshlets + mi);
+				b0 = __ldg(reinterpret_cast<const uint2*>(mp));
+				b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8));
+				if (track)
+					word = alive_flatten ? 0xffffffffu : (LATE ? __ldcg(p.meshlet_visibility + (mvi >> 5)) : __ldg(p.meshlet_visibility + (mvi >> 5)));
+			}
+			const float4 row0 = rec.row0, row1 = rec.row1, row2 = rec.row2, aux = rec.aux;
+
+			bool oldbit = false, skip = false, alive = active;
+			if (track)
+			{
+				const bool bit = (word >> (mvi & 31u)) & 1u;
+				oldbit = bit;
+				if (!LATE)
+					alive = alive && bit; // :91-92
+				else
+					skip = (ids.w & kRecLate) != 0u && bit; // :97-98
+			}
+
+			const FilterResult fr = filter_meshlet<LATE>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
+			const bool decided = !alive || (fr.decided && filter_on && (ids.w & kRecExactOnly) == 0u);
+			const bool visible = alive && fr.visible;
+
+			// ---- undecided lanes -> queue (exact path on full warps) ----
+			const uint32_t umask = __ballot_sync(0xffffffffu, !decided);
+			if (umask)
+			{
+				if (!decided)
+					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(ids.z, mi, mvi, code | ((ids.w & kRecLate) << 31));
+				nq += __popc(umask);
+			}
+			commit(active && decided, visible, skip, oldbit, mvi, code);
+			if (nq >= 32u)
+				drain(32u);
+		}
+	}
+	while (nq)
+		drain(min(nq, 32u));
+	if (nst)
+		flush_stage(p, stage, nst);
+
+	// ---- last-block epilogue: clustersubmit.comp.glsl:25-45 ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+		s_is_last = atomicAdd(&p.scratch->cluster_done, 1u) == gridDim.x - 1;
+	__syncthreads();
+	if (!s_is_last)
+		return;
+	__threadfence();
+
+	uint32_t clusterCount = *reinterpret_cast<volatile uint32_t*>(&p.scratch->cluster_counter);
+	uint32_t count = min(clusterCount, p.cluster_limit);
+	if (tid == 0)
+	{
+		p.cluster_count4[0] = clusterCount;
+		p.cluster_count4[1] = NVC_CLUSTER_TILE;
+		p.cluster_count4[2] = min((count + 255) / 256, NVC_MAX_DISPATCH_GROUPS);
+		p.cluster_count4[3] = 256 / NVC_CLUSTER_TILE;
+	}
+	uint32_t boundary = (count + 255) & ~255u;
+	if (count + tid < boundary)
+		p.cluster_indices[count + tid] = ~0u;
+	__syncthreads();
+	if (tid == 0)
+	{
+		p.scratch->cluster_counter = 0;
+		p.scratch->cluster_done = 0;
+		p.scratch->cluster_batch = 0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
 // taskcull: meshlet.task.glsl:53-149 — one warp per command (two 32-lane halves), payload compaction per command
 // ------------------------------------------------------------------------------------------------------
 
@@ -1529,6 +1813,17 @@ uint32_t hiz_stage_bytes(const HiZDesc& hiz)
 
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream)
 {
+	if (p.use_filter)
+	{
+#if NVC_PDL && !defined(NVC_EMU)
+		return launch_pdl(late ? clustercull_filter_kernel<true> : clustercull_filter_kernel<false>, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
+#endif
+		if (late)
+			clustercull_filter_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p);
+		else
+			clustercull_filter_kernel<false><<<blocks, kClusterBlock, 0, stream>>>(p);
+		return cudaGetLastError();
+	}
 	const uint32_t stage_bytes = late ? hiz_stage_bytes(p.hiz) : 0u;
 #if NVC_PDL && !defined(NVC_EMU)
 	void (*kernel)(ClusterParams) = late ? (stage_bytes ? clustercull_kernel<true, true> : clustercull_kernel<true, false>) : clustercull_kernel<false, false>;
@@ -1577,6 +1872,14 @@ cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_l
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_kernel<true, false>, kClusterBlock, 0);
 	if (e == cudaSuccess)
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late_staged, clustercull_kernel<true, true>, kClusterBlock, stage_bytes);
+	return e;
+}
+
+cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
+{
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false>, kClusterBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true>, kClusterBlock, 0);
 	return e;
 }
 

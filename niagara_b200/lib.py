@@ -27,6 +27,7 @@ SIGNATURES = [
     ("nvc_version", ctypes.c_char_p, []),
     ("nvc_prepare_meshes", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
     ("nvc_set_hiz_staging", ctypes.c_int, [c_void_p, ctypes.c_uint32]),
+    ("nvc_set_cluster_filter", ctypes.c_int, [c_void_p, ctypes.c_int]),
     ("nvc_previous_pow2", ctypes.c_uint32, [ctypes.c_uint32]),
     ("nvc_image_mip_levels", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     ("nvc_hiz_layout", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(HiZ)]),
