@@ -455,6 +455,8 @@ def main():
     draws_per_step = early_reached + D
 
     # ---- timed region: device-resident inputs ----
+    filter_stats = (ctypes.c_uint64 * 2)()
+    lib.nvc_filter_stats(path.ctx, filter_stats, 1)  # reset the filter's diagnostic counters
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -471,6 +473,7 @@ def main():
     stop.record()
     sync_all()
     total_ms = start.elapsed_time(stop)
+    lib.nvc_filter_stats(path.ctx, filter_stats, 1)
     pass_ms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(5)] for k in range(K)])
 
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -600,6 +603,12 @@ def main():
             "issue_roofline": issue_roofline(k_ms, clocks, args),
             "gpu_launches": (5 + ((3 if sm_push else 2) if gather == "ce" else 0)) * K,
             "gather_transport": ("sm-push" if sm_push else gather),
+            "cluster_filter": {
+                "enabled": os.environ.get("NVC_CLUSTER_FILTER", "1") != "0",
+                "meshlets_filtered_per_step": int(filter_stats[0]) // max(K, 1),
+                "took_exact_path_per_step": int(filter_stats[1]) // max(K, 1),
+                "exact_share": (float(filter_stats[1]) / float(filter_stats[0])) if filter_stats[0] else None,
+            },
         }
         if e2e:
             line["e2e"] = e2e

@@ -206,10 +206,20 @@ NVC_API int nvc_prepare_meshes(NvcContext* ctx, void* stream, const NvcMesh* mes
  * Results are identical either way.  Also settable with the environment variable NVC_HIZ_STAGE_TEXELS. */
 NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels);
 
+/* Derived, optional, results identical (like nvc_prepare_meshes): allocates a context-owned FOOTPRINT IMAGE for this pyramid
+ * (same texel count + one row / column per mip).  nvc_depth_pyramid then also writes, for every mip and every 2 x 2 sampler
+ * footprint, the minimum of its four (edge-clamped) texels; the late cluster pass reads ONE value per meshlet instead of four
+ * scattered texels.  The image is valid only for pyramids written by nvc_depth_pyramid: a caller that stores texels itself must
+ * not prepare (or must pass NULL here to release).  Allocates / frees: call outside stream capture.  hiz == NULL releases. */
+NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz);
+
 /* The cluster pass runs by default as a conservative FILTER (fused arithmetic with an error margin on every comparison,
  * per-command transforms) whose undecided meshlets are re-evaluated by the exact strict-IEEE path: results are identical,
  * the pass is ~2x faster.  enabled = 0 selects the exact kernel for every meshlet (A/B measurements, debugging). */
 NVC_API int nvc_set_cluster_filter(NvcContext* ctx, int enabled);
+/* Diagnostics (synchronises the device): out[0] = meshlets the filtered cluster passes evaluated, out[1] = how many of them
+ * were undecided and took the exact path, both cumulative since the last call with reset != 0. */
+NVC_API int nvc_filter_stats(NvcContext* ctx, uint64_t* out_items_undecided2, int reset);
 
 /* ---- pyramid layout (host only): niagara.cpp:439-447 previousPow2, resources.cpp:280-292 getImageMipLevels,
  *      niagara.cpp:1339-1342 ------------------------------------------------------------------------- */

@@ -100,6 +100,16 @@ bool fill_hiz(const NvcHiZ* in, nvc::HiZDesc& out)
 	return true;
 }
 
+// Attaches the context's footprint image when it was built (nvc_depth_pyramid) for exactly this pyramid.
+void attach_footprints(const NvcContext* ctx, const NvcHiZ* in, nvc::HiZDesc& out)
+{
+	out.fp = nullptr;
+	if (!ctx->hiz_fp || !ctx->hiz_fp_valid || !in || ctx->hiz_fp_key != in->texels || ctx->hiz_fp_width != in->width || ctx->hiz_fp_height != in->height || ctx->hiz_fp_levels != in->levels)
+		return;
+	out.fp = ctx->hiz_fp;
+	memcpy(out.fp_offset, ctx->hiz_fp_offset, sizeof(out.fp_offset));
+}
+
 } // namespace
 
 extern "C"
@@ -221,6 +231,8 @@ NVC_API void nvc_destroy(NvcContext* ctx)
 		cudaFree(ctx->mesh_heads);
 	if (ctx->mesh_errors)
 		cudaFree(ctx->mesh_errors);
+	if (ctx->hiz_fp)
+		cudaFree(ctx->hiz_fp);
 	delete ctx;
 }
 
@@ -282,6 +294,27 @@ NVC_API int nvc_set_cluster_filter(NvcContext* ctx, int enabled)
 	return NVC_OK;
 }
 
+NVC_API int nvc_filter_stats(NvcContext* ctx, uint64_t* out_items_undecided2, int reset)
+{
+	if (!ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	DeviceGuard guard(ctx->device);
+	cudaError_t e = cudaDeviceSynchronize();
+	unsigned long long v[2] = { 0, 0 };
+	if (e == cudaSuccess)
+		e = cudaMemcpy(v, &ctx->scratch->filter_items, sizeof(v), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && reset)
+		e = cudaMemset(&ctx->scratch->filter_items, 0, sizeof(v));
+	if (e != cudaSuccess)
+		return cuda_fail(ctx, e, "nvc_filter_stats");
+	if (out_items_undecided2)
+	{
+		out_items_undecided2[0] = v[0];
+		out_items_undecided2[1] = v[1];
+	}
+	return NVC_OK;
+}
+
 NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull, int late, int task,
     const NvcMeshDraw* draws, const NvcMesh* meshes, uint32_t* draw_visibility,
     void* commands, uint32_t* command_count4, const NvcHiZ* hiz)
@@ -340,6 +373,8 @@ static int fill_cluster_params(NvcContext* ctx, const NvcCullData* cull, int lat
 	bool need_hiz = late && cull->clusterOcclusionEnabled == 1;
 	if (!fill_hiz(hiz, p.hiz) && need_hiz)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (need_hiz)
+		attach_footprints(ctx, hiz, p.hiz);
 	return NVC_OK;
 }
 
@@ -421,7 +456,57 @@ NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
 	p.depth_height = depth_height;
 	p.scratch = ctx->scratch;
 	cudaError_t e = nvc::launch_pyramid(p, static_cast<cudaStream_t>(stream));
+	if (e == cudaSuccess && ctx->hiz_fp && ctx->hiz_fp_key == hiz->texels && ctx->hiz_fp_width == hiz->width && ctx->hiz_fp_height == hiz->height && ctx->hiz_fp_levels == hiz->levels)
+	{
+		// derived footprint image of the pyramid just built (nvc_prepare_hiz), one more launch on the same stream
+		memcpy(p.hiz.fp_offset, ctx->hiz_fp_offset, sizeof(p.hiz.fp_offset));
+		e = nvc::launch_footprint(p.hiz, ctx->hiz_fp, ctx->hiz_fp_total, static_cast<cudaStream_t>(stream));
+		ctx->hiz_fp_valid = e == cudaSuccess;
+	}
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_depth_pyramid");
+}
+
+NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz)
+{
+	if (!ctx)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	DeviceGuard guard(ctx->device);
+	if (ctx->hiz_fp)
+	{
+		cudaDeviceSynchronize();
+		cudaFree(ctx->hiz_fp);
+		ctx->hiz_fp = nullptr;
+	}
+	ctx->hiz_fp_key = nullptr;
+	ctx->hiz_fp_valid = false;
+	ctx->hiz_fp_total = 0;
+	if (!hiz)
+		return NVC_OK; // un-prepare
+	if (!hiz->texels || hiz->levels == 0 || hiz->levels > NVC_MAX_HIZ_LEVELS || hiz->width == 0 || hiz->height == 0 || hiz->width > 65536 || hiz->height > 65536)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	uint64_t total = 0;
+	for (uint32_t l = 0; l < hiz->levels; ++l)
+	{
+		uint32_t w = hiz->width >> l, h = hiz->height >> l;
+		w = w ? w : 1;
+		h = h ? h : 1;
+		ctx->hiz_fp_offset[l] = uint32_t(total);
+		total += uint64_t(w + 1) * (h + 1);
+	}
+	if (total >= (1ull << 31))
+		return NVC_ERROR_UNSUPPORTED;
+	cudaError_t e = cudaMalloc(&ctx->hiz_fp, size_t(total) * sizeof(float));
+	if (e != cudaSuccess)
+	{
+		ctx->hiz_fp = nullptr;
+		return e == cudaErrorMemoryAllocation ? NVC_ERROR_OUT_OF_MEMORY : cuda_fail(ctx, e, "nvc_prepare_hiz");
+	}
+	ctx->hiz_fp_key = hiz->texels;
+	ctx->hiz_fp_width = hiz->width;
+	ctx->hiz_fp_height = hiz->height;
+	ctx->hiz_fp_levels = hiz->levels;
+	ctx->hiz_fp_total = uint32_t(total);
+	return NVC_OK;
 }
 
 NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices,

@@ -113,10 +113,10 @@ inline FilterConsts make_filter_consts(const NvcCullData& cd, const HiZDesc& hiz
 	double fk = f01 > f23 ? f01 : f23;
 	fk = fk > 1.0 ? fk : 1.0;
 	fc.vrE = float(vr > 1.0 ? vr : 1.0) * 1.000001f;
-	fc.mFk = float(1.5 * fk);
-	fc.zfarLo = cd.zfar * (1.f - 9.5367431640625e-7f);
-	fc.zfarHi = cd.zfar * (1.f + 9.5367431640625e-7f);
-	fc.zn4u = float(4.0 * u * double(cd.znear));
+	fc.fr.x = float(1.5 * fk);
+	fc.fr.y = cd.zfar * (1.f - 9.5367431640625e-7f);
+	fc.fr.z = cd.zfar * (1.f + 9.5367431640625e-7f);
+	fc.fr.w = float(4.0 * u * double(cd.znear));
 	fc.enabled = ok ? 1u : 0u;
 
 	// occlusion stage
@@ -126,28 +126,28 @@ inline FilterConsts make_filter_consts(const NvcCullData& cd, const HiZDesc& hiz
 	if (occ)
 	{
 		const double hpx = 0.5 * double(cd.P00), hpy = 0.5 * double(cd.P11);
-		fc.hPx = float(hpx);
-		fc.hPyn = float(-hpy);
-		fc.kGx = float(1.0 / hpx);
-		fc.kGrx = float(sqrt(1.0 + 1.0 / (hpx * hpx)) * 1.000001);
-		fc.kGy = float(1.0 / hpy);
-		fc.kGry = float(sqrt(1.0 + 1.0 / (hpy * hpy)) * 1.000001);
-		fc.sxk = float(2.0 * hpx * double(cd.pyramidWidth));
-		fc.syk = float(2.0 * hpy * double(cd.pyramidHeight));
+		fc.pr.x = float(hpx);
+		fc.pr.y = float(-hpy);
+		fc.cg.x = float(1.0 / hpx);
+		fc.cg.y = float(sqrt(1.0 + 1.0 / (hpx * hpx)) * 1.000001);
+		fc.cg.z = float(1.0 / hpy);
+		fc.cg.w = float(sqrt(1.0 + 1.0 / (hpy * hpy)) * 1.000001);
+		fc.pr.z = float(2.0 * hpx * double(cd.pyramidWidth));
+		fc.pr.w = float(2.0 * hpy * double(cd.pyramidHeight));
 		auto kuv = [](double hp) { return 1.1 * 1.41421356237 * (hp + 1.0 / hp) + 0.62 * (1.0 + hp) + 0.25 * hp + 2.2; };
 		const double Kuv = kuv(hpx) > kuv(hpy) ? kuv(hpx) : kuv(hpy);
 		const double pmax = double(cd.pyramidWidth > cd.pyramidHeight ? cd.pyramidWidth : cd.pyramidHeight);
 		const double hpmax = hpx > hpy ? hpx : hpy, gmax = 1.0 / (hpx < hpy ? hpx : hpy);
 		fc.Kuv = float(Kuv);
-		fc.KuvP = float(pmax * Kuv * 1.05);
-		fc.Km1 = float(pmax * (1.24 * (1.0 + hpmax) + 0.6) * 1.1);
-		fc.Km2 = float((5.0 + gmax) * 1.1);
-		fc.Kfp = float(2.0 * Kuv * 1.05);
+		fc.mk.z = float(pmax * Kuv * 1.05);
+		fc.mk.x = float(pmax * (1.24 * (1.0 + hpmax) + 0.6) * 1.1);
+		fc.mk.y = float((5.0 + gmax) * 1.1);
+		fc.mk.w = float(2.0 * Kuv * 1.05);
 		const float top = float(1u << (hiz.levels - 1));
-		fc.lbLevMax = bits(top);
-		fc.lbMax = bits(top * 2.f);
-		fc.pwBits = bits(float(hiz.width));
-		fc.phBits = bits(float(hiz.height));
+		fc.lv.y = bits(top);
+		fc.lv.x = bits(top * 2.f);
+		fc.lv.z = bits(float(hiz.width));
+		fc.lv.w = bits(float(hiz.height));
 	}
 	fc.occ_ok = occ ? 1u : 0u;
 	return fc;
@@ -200,7 +200,7 @@ __device__ __forceinline__ void build_record(const FilterConsts& fc, const float
 	rec.row2 = rows[2];
 	rec.aux.x = s;
 	rec.aux.y = 42.f * u * s * fc.vrE;
-	rec.aux.z = nvf_fma(12.f * u, tmax, fc.zn4u) + 7.8886091e-31f /* 2^-100 */;
+	rec.aux.z = nvf_fma(12.f * u, tmax, fc.fr.w) + 7.8886091e-31f /* 2^-100 */;
 	rec.aux.w = 8300.f * s;
 	rec.ids = make_uint4(taskOffset, mvo, drawId, (lateVis == 1u ? kRecLate : 0u) | (sane ? 0u : kRecExactOnly));
 	(void)znear;
@@ -224,7 +224,7 @@ struct FilterResult
 
 // One meshlet through the filter.  `b0`, `b1`: first 12 bytes of the Meshlet (center/radius halves, cone s8 x 4).
 // LATE && occlusion: the Hi-Z stage runs; `backface`: clusterBackfaceEnabled != 0.
-template <bool LATE>
+template <bool LATE, bool FP>
 __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, const NvcCullData& cd, const HiZDesc& hiz, const float4 row0, const float4 row1, const float4 row2,
     const float4 aux, uint2 b0, uint32_t b1, bool backface, bool occlusion)
 {
@@ -238,14 +238,14 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	const float E = nvf_fma(aux.y, l1, aux.z); // inf / NaN when any meshlet field is not finite: nothing below is "sure" then
 
 	// ---- frustum: every test has the form  b > -r --------------------------------------------------------------
-	const float mF = fc.mFk * E;
+	const float mF = fc.fr.x * E;
 	const float bx = nvf_fma(-fabsf(cx), cd.frustum[0], cz * cd.frustum[1]);
 	const float by = nvf_fma(-fabsf(cy), cd.frustum[2], cz * cd.frustum[3]);
 	const float bn = cz - cd.znear;
 	const float m3 = fminf(fminf(bx, by), bn); // operands are finite (sane record, finite meshlet) or E is not
 	const float rp = mF - r, rm = -mF - r;
-	bool pass = fminf(m3, fc.zfarLo - cz) > rp;
-	bool fail = m3 < rm || (fc.zfarHi - cz) < rm;
+	bool pass = fminf(m3, fc.fr.y - cz) > rp;
+	bool fail = m3 < rm || (fc.fr.z - cz) < rm;
 
 	// ---- cone, scaled by 127 s -------------------------------------------------------------------------------------
 	if (backface)
@@ -280,22 +280,22 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	const float g = nvf_fma(r, iD, 1.f);
 	const float gr = g * relE;
 	// domain of the error analysis: radius >= 0, sphere inside the validity cone, small relative uncertainty
-	const float cone_x = nvf_fma(-fc.kGx, cz, nvf_fma(r, fc.kGrx, fabsf(cx))), cone_y = nvf_fma(-fc.kGy, cz, nvf_fma(r, fc.kGry, fabsf(cy)));
+	const float cone_x = nvf_fma(-fc.cg.x, cz, nvf_fma(r, fc.cg.y, fabsf(cx))), cone_y = nvf_fma(-fc.cg.z, cz, nvf_fma(r, fc.cg.w, fabsf(cy)));
 	const bool dom_ok = r >= 0.f && cone_x <= 0.f && cone_y <= 0.f && gr < 9.765625e-4f /* 2^-10 */ && fc.occ_ok != 0u;
 
 	const float vx = nvf_sqrt(nvf_fma(cx, cx, czr2)), vy = nvf_sqrt(nvf_fma(cy, cy, czr2));
 	const float cxz = cx * cz, cyz = cy * cz, rvx = r * vx, rvy = r * vy;
-	const float kx = icz * fc.hPx, ky = icz * fc.hPyn;
+	const float kx = icz * fc.pr.x, ky = icz * fc.pr.y;
 	const float aabb_x = nvf_fma(cxz - rvx, kx, 0.5f), aabb_z = nvf_fma(cxz + rvx, kx, 0.5f);
 	const float aabb_y = nvf_fma(cyz + rvy, ky, 0.5f), aabb_w = nvf_fma(cyz - rvy, ky, 0.5f);
 
 	// mip level: L = ceil(log2 m) clamped to [1, levels], as the exponent field Lb of 2^L
-	const float Sx = rvx * (icz * fc.sxk), Sy = rvy * (icz * fc.syk);
+	const float Sx = rvx * (icz * fc.pr.z), Sy = rvy * (icz * fc.pr.w);
 	const float m = fmaxf(Sx, Sy);
 	uint32_t Lb = (__float_as_uint(m) + 0x007fffffu) & 0x7f800000u;
-	Lb = min(max(Lb, 0x40000000u), fc.lbMax);
+	Lb = min(max(Lb, 0x40000000u), fc.lv.x);
 	const float P = __uint_as_float(Lb);
-	const float dm = gr * nvf_fma(m, fc.Km2, fc.Km1);
+	const float dm = gr * nvf_fma(m, fc.mk.y, fc.mk.x);
 	const bool lev_ok = (P - m) > dm && fabsf(nvf_fma(-0.5f, P, m)) > dm;
 
 	// does the box fit 2x2 texels of the next finer mip?  scale = 2^(1-L)
@@ -303,34 +303,44 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	const float px = (aabb_x * cd.pyramidWidth) * scale, py = (aabb_y * cd.pyramidHeight) * scale;
 	const float fx = px - floorf(px), fy = py - floorf(py);
 	const float dfx = nvf_fma(Sx, scale, fx) - 2.f, dfy = nvf_fma(Sy, scale, fy) - 2.f;
-	const float ef = scale * nvf_fma(gr, fc.KuvP, dm);
+	const float ef = scale * nvf_fma(gr, fc.mk.z, dm);
 	const float hf = 0.5f - ef;
 	const float dmax = fmaxf(dfx, dfy);
 	const bool fits = dmax < -ef;
 	const bool fit_ok = fabsf(fx - 0.5f) < hf && fabsf(fy - 0.5f) < hf && (fits || dmax > ef);
 
 	// final level (exponent field) and its size
-	const uint32_t LbF = min(Lb - (fits ? 0x00800000u : 0u), fc.lbLevMax);
+	const uint32_t LbF = min(Lb - (fits ? 0x00800000u : 0u), fc.lv.y);
 	const uint32_t level = (LbF >> 23) - 127u;
-	const float wf = fmaxf(__uint_as_float(fc.pwBits + 0x3f800000u - LbF), 1.f), hf2 = fmaxf(__uint_as_float(fc.phBits + 0x3f800000u - LbF), 1.f);
+	const float wf = fmaxf(__uint_as_float(fc.lv.z + 0x3f800000u - LbF), 1.f), hf2 = fmaxf(__uint_as_float(fc.lv.w + 0x3f800000u - LbF), 1.f);
 	const float whx = 0.5f * wf, why = 0.5f * hf2;
 	const float x = nvf_fma(aabb_x + aabb_z, whx, -0.5f), y = nvf_fma(aabb_y + aabb_w, why, -0.5f);
 	const float flx = floorf(x), fly = floorf(y);
-	const float efp = (fmaxf(whx, why) * gr) * fc.Kfp;
+	const float efp = (fmaxf(whx, why) * gr) * fc.mk.w;
 	const float hfp = 0.5f - efp;
 	const bool fp_ok = fabsf((x - flx) - 0.5f) < hfp && fabsf((y - fly) - 0.5f) < hfp;
 	const bool robust = sure_ok && dom_ok && lev_ok && fit_ok && fp_ok;
 
 	const float wmax = wf - 1.f, hmax = hf2 - 1.f;
-	const uint32_t x0 = (uint32_t)fminf(fmaxf(flx, 0.f), wmax), x1 = (uint32_t)fminf(fmaxf(flx + 1.f, 0.f), wmax);
-	const uint32_t y0 = (uint32_t)fminf(fmaxf(fly, 0.f), hmax), y1 = (uint32_t)fminf(fmaxf(fly + 1.f, 0.f), hmax);
 	const uint32_t wi = max(1u, hiz.width >> level);
-	const uint32_t base = hiz.level_offset[level];
-	const uint32_t r0 = base + y0 * wi, r1 = base + y1 * wi;
-	// clamped indices are always inside the level: the four loads are unconditional and in flight together
-	const float t00 = __ldg(hiz.texels + (r0 + x0)), t01 = __ldg(hiz.texels + (r0 + x1));
-	const float t10 = __ldg(hiz.texels + (r1 + x0)), t11 = __ldg(hiz.texels + (r1 + x1));
-	const float depth = fminf(fminf(t00, t01), fminf(t10, t11)); // fract != 0 on both axes here: all four texels count
+	float depth;
+	if (FP)
+	{
+		// fract != 0 on both axes here, so all four texels of the footprint count: one load from the footprint image
+		const uint32_t ix = (uint32_t)(fminf(fmaxf(flx, -1.f), wmax) + 1.f), iy = (uint32_t)(fminf(fmaxf(fly, -1.f), hmax) + 1.f);
+		depth = __ldg(hiz.fp + (hiz.fp_offset[level] + iy * (wi + 1u) + ix));
+	}
+	else
+	{
+		const uint32_t x0 = (uint32_t)fminf(fmaxf(flx, 0.f), wmax), x1 = (uint32_t)fminf(fmaxf(flx + 1.f, 0.f), wmax);
+		const uint32_t y0 = (uint32_t)fminf(fmaxf(fly, 0.f), hmax), y1 = (uint32_t)fminf(fmaxf(fly + 1.f, 0.f), hmax);
+		const uint32_t base = hiz.level_offset[level];
+		const uint32_t r0 = base + y0 * wi, r1 = base + y1 * wi;
+		// clamped indices are always inside the level: the four loads are unconditional and in flight together
+		const float t00 = __ldg(hiz.texels + (r0 + x0)), t01 = __ldg(hiz.texels + (r0 + x1));
+		const float t10 = __ldg(hiz.texels + (r1 + x0)), t11 = __ldg(hiz.texels + (r1 + x1));
+		depth = fminf(fminf(t00, t01), fminf(t10, t11)); // fract != 0 on both axes here: all four texels count
+	}
 
 	const float dS = cd.znear * iD;
 	const float dd = dS - depth;

@@ -32,6 +32,12 @@ struct NvcContext
 	void* mesh_heads = nullptr;
 	float* mesh_errors = nullptr;
 	int nccl_rank = 0, nccl_world = 1;
+	// footprint image of one pyramid (nvc_prepare_hiz): keyed by the pyramid's texel pointer and shape
+	float* hiz_fp = nullptr;
+	const float* hiz_fp_key = nullptr;
+	uint32_t hiz_fp_width = 0, hiz_fp_height = 0, hiz_fp_levels = 0, hiz_fp_total = 0;
+	uint32_t hiz_fp_offset[NVC_MAX_HIZ_LEVELS] = {};
+	bool hiz_fp_valid = false; // set by nvc_depth_pyramid, cleared by nvc_prepare_hiz
 };
 
 namespace nvc
@@ -56,6 +62,9 @@ struct alignas(128) Scratch
 	uint32_t pad4[31];
 	uint32_t pyramid_done;
 	uint32_t pad5[31];
+	// filtered cluster pass, cumulative since the last nvc_filter_stats(reset): meshlets evaluated, meshlets that took the exact path
+	unsigned long long filter_items, filter_undecided;
+	uint32_t pad6[28];
 };
 
 struct HiZDesc
@@ -66,6 +75,12 @@ struct HiZDesc
 	// mips >= stage_level (the coarse tail of the packed pyramid, stage_texels texels) are staged into shared memory
 	// once per CTA with one TMA bulk copy; stage_level == levels disables staging
 	uint32_t stage_level, stage_texels;
+	// Footprint image (nvc_prepare_hiz; built by nvc_depth_pyramid): for every mip, F(i, j) = min of the 2 x 2 texel
+	// footprint whose lower corner is (i, j), i in [-1, w-1], j in [-1, h-1], indices clamped to the level — what the
+	// MIN-reduction sampler returns for any coordinate whose bilinear footprint starts there (resources.cpp:294-325).
+	// Level l: fp + fp_offset[l], pitch w + 1, entry (i + 1, j + 1).  fp == nullptr: not available.
+	const float* fp;
+	uint32_t fp_offset[NVC_MAX_HIZ_LEVELS];
 };
 
 // Derived, read-only cull view of the reference's 208-byte Mesh records, built once per geometry upload by
@@ -98,25 +113,18 @@ struct DrawCullParams
 };
 
 // Per-launch constants of the conservative meshlet filter (nvc_filter.cuh; host-computed by make_filter_consts).
+// Grouped in 16-byte vectors in the order the kernel consumes them, so that each group is ONE uniform load per chunk.
 struct FilterConsts
 {
-	float vrE;            // max(max row abs sum of V3, 1)
-	float mFk;            // frustum margin = mFk * E
-	float zfarLo, zfarHi; // zfar (1 -+ 2^-20)
-	float hPx, hPyn;      // 0.5 P00, -0.5 P11
-	float kGx, kGrx;      // validity cone per axis: |cx| + r kGrx <= kGx cz  (kGx = 1 / hPx, kGrx = sqrt(1 + kGx^2))
-	float kGy, kGry;
-	float sxk, syk;       // size.x * pyramidWidth = r vx icz sxk  (sxk = 2 hPx pw), same for y (positive)
-	float Kuv;            // uv error = Kuv g relE
-	float KuvP;           // max(pw, ph) Kuv 1.05  (px error in base-level texels per unit gr)
-	float Km1, Km2;       // dm = gr (Km1 + Km2 m)
-	float Kfp;            // footprint margin = Kfp whf gr  (whf = w/2)
-	float zn4u;           // 4 u znear (enters Et)
-	uint32_t lbMax;       // float bits of 2^(levels)      = ceiling of the clamped L
-	uint32_t lbLevMax;    // float bits of 2^(levels - 1)  = top mip
-	uint32_t pwBits, phBits; // float bits of (float)hiz.width, (float)hiz.height (powers of two when occ_ok)
-	uint32_t enabled;     // 0: every item is undecided (unusual view / projection: the exact path does everything)
-	uint32_t occ_ok;      // 0: the occlusion stage is never decided here (non power-of-two pyramid, ...)
+	float4 fr;        // mFk (frustum margin = mFk * E), zfarLo, zfarHi (zfar (1 -+ 2^-20)), zn4u (4 u znear, enters Et)
+	float4 pr;        // hPx, hPyn (0.5 P00, -0.5 P11), sxk, syk (size.x * pyramidWidth = r vx icz sxk, sxk = 2 hPx pw; same for y)
+	float4 cg;        // kGx, kGrx, kGy, kGry: validity cone per axis |cx| + r kGrx <= kGx cz (kGx = 1 / hPx, kGrx = sqrt(1 + kGx^2))
+	float4 mk;        // Km1, Km2 (dm = gr (Km1 + Km2 m)), KuvP (max(pw, ph) Kuv 1.05), Kfp (footprint margin = Kfp whf gr)
+	uint4 lv;         // float bits of 2^levels, 2^(levels-1), (float)hiz.width, (float)hiz.height
+	float vrE;        // max(max row abs sum of V3, 1)
+	float Kuv;        // uv error = Kuv g relE (informational; folded into KuvP / Kfp)
+	uint32_t enabled; // 0: every item is undecided (unusual view / projection: the exact path does everything)
+	uint32_t occ_ok;  // 0: the occlusion stage is never decided here (non power-of-two pyramid, ...)
 };
 
 struct ClusterParams
@@ -150,6 +158,7 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaS
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream);
+cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cudaStream_t stream);
 cudaError_t launch_decode_clusters(const uint32_t* cluster_indices, const uint32_t* cluster_count4, const NvcMeshTaskCommand* task_commands, const NvcMeshlet* meshlets, NvcClusterRecord* records, uint32_t* stats4, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_cook_meshlet_bounds(const NvcVertex* vertices, uint32_t vertex_count, const uint32_t* meshletdata, uint32_t meshletdata_words, NvcMeshlet* meshlets, uint32_t meshlet_count, uint32_t* rejected, cudaStream_t stream);
 cudaError_t launch_update_draws(NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices, const NvcMeshDraw* update_values, uint32_t count, cudaStream_t stream);

@@ -1037,7 +1037,7 @@ struct FilterShared
 	uint32_t stage[kClusterWarps][kFStage];
 };
 
-template <bool LATE>
+template <bool LATE, bool FP>
 __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
 {
 	__shared__ FilterShared sh;
@@ -1053,6 +1053,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 	uint4* const queue = sh.queue[warp];
 	CmdRecord* const recs = sh.rec[warp];
 	uint32_t nst = 0, nq = 0;
+	uint32_t stat_items = 0, stat_undecided = 0; // per warp (uniform)
 
 	const uint32_t ncmd = p.command_count4[1] * 64u; // niagara.cpp:1599: commandId < X * 64
 	const uint32_t nbatch = (ncmd + 31u) / 32u;
@@ -1174,6 +1175,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		const bool uniform = count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0);
 		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u;
 		__syncwarp(); // records visible to the whole warp
+		stat_items += total;
 
 		for (uint32_t base = 0; base < total; base += 32)
 		{
@@ -1203,7 +1205,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 				}
 			}
 			j &= 31u;
-			uint32_t mgi = item - __shfl_sync(0xffffffffu, excl, j);
+			uint32_t mgi = uniform ? item - j * count0 : item - __shfl_sync(0xffffffffu, excl, j);
 			if (alive_flatten)
 			{
 				const uint32_t mlo = __shfl_sync(0xffffffffu, amask_lo, j), mhi = __shfl_sync(0xffffffffu, amask_hi, j);
@@ -1239,7 +1241,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 					skip = (ids.w & kRecLate) != 0u && bit; // :97-98
 			}
 
-			const FilterResult fr = filter_meshlet<LATE>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
+			const FilterResult fr = filter_meshlet<LATE, FP>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
 			const bool decided = !alive || (fr.decided && filter_on && (ids.w & kRecExactOnly) == 0u);
 			const bool visible = alive && fr.visible;
 
@@ -1250,6 +1252,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 				if (!decided)
 					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(ids.z, mi, mvi, code | ((ids.w & kRecLate) << 31));
 				nq += __popc(umask);
+				stat_undecided += __popc(umask);
 			}
 			commit(active && decided, visible, skip, oldbit, mvi, code);
 			if (nq >= 32u)
@@ -1260,6 +1263,12 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		drain(min(nq, 32u));
 	if (nst)
 		flush_stage(p, stage, nst);
+	if (lane == 0 && stat_items)
+	{
+		atomicAdd(&p.scratch->filter_items, (unsigned long long)stat_items);
+		if (stat_undecided)
+			atomicAdd(&p.scratch->filter_undecided, (unsigned long long)stat_undecided);
+	}
 
 	// ---- last-block epilogue: clustersubmit.comp.glsl:25-45 ----
 	__threadfence();
@@ -1780,6 +1789,45 @@ static cudaError_t launch_pdl(void (*kernel)(P, Extra...), dim3 grid, dim3 block
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------------
+// footprint image: F_l(i, j) = min over the clamped 2 x 2 footprint (i, i+1) x (j, j+1) of mip l, i in [-1, w-1]
+// (see HiZDesc).  One thread per entry over all levels; the pyramid was just written and is read from L2.
+// With it a sampler access whose four texels all count (fract != 0 on both axes — the only case the filter decides)
+// is ONE load instead of four scattered ones.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float* __restrict__ fp, uint32_t total)
+{
+	NVC_GRID_DEPENDENCY_SYNC();
+	const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+	if (g >= total)
+		return;
+	uint32_t l = 0;
+	while (l + 1 < hz.levels && g >= hz.fp_offset[l + 1])
+		++l;
+	const uint32_t w = max(1u, hz.width >> l), h = max(1u, hz.height >> l);
+	const uint32_t i = g - hz.fp_offset[l];
+	const uint32_t pitch = w + 1u;
+	const uint32_t iy = i / pitch, ix = i - iy * pitch;
+	const uint32_t x0 = ix ? ix - 1u : 0u, x1 = min(ix, w - 1u);
+	const uint32_t y0 = iy ? iy - 1u : 0u, y1 = min(iy, h - 1u);
+	const float* t = hz.texels + hz.level_offset[l];
+	// written by pyramid_kernel in the previous launch: plain loads are coherent across kernel boundaries
+	const float a = __ldg(t + y0 * w + x0), b = __ldg(t + y0 * w + x1), c = __ldg(t + y1 * w + x0), d = __ldg(t + y1 * w + x1);
+	fp[g] = fminf(fminf(a, b), fminf(c, d));
+}
+
+cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cudaStream_t stream)
+{
+	if (total == 0)
+		return cudaSuccess;
+#if NVC_PDL && !defined(NVC_EMU)
+	return launch_pdl(footprint_kernel, dim3((total + 255u) / 256u), dim3(256), 0, stream, hiz, fp, total);
+#else
+	footprint_kernel<<<(total + 255u) / 256u, 256, 0, stream>>>(hiz, fp, total);
+	return cudaGetLastError();
+#endif
+}
+
 cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
 {
 	uint32_t blocks = (p.cull.drawCount + kDrawBlock - 1) / kDrawBlock;
@@ -1816,12 +1864,14 @@ cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t block
 	if (p.use_filter)
 	{
 #if NVC_PDL && !defined(NVC_EMU)
-		return launch_pdl(late ? clustercull_filter_kernel<true> : clustercull_filter_kernel<false>, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
+		return launch_pdl(late ? (p.hiz.fp ? clustercull_filter_kernel<true, true> : clustercull_filter_kernel<true, false>) : clustercull_filter_kernel<false, false>, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
 #endif
-		if (late)
-			clustercull_filter_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p);
+		if (late && p.hiz.fp)
+			clustercull_filter_kernel<true, true><<<blocks, kClusterBlock, 0, stream>>>(p);
+		else if (late)
+			clustercull_filter_kernel<true, false><<<blocks, kClusterBlock, 0, stream>>>(p);
 		else
-			clustercull_filter_kernel<false><<<blocks, kClusterBlock, 0, stream>>>(p);
+			clustercull_filter_kernel<false, false><<<blocks, kClusterBlock, 0, stream>>>(p);
 		return cudaGetLastError();
 	}
 	const uint32_t stage_bytes = late ? hiz_stage_bytes(p.hiz) : 0u;
@@ -1877,9 +1927,9 @@ cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_l
 
 cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
 {
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false>, kClusterBlock, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false>, kClusterBlock, 0);
 	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true>, kClusterBlock, 0);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false>, kClusterBlock, 0);
 	return e;
 }
 

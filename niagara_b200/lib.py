@@ -27,7 +27,9 @@ SIGNATURES = [
     ("nvc_version", ctypes.c_char_p, []),
     ("nvc_prepare_meshes", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint32]),
     ("nvc_set_hiz_staging", ctypes.c_int, [c_void_p, ctypes.c_uint32]),
+    ("nvc_prepare_hiz", ctypes.c_int, [c_void_p, ctypes.POINTER(HiZ)]),
     ("nvc_set_cluster_filter", ctypes.c_int, [c_void_p, ctypes.c_int]),
+    ("nvc_filter_stats", ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     ("nvc_previous_pow2", ctypes.c_uint32, [ctypes.c_uint32]),
     ("nvc_image_mip_levels", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     ("nvc_hiz_layout", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(HiZ)]),

@@ -8,6 +8,7 @@
 Buffers carry the reference's names (db, mb, mlb, dvb, mvb, dcb, dccb, cib, ccb, depthPyramid; niagara.cpp:1027-1090).
 PyTorch is only used to own device memory and streams; every pass goes through the C ABI (libniagara_cull.so)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -25,7 +26,7 @@ def _round_up(v, m):
 
 
 class VisibilityPath:
-    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, hiz_stage_texels=None, prepare_meshes=True):
+    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, device="cuda:0", task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, hiz_stage_texels=None, prepare_meshes=True, prepare_hiz=True):
         """meshes / meshlets / draws: structured numpy arrays (layout.MESH_DTYPE / MESHLET_DTYPE / MESHDRAW_DTYPE) or
         already-resident torch uint8 tensors.  draws must already carry meshletVisibilityOffset
         (host.visibility_offsets)."""
@@ -67,6 +68,8 @@ class VisibilityPath:
         check(self.lib.nvc_hiz_layout(self.depth_width, self.depth_height, ctypes.byref(self.hiz)), self.ctx, "nvc_hiz_layout")
         self.depthPyramid = torch.zeros(self.hiz.total_texels, dtype=torch.float32, device=self.device)
         self.hiz.texels = self.depthPyramid.data_ptr()
+        if prepare_hiz and os.environ.get("NVC_PREPARE_HIZ", "1") != "0":  # derived footprint image of the pyramid (rebuilt by every nvc_depth_pyramid call)
+            check(self.lib.nvc_prepare_hiz(self.ctx, ctypes.byref(self.hiz)), self.ctx, "nvc_prepare_hiz")
 
     # -- buffers ------------------------------------------------------------------------------------------
     def _upload(self, arr):

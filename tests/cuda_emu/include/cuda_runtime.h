@@ -84,6 +84,8 @@ inline cudaError_t cudaMalloc(T** p, size_t n)
 	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+enum { cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1 };
+inline cudaError_t cudaMemcpy(void* d, const void* s_, size_t n, int) { memcpy(d, s_, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 template <typename K>
@@ -186,6 +188,7 @@ inline void __stcs(T* p, T v) { *p = v; }
 template <typename T>
 inline void __stcg(T* p, T v) { *p = v; }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline uint32_t atomicAnd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }

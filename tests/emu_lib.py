@@ -53,7 +53,7 @@ def _p(a):
 class EmuPath(oracle_lib.OraclePath):
     """OraclePath's buffers, every pass executed by the product's kernels under the SIMT emulation."""
 
-    def __init__(self, *args, defines=(), prepare_meshes=True, **kwargs):
+    def __init__(self, *args, defines=(), prepare_meshes=True, prepare_hiz=True, **kwargs):
         super().__init__(*args, **kwargs)
         self.emu = load(defines)
         self.ctx = ctypes.c_void_p()
@@ -61,6 +61,8 @@ class EmuPath(oracle_lib.OraclePath):
         assert self.emu.nvc_create(0, ctypes.byref(limits), ctypes.byref(self.ctx)) == 0
         if prepare_meshes:
             assert self.emu.nvc_prepare_meshes(self.ctx, None, _p(self.meshes), len(self.meshes)) == 0
+        if prepare_hiz:
+            assert self.emu.nvc_prepare_hiz(self.ctx, ctypes.byref(self.hiz)) == 0
 
     def _check(self, status, what):
         assert status == 0, (what, status, self.emu.nvc_last_error(self.ctx))

@@ -176,6 +176,30 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 		hiz.width = hz.width, hiz.height = hz.height, hiz.levels = hz.levels;
 		memcpy(hiz.level_offset, hz.level_offset, sizeof(hiz.level_offset));
 		hiz.stage_level = hz.levels;
+		// footprint image (what footprint_kernel builds)
+		std::vector<float> fp;
+		{
+			uint32_t total = 0;
+			for (uint32_t l = 0; l < hz.levels; ++l)
+			{
+				uint32_t w = std::max(1u, hz.width >> l), h = std::max(1u, hz.height >> l);
+				hiz.fp_offset[l] = total;
+				total += (w + 1) * (h + 1);
+			}
+			fp.resize(total);
+			for (uint32_t l = 0; l < hz.levels; ++l)
+			{
+				uint32_t w = std::max(1u, hz.width >> l), h = std::max(1u, hz.height >> l);
+				const float* t = texels.data() + hz.level_offset[l];
+				for (uint32_t iy = 0; iy <= h; ++iy)
+					for (uint32_t ix = 0; ix <= w; ++ix)
+					{
+						uint32_t x0 = ix ? ix - 1 : 0, x1 = std::min(ix, w - 1), y0 = iy ? iy - 1 : 0, y1 = std::min(iy, h - 1);
+						fp[hiz.fp_offset[l] + iy * (w + 1) + ix] = fminf(fminf(t[y0 * w + x0], t[y0 * w + x1]), fminf(t[y1 * w + x0], t[y1 * w + x1]));
+					}
+			}
+			hiz.fp = fp.data();
+		}
 		FilterConsts fc = make_filter_consts(cd, hiz, true);
 
 		// view-space -> world: world = R_cam * (vx, vy, -vz) + pos  (view = inverse camera transform with z flipped)
@@ -276,7 +300,15 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 					++st.undecided;
 					continue;
 				}
-				FilterResult fr = filter_meshlet<true>(fc, cd, hiz, rec.row0, rec.row1, rec.row2, rec.aux, b0, b1, cd.clusterBackfaceEnabled != 0, cd.clusterOcclusionEnabled == 1);
+				FilterResult fr = filter_meshlet<true, false>(fc, cd, hiz, rec.row0, rec.row1, rec.row2, rec.aux, b0, b1, cd.clusterBackfaceEnabled != 0, cd.clusterOcclusionEnabled == 1);
+				{
+					// the footprint-image variant must give the same answer
+					FilterDebug keep = dbg;
+					FilterResult fq = filter_meshlet<true, true>(fc, cd, hiz, rec.row0, rec.row1, rec.row2, rec.aux, b0, b1, cd.clusterBackfaceEnabled != 0, cd.clusterOcclusionEnabled == 1);
+					if (fq.decided && fq.visible != ve) // (the jitter differs between the two calls, so `decided` may differ)
+						++st.wrong;
+					dbg = keep;
+				}
 				if (!fr.decided)
 				{
 					++st.undecided;
