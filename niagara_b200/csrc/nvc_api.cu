@@ -403,9 +403,14 @@ NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cu
 	// nvc_set_cluster_filter(ctx, 0) select the exact kernel
 	if (ctx->cluster_filter && !staged)
 	{
-		p.use_filter = 1;
-		p.filter = nvc::make_filter_consts(p.cull, p.hiz, late && cull->clusterOcclusionEnabled == 1);
-		blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_filter_blocks_late : ctx->cluster_filter_blocks_early);
+		const bool need_occlusion = late && cull->clusterOcclusionEnabled == 1;
+		p.filter = nvc::make_filter_consts(p.cull, p.hiz, need_occlusion);
+		// unusual view / projection / pyramid shapes are outside the filter's error analysis: the exact kernel takes the pass
+		if (p.filter.enabled && (!need_occlusion || p.filter.occ_ok))
+		{
+			p.use_filter = 1;
+			blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_filter_blocks_late : ctx->cluster_filter_blocks_early);
+		}
 	}
 	cudaError_t e = nvc::launch_clustercull(p, late != 0, blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_clustercull");

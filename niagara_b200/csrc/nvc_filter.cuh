@@ -281,7 +281,7 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	const float gr = g * relE;
 	// domain of the error analysis: radius >= 0, sphere inside the validity cone, small relative uncertainty
 	const float cone_x = nvf_fma(-fc.cg.x, cz, nvf_fma(r, fc.cg.y, fabsf(cx))), cone_y = nvf_fma(-fc.cg.z, cz, nvf_fma(r, fc.cg.w, fabsf(cy)));
-	const bool dom_ok = r >= 0.f && cone_x <= 0.f && cone_y <= 0.f && gr < 9.765625e-4f /* 2^-10 */ && fc.occ_ok != 0u;
+	const bool dom_ok = r >= 0.f && cone_x <= 0.f && cone_y <= 0.f && gr < 9.765625e-4f /* 2^-10 */; // (fc.occ_ok is checked by the host: nvc_clustercull)
 
 	const float vx = nvf_sqrt(nvf_fma(cx, cx, czr2)), vy = nvf_sqrt(nvf_fma(cy, cy, czr2));
 	const float cxz = cx * cz, cyz = cy * cz, rvx = r * vx, rvy = r * vy;

@@ -1037,7 +1037,9 @@ struct FilterShared
 	uint32_t stage[kClusterWarps][kFStage];
 };
 
-template <bool LATE, bool FP>
+// TRACK: clusterOcclusionEnabled == 1 && postPass == 0 (the main passes of a frame) as a compile-time fact; the generic
+// instantiation reads the flags at run time.
+template <bool LATE, bool FP, bool TRACK>
 __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
 {
 	__shared__ FilterShared sh;
@@ -1057,12 +1059,11 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 
 	const uint32_t ncmd = p.command_count4[1] * 64u; // niagara.cpp:1599: commandId < X * 64
 	const uint32_t nbatch = (ncmd + 31u) / 32u;
-	const bool track = cd.clusterOcclusionEnabled == 1 && cd.postPass == 0; // clustercull.comp.glsl:86
-	const bool track_late = LATE && cd.clusterOcclusionEnabled == 1;
-	const bool bits_known = cd.postPass == 0;
+	const bool track = TRACK || (cd.clusterOcclusionEnabled == 1 && cd.postPass == 0); // clustercull.comp.glsl:86
+	const bool track_late = LATE && (TRACK || cd.clusterOcclusionEnabled == 1);
+	const bool bits_known = TRACK || cd.postPass == 0;
 	const bool backface = cd.clusterBackfaceEnabled != 0;
-	const bool occlusion = LATE && cd.clusterOcclusionEnabled == 1;
-	const bool filter_on = fc.enabled != 0u;
+	const bool occlusion = LATE && (TRACK || cd.clusterOcclusionEnabled == 1);
 
 	// bookkeeping of one group of <= 32 verdicts: visibility bits (late, :126-131) and compaction (:133-139)
 	auto commit = [&](bool active, bool visible, bool skip, bool oldbit, uint32_t mvi, uint32_t code) {
@@ -1217,7 +1218,6 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			const CmdRecord& rec = recs[active ? j : (lane & 0u)];
 			const uint4 ids = rec.ids;
 			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
-			const uint32_t code = (batch * 32u + j) | (mgi << 24); // :138
 			uint2 b0 = make_uint2(0u, 0u);
 			uint32_t b1 = 0u, word = 0u;
 			if (active)
@@ -1242,10 +1242,17 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			}
 
 			const FilterResult fr = filter_meshlet<LATE, FP>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
-			const bool decided = !alive || (fr.decided && filter_on && (ids.w & kRecExactOnly) == 0u);
+			const bool decided = !alive || (fr.decided && (ids.w & kRecExactOnly) == 0u);
 			const bool visible = alive && fr.visible;
 
+			// ---- fast exit: nothing undecided, no visibility bit changes, nothing to append (the steady-state chunk) ----
+			const bool emits = visible && !skip;
+			const bool changes = track_late && (!bits_known || oldbit != visible);
+			if (!__any_sync(0xffffffffu, !decided || (active && (emits || changes))))
+				continue;
+
 			// ---- undecided lanes -> queue (exact path on full warps) ----
+			const uint32_t code = (batch * 32u + j) | (mgi << 24); // :138
 			const uint32_t umask = __ballot_sync(0xffffffffu, !decided);
 			if (umask)
 			{
@@ -1863,16 +1870,19 @@ cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t block
 {
 	if (p.use_filter)
 	{
-#if NVC_PDL && !defined(NVC_EMU)
-		return launch_pdl(late ? (p.hiz.fp ? clustercull_filter_kernel<true, true> : clustercull_filter_kernel<true, false>) : clustercull_filter_kernel<false, false>, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
-#endif
-		if (late && p.hiz.fp)
-			clustercull_filter_kernel<true, true><<<blocks, kClusterBlock, 0, stream>>>(p);
-		else if (late)
-			clustercull_filter_kernel<true, false><<<blocks, kClusterBlock, 0, stream>>>(p);
+		const bool track = p.cull.clusterOcclusionEnabled == 1 && p.cull.postPass == 0;
+		void (*kernel)(ClusterParams);
+		if (late)
+			kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true> : clustercull_filter_kernel<true, true, false>)
+			                  : (track ? clustercull_filter_kernel<true, false, true> : clustercull_filter_kernel<true, false, false>);
 		else
-			clustercull_filter_kernel<false, false><<<blocks, kClusterBlock, 0, stream>>>(p);
+			kernel = track ? clustercull_filter_kernel<false, false, true> : clustercull_filter_kernel<false, false, false>;
+#if NVC_PDL && !defined(NVC_EMU)
+		return launch_pdl(kernel, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
+#else
+		kernel<<<blocks, kClusterBlock, 0, stream>>>(p);
 		return cudaGetLastError();
+#endif
 	}
 	const uint32_t stage_bytes = late ? hiz_stage_bytes(p.hiz) : 0u;
 #if NVC_PDL && !defined(NVC_EMU)
@@ -1927,9 +1937,9 @@ cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_l
 
 cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
 {
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false>, kClusterBlock, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false, false>, kClusterBlock, 0);
 	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false>, kClusterBlock, 0);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false, false>, kClusterBlock, 0);
 	return e;
 }
 
