@@ -112,7 +112,8 @@ def synthetic_depth(width, height, znear=0.1, occluders=200, seed=4, zrange=(5.0
 class Scene:
     """Everything one configuration needs, in host memory."""
 
-    def __init__(self, name, meshes, meshlets, draws, depth, camera, screen, visibility_bits, note=""):
+    def __init__(self, name, meshes, meshlets, draws, depth, camera, screen, visibility_bits, note="", helpers=None):
+        self.helpers = helpers  # None = niagara_b200.host; bench.py's CPU arms pass the checker's own helpers
         self.name = name
         self.meshes = meshes
         self.meshlets = meshlets
@@ -124,10 +125,11 @@ class Scene:
         self.note = note
 
     def cull_data(self, **toggles):
-        return host.cull_data(self.camera, self.screen[0], self.screen[1], len(self.draws), **toggles)
+        return (self.helpers or host).cull_data(self.camera, self.screen[0], self.screen[1], len(self.draws), **toggles)
 
     def __getstate__(self):
         st = dict(self.__dict__)
+        st["helpers"] = None
         c = self.camera
         st["camera"] = (tuple(c.position), tuple(c.orientation), float(c.fovY), float(c.znear))
         return st
@@ -155,17 +157,18 @@ def config2_scene(draw_count=1_000_000, num_meshes=1024, screen=(4096, 4096), se
     return s
 
 
-def config4_scene(draw_count=1_000_000, meshlets_per_draw=10, screen=(4096, 4096), seed=21, occluders=120):
+def config4_scene(draw_count=1_000_000, meshlets_per_draw=10, screen=(4096, 4096), seed=21, occluders=120, helpers=None):
     """BASELINE configs[3]: 10M synthetic meshlets / 1M draws: one UNIQUE mesh per draw (so Meshlet[] = 240 MB >> L2,
     SURVEY F9), every draw inside the frustum so that the cluster pass really tests ~all meshlet instances."""
+    h = helpers or host
     meshes, nmeshlets = synthetic_meshes(draw_count, 1, meshlets_per_draw, seed=seed)
     meshlets = synthetic_meshlets(nmeshlets, seed=seed + 1)
-    cam = host.make_camera()
+    cam = h.make_camera()
     aspect = screen[0] / screen[1]
     draws = frustum_draws(draw_count, np.arange(draw_count, dtype=np.uint32), fov_y=cam.fovY, aspect=aspect, seed=seed + 2)
-    bits, _ = host.visibility_offsets(draws, meshes)
+    bits, _ = h.visibility_offsets(draws, meshes)
     depth = synthetic_depth(screen[0], screen[1], cam.znear, occluders=occluders, seed=seed + 3, zrange=(60.0, 190.0), max_extent=0.12)
-    s = Scene("C4", meshes, meshlets, draws, depth, cam, screen, bits)
+    s = Scene("C4", meshes, meshlets, draws, depth, cam, screen, bits, helpers=helpers)
     s.note = "%d draws x %d unique meshlets each (%d meshlet instances), all inside the frustum, %dx%d depth" % (
         draw_count,
         meshlets_per_draw,

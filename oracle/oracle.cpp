@@ -31,6 +31,10 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <sched.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <math.h>
 #include <vector>
 
 #if defined(__FAST_MATH__)
@@ -454,6 +458,36 @@ void clusterRange(const NvcCullData& cd, bool late, const NvcMeshTaskCommand* cm
 
 // Minimal persistent worker pool: the multi-threaded oracle is also the reported CPU baseline, so it should not pay
 // for creating (cores) threads in every pass.
+// ORC_PIN=1 (bench.py's CPU arms): every worker stays on ONE of the CPUs the process may use (worker i -> i-th allowed
+// CPU), so that the timing does not depend on where the scheduler happens to migrate 128 threads.
+inline void pinWorker(int index)
+{
+	static const bool enabled = [] { const char* e = getenv("ORC_PIN"); return e && atoi(e) != 0; }();
+	if (!enabled)
+		return;
+	cpu_set_t allowed;
+	CPU_ZERO(&allowed);
+	if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+		return;
+	int n = CPU_COUNT(&allowed);
+	if (n <= 0)
+		return;
+	int want = index % n, seen = 0;
+	for (int c = 0; c < CPU_SETSIZE; ++c)
+		if (CPU_ISSET(c, &allowed))
+		{
+			if (seen == want)
+			{
+				cpu_set_t one;
+				CPU_ZERO(&one);
+				CPU_SET(c, &one);
+				pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+				return;
+			}
+			++seen;
+		}
+}
+
 class Pool
 {
 public:
@@ -502,6 +536,7 @@ private:
 
 	void loop(int idx)
 	{
+		pinWorker(idx + 1);
 		uint64_t seen = 0;
 		for (;;)
 		{
@@ -859,5 +894,102 @@ void orc_transform_point(const float m[16], const float p[3], float out[3])
 }
 
 int orc_hardware_threads(void) { return int(std::thread::hardware_concurrency()); }
+
+// ---- host-side helpers of the CHECKER (so that bench.py's CPU arms never load the product library) --------------------
+// niagara.cpp:1002-1020: meshletVisibilityOffset = running sum over draws of the max-over-LODs meshlet count
+uint32_t orc_visibility_offsets(NvcMeshDraw* draws, uint32_t draw_count, const NvcMesh* meshes)
+{
+	uint32_t total = 0;
+	for (uint32_t i = 0; i < draw_count; ++i)
+	{
+		const NvcMesh& mesh = meshes[draws[i].meshIndex];
+		draws[i].meshletVisibilityOffset = total;
+		uint32_t most = 0;
+		for (uint32_t l = 0; l < mesh.lodCount && l < NVC_MAX_LODS; ++l)
+			most = std::max(most, mesh.lods[l].meshletCount);
+		total += most;
+	}
+	return total;
+}
+
+// niagara.cpp:1339-1342 + resources.cpp:280-292: pyramid = previous power of two of the depth target, full mip chain,
+// packed level after level
+int orc_hiz_layout(uint32_t depth_width, uint32_t depth_height, NvcHiZ* out)
+{
+	if (!out || depth_width == 0 || depth_height == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	auto pow2 = [](uint32_t v) { uint32_t r = 1; while (r * 2 < v) r *= 2; return r; }; // niagara.cpp:439-447 (strictly below v)
+	memset(out, 0, sizeof(*out));
+	out->width = pow2(depth_width);
+	out->height = pow2(depth_height);
+	uint32_t w = out->width, h = out->height, levels = 0, total = 0;
+	while (levels < NVC_MAX_HIZ_LEVELS)
+	{
+		out->level_offset[levels++] = total;
+		total += w * h;
+		if (w == 1 && h == 1)
+			break;
+		w = std::max(1u, w / 2);
+		h = std::max(1u, h / 2);
+	}
+	out->levels = levels;
+	out->total_texels = total;
+	return NVC_OK;
+}
+
+// niagara.cpp:424-432,1487-1516 in double precision, rounded once: view = scale(1,1,-1) * inverse(T * R(q)),
+// infinite-far reverse-Z projection, normalised frustum side planes, 1-pixel LOD target, pyramid size
+void orc_cull_data(const NvcCamera* camera, uint32_t screen_width, uint32_t screen_height, uint32_t draw_count, const NvcCullOptions* options, NvcCullData* out)
+{
+	const double x = camera->orientation[0], y = camera->orientation[1], z = camera->orientation[2], w = camera->orientation[3];
+	// rotation matrix of the unit quaternion, R[row][col]
+	const double R[3][3] = { { 1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y) }, { 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x) }, { 2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y) } };
+	NvcCullData cd;
+	memset(&cd, 0, sizeof(cd));
+	for (int r = 0; r < 3; ++r)
+	{
+		const double flip = r == 2 ? -1.0 : 1.0;
+		double t = 0;
+		for (int c = 0; c < 3; ++c)
+		{
+			cd.view[c * 4 + r] = float(flip * R[c][r]) + 0.0f; // (R^T)[r][c], column-major storage; + 0: no negative zeros
+			t += R[c][r] * camera->position[c];
+		}
+		cd.view[12 + r] = float(-flip * t) + 0.0f;
+	}
+	cd.view[15] = 1.f;
+	// the projection terms in binary32 like the reference's glm code (niagara.cpp:424-432)
+	const float aspect = float(screen_width) / float(screen_height);
+	const float f = 1.0f / tanf(camera->fovY / 2.0f);
+	cd.P00 = f / aspect;
+	cd.P11 = f;
+	cd.znear = camera->znear;
+	cd.zfar = options->draw_distance;
+	// planes row3 + row0 = (P00, 0, 1, 0), row3 + row1 = (0, P11, 1, 0), normalised by the length of their xyz
+	const float nx = sqrtf(cd.P00 * cd.P00 + 1.0f), ny = sqrtf(cd.P11 * cd.P11 + 1.0f);
+	cd.frustum[0] = cd.P00 / nx;
+	cd.frustum[1] = 1.0f / nx;
+	cd.frustum[2] = cd.P11 / ny;
+	cd.frustum[3] = 1.0f / ny;
+	cd.drawCount = draw_count;
+	cd.cullingEnabled = options->culling;
+	cd.lodEnabled = options->lod;
+	cd.occlusionEnabled = options->occlusion;
+	cd.lodTarget = (2 / cd.P11) * (1.f / float(screen_height)) * float(1 << options->debug_lod_step);
+	auto pow2 = [](uint32_t v) { uint32_t r = 1; while (r * 2 < v) r *= 2; return r; }; // niagara.cpp:439-447 (strictly below v)
+	cd.pyramidWidth = float(pow2(screen_width));
+	cd.pyramidHeight = float(pow2(screen_height));
+	cd.clusterOcclusionEnabled = options->occlusion && options->cluster_occlusion && options->mesh_shading;
+	*out = cd;
+}
+
+// niagara.cpp:1547-1550,1595-1596: the per-pass copy of the frame's CullData
+void orc_pass_data(const NvcCullData* frame, int for_drawcull, uint32_t post_pass, NvcCullData* out)
+{
+	*out = *frame;
+	if (for_drawcull)
+		out->clusterBackfaceEnabled = post_pass == 0;
+	out->postPass = post_pass;
+}
 
 } // extern "C"

@@ -48,8 +48,54 @@ def load():
     lib.orc_cone_cull.argtypes = [vp, ctypes.c_float, vp, ctypes.c_float]
     lib.orc_transform_point.argtypes = [vp, vp, vp]
     lib.orc_hardware_threads.restype = ctypes.c_int
+    lib.orc_visibility_offsets.restype = ctypes.c_uint32
+    lib.orc_visibility_offsets.argtypes = [vp, ctypes.c_uint32, vp]
+    lib.orc_hiz_layout.restype = ctypes.c_int
+    lib.orc_hiz_layout.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(layout.HiZ)]
+    lib.orc_cull_data.restype = None
+    lib.orc_cull_data.argtypes = [ctypes.POINTER(layout.Camera), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(layout.CullOptions), ctypes.POINTER(layout.CullData)]
+    lib.orc_pass_data.restype = None
+    lib.orc_pass_data.argtypes = [ctypes.POINTER(layout.CullData), ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(layout.CullData)]
     _LIB = lib
     return lib
+
+
+class CheckerHost:
+    """Host-side helpers served by the ORACLE library (orc_*), with the surface of niagara_b200.host that the scene
+    generators and OraclePath need.  bench.py's CPU arms use it so that they never load the product library."""
+
+    @staticmethod
+    def visibility_offsets(draws, meshes):
+        meshes = np.ascontiguousarray(meshes)
+        return int(load().orc_visibility_offsets(draws.ctypes.data_as(vp), len(draws), meshes.ctypes.data_as(vp))), 1
+
+    @staticmethod
+    def make_camera(position=(0.0, 0.0, 0.0), orientation=(0.0, 0.0, 0.0, 1.0), fov_y=1.2217304763960306, znear=0.1):
+        cam = layout.Camera()
+        cam.position[:] = position
+        cam.orientation[:] = orientation
+        cam.fovY = fov_y
+        cam.znear = znear
+        return cam
+
+    @staticmethod
+    def cull_data(camera, screen_width, screen_height, draw_count, draw_distance=200.0, culling=True, lod=True, occlusion=True, cluster_occlusion=True, mesh_shading=True, debug_lod_step=0):
+        opts = layout.CullOptions(float(draw_distance), int(culling), int(lod), int(occlusion), int(cluster_occlusion), int(mesh_shading), int(debug_lod_step))
+        out = layout.CullData()
+        load().orc_cull_data(ctypes.byref(camera), int(screen_width), int(screen_height), int(draw_count), ctypes.byref(opts), ctypes.byref(out))
+        return out
+
+    @staticmethod
+    def hiz_layout(depth_width, depth_height):
+        hiz = layout.HiZ()
+        assert load().orc_hiz_layout(int(depth_width), int(depth_height), ctypes.byref(hiz)) == 0
+        return hiz
+
+    @staticmethod
+    def pass_data(cull_data, for_drawcull, post_pass):
+        out = layout.CullData()
+        load().orc_pass_data(ctypes.byref(cull_data), int(for_drawcull), int(post_pass), ctypes.byref(out))
+        return out
 
 
 def _p(a):
@@ -63,8 +109,13 @@ def _round_up(v, m):
 class OraclePath:
     """Same surface as niagara_b200.path.VisibilityPath, on host arrays, through the oracle."""
 
-    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, threads=1, cmd_capacity=None, cluster_capacity=None):
-        from niagara_b200 import host
+    def __init__(self, meshes, meshlets, draws, depth_width, depth_height, task_wglimit=layout.TASK_WGLIMIT, cluster_limit=layout.CLUSTER_LIMIT, mesh_shading=True, threads=1, cmd_capacity=None, cluster_capacity=None, helpers=None):
+        """helpers: None = the product's host helpers (niagara_b200.host, what the tests compare against), or CheckerHost."""
+        if helpers is None:
+            from niagara_b200 import host
+        else:
+            host = helpers
+        self.helpers = helpers
 
         self.lib = load()
         self.threads = threads
@@ -93,6 +144,8 @@ class OraclePath:
         self.mvb = np.zeros(max(1, (int(count) + 31) // 32), dtype=np.uint32)
 
     def _pass_data(self, cull_data, for_drawcull, post_pass):
+        if self.helpers is not None:
+            return self.helpers.pass_data(cull_data, for_drawcull, post_pass)
         from niagara_b200.lib import load_library
 
         out = layout.CullData()
