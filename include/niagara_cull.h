@@ -336,11 +336,16 @@ NVC_API int nvc_allgather_visible(NvcContext* ctx, void* stream, const void* loc
  * PUSHES its slab + counters into slot `rank` of every rank's gathered buffers with peer cudaMemcpyAsync over CUDA-IPC
  * mappings, then raises a flag in the peer's memory; nvc_gather_wait blocks a stream (device side) until all ranks'
  * data of the latest push has landed.  One process per GPU.
- *   nvc_gather_create   allocates this rank's receive buffers, returns a 192-byte IPC ticket
+ *   nvc_gather_create   allocates this rank's receive buffers (double-buffered by frame parity), returns a 192-byte IPC ticket
  *   nvc_gather_connect  all ranks' tickets (world x 192 bytes, rank order, exchanged by the caller)
- *   nvc_gather_push     enqueue after the pass that produced local_slab / local_count4 on `stream`
- *   nvc_gather_wait     enqueue on the stream that consumes the gathered data (or reuses local_slab)
- *   nvc_gather_buffers  this rank's gathered slabs [world][slab_bytes] and counters [world][4] */
+ *   nvc_gather_push     enqueue after the pass that produced local_slab / local_count4 on `stream`; the counters are
+ *                       snapshotted in stream order, the slab must stay unchanged until nvc_gather_wait
+ *   nvc_gather_wait     enqueue on the stream that consumes the gathered data (or reuses local_slab); every push must be
+ *                       followed by its wait before the second-next push
+ *   nvc_gather_buffers  this rank's gathered slabs [world][slab_bytes] and counters [world][4] of the latest frame, valid from
+ *                       its nvc_gather_wait until the next nvc_gather_wait
+ * No barrier is needed between frames: receivers acknowledge to senders which frame they are done with, and a sender reuses a
+ * parity buffer only after every peer has acknowledged its previous user (a fast rank runs at most one frame ahead). */
 NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int world_size, void* ticket192_out);
 NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets);
 NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4);

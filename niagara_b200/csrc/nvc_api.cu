@@ -9,6 +9,10 @@
 namespace
 {
 
+// Coarse Hi-Z mips staged per CTA (TMA): static + dynamic shared memory of clustercull_kernel<true, true> must stay under the
+// 48 KB a kernel gets without opting in; its static part is 8.2 KB (s_stage[8][256] + barriers), so 39 KB = 9984 texels.
+constexpr uint32_t kMaxStageTexels = 9984;
+
 int cuda_fail(NvcContext* ctx, cudaError_t e, const char* what)
 {
 	if (ctx)
@@ -185,8 +189,8 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 	{
 		if (const char* env = getenv("NVC_HIZ_STAGE_TEXELS"))
 			ctx->hiz_stage_budget = uint32_t(strtoul(env, nullptr, 10));
-		if (ctx->hiz_stage_budget > 11264)
-			ctx->hiz_stage_budget = 11264; // 44 KB: stays under the 48 KB dynamic shared memory default
+		if (ctx->hiz_stage_budget > kMaxStageTexels)
+			ctx->hiz_stage_budget = kMaxStageTexels;
 		e = nvc::clustercull_occupancy(&ctx->cluster_blocks_early, &ctx->cluster_blocks_late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
 	}
 	if (e == cudaSuccess)
@@ -276,7 +280,7 @@ NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels)
 	if (!ctx)
 		return NVC_ERROR_INVALID_ARGUMENT;
 	DeviceGuard guard(ctx->device);
-	ctx->hiz_stage_budget = texels > 11264 ? 11264 : texels; // 44 KB: stays under the 48 KB dynamic shared memory default
+	ctx->hiz_stage_budget = texels > kMaxStageTexels ? kMaxStageTexels : texels;
 	int early = 0, late = 0;
 	cudaError_t e = nvc::clustercull_occupancy(&early, &late, &ctx->cluster_blocks_late_staged, ctx->hiz_stage_budget * 4u);
 	if (e != cudaSuccess)
@@ -436,6 +440,8 @@ NVC_API int nvc_decode_clusters(NvcContext* ctx, void* stream, const uint32_t* c
     const NvcMeshTaskCommand* task_commands, const NvcMeshlet* meshlets, NvcClusterRecord* records, uint32_t* stats4)
 {
 	if (!ctx || !cluster_indices || !cluster_count4 || !task_commands || !meshlets || !stats4)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!device_is_current(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaError_t e = nvc::launch_decode_clusters(cluster_indices, cluster_count4, task_commands, meshlets, records, stats4, uint32_t(ctx->sm_count) * 8u, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_decode_clusters");

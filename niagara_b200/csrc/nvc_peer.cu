@@ -4,6 +4,16 @@
 // the peer's memory; the receiver's stream blocks in a tiny spin kernel until all flags carry the current frame tag.
 // Unlike an NCCL all-gather this needs no SMs, so it overlaps the (persistent, SM-filling) late cluster pass.
 // One process per GPU; the IPC tickets are exchanged by the caller (any transport).
+//
+// Flow control (no barrier anywhere): the receive buffers are DOUBLE-BUFFERED by the parity of the frame tag, and every
+// receiver acknowledges to every sender which frame it has finished with:
+//   push(T)  waits (device side, on a side stream) until every peer has acknowledged frame T-2 — the previous user of the
+//            parity-T&1 buffers — then copies into the peers' parity-T&1 slots and raises flag = T;
+//   wait(T)  first tells every peer "I am done with frame T-1" (everything enqueued on `stream` before this call has read
+//            it), then blocks `stream` until all flags carry T.  The gathered data of frame T stay valid until this rank
+//            calls wait(T+1).
+// A fast rank can therefore run at most one frame ahead of the slowest consumer of its data; nothing is overwritten
+// while it may still be read.
 #include "nvc_internal.h"
 
 #include <stdlib.h>
@@ -15,11 +25,14 @@ namespace
 constexpr int kMaxWorld = 64;
 constexpr int kSideStreams = 8; // one per peer at 8 GPUs: independent copy engines
 
-struct Ticket // what a rank publishes: IPC handles of its three receive buffers
+struct Ticket // what a rank publishes: IPC handles of its receive buffers (counts, flags and acks share one allocation)
 {
 	cudaIpcMemHandle_t slabs, counts, flags;
 };
 static_assert(sizeof(Ticket) == 192, "ticket is 3 x 64 bytes");
+
+// layout of the small `flags` allocation (uint32 words): [0, kMaxWorld) data flags, [kMaxWorld, 2 kMaxWorld) acks
+constexpr int kAckBase = 64;
 
 __global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag)
 {
@@ -35,8 +48,9 @@ __global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int r
 // device) to every rank's slot with 16-byte peer stores.  Launched on a high-priority stream right before the late
 // cluster pass so that its CTAs are placed first; the persistent cluster kernel fills the remaining slots.
 __global__ void __launch_bounds__(512) push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* const* peer_slabs,
-    uint32_t* const* peer_counts, size_t slab_bytes, int world, int rank)
+    uint32_t* const* peer_counts, size_t slab_bytes, int world, int rank, uint32_t parity)
 {
+	const size_t slot = size_t(parity) * world + rank;
 	const uint32_t count = local_count4[0];
 	size_t bytes = size_t(count) * sizeof(NvcMeshTaskCommand);
 	bytes = bytes < slab_bytes ? bytes : slab_bytes;
@@ -48,15 +62,26 @@ __global__ void __launch_bounds__(512) push_kernel(const uint4* __restrict__ loc
 		for (int k = 0; k < world; ++k)
 		{
 			int p = (rank + k) % world;
-			reinterpret_cast<uint4*>(peer_slabs[p] + size_t(rank) * slab_bytes)[i] = v;
+			reinterpret_cast<uint4*>(peer_slabs[p] + slot * slab_bytes)[i] = v;
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x < uint32_t(world))
 	{
 		uint4 c = *reinterpret_cast<const uint4*>(local_count4);
-		*reinterpret_cast<uint4*>(peer_counts[threadIdx.x] + 4 * rank) = c;
+		*reinterpret_cast<uint4*>(peer_counts[threadIdx.x] + 4 * slot) = c;
 	}
 	__threadfence_system();
+}
+
+// tells every peer that this rank is done with frame `tag`: acks[rank] = tag in the peer's memory
+__global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag)
+{
+	int p = threadIdx.x;
+	if (p < world)
+	{
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + kAckBase + rank) = tag;
+	}
 }
 
 __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag)
@@ -77,9 +102,9 @@ struct NvcGather
 {
 	int world = 1, rank = 0;
 	size_t slab_bytes = 0;
-	uint8_t* slabs = nullptr;   // [world][slab_bytes]   receive buffer of this rank
-	uint32_t* counts = nullptr; // [world][4]
-	uint32_t* flags = nullptr;  // [world]
+	uint8_t* slabs = nullptr;   // [2][world][slab_bytes] receive buffers of this rank, indexed by tag parity
+	uint32_t* counts = nullptr; // [2][world][4]
+	uint32_t* flags = nullptr;  // [kMaxWorld] data flags + [kMaxWorld] acks
 	uint8_t* peer_slabs[kMaxWorld] = {};
 	uint32_t* peer_counts[kMaxWorld] = {};
 	uint32_t* peer_flags[kMaxWorld] = {};
@@ -90,7 +115,9 @@ struct NvcGather
 	int mode = 0;              // 0 = copy engines, 1 = SM push kernel
 	cudaStream_t side[kSideStreams] = {};
 	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
-	uint32_t tag = 0;
+	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity
+	cudaEvent_t acked = nullptr;
+	uint32_t tag = 0, acked_tag = 0;
 	bool connected = false;
 };
 
@@ -123,6 +150,9 @@ void gather_destroy(NvcContext* ctx)
 	}
 	if (g->fork)
 		cudaEventDestroy(g->fork);
+	if (g->acked)
+		cudaEventDestroy(g->acked);
+	cudaFree(g->count_stage);
 	cudaFree(g->slabs);
 	cudaFree(g->counts);
 	cudaFree(g->flags);
@@ -142,19 +172,31 @@ extern "C"
 
 NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int world, void* ticket192_out)
 {
-	if (!ctx || !ticket192_out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || slab_bytes == 0)
+	// slabs are moved in 16-byte units (and hold whole 64-command groups in the reference's sizing)
+	if (!ctx || !ticket192_out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || slab_bytes == 0 || slab_bytes % 16 != 0)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	int previous_device = -1;
+	cudaGetDevice(&previous_device);
 	cudaSetDevice(ctx->device);
+	struct Restore
+	{
+		int d;
+		~Restore()
+		{
+			if (d >= 0)
+				cudaSetDevice(d);
+		}
+	} restore{ previous_device };
 	nvc::gather_destroy(ctx);
 	NvcGather* g = new NvcGather();
 	g->world = world;
 	g->rank = rank;
 	g->slab_bytes = slab_bytes;
-	cudaError_t e = cudaMalloc(&g->slabs, slab_bytes * world);
+	cudaError_t e = cudaMalloc(&g->slabs, 2 * slab_bytes * world);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&g->counts, sizeof(uint32_t) * 4 * world);
+		e = cudaMalloc(&g->counts, 2 * sizeof(uint32_t) * 4 * world);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&g->flags, sizeof(uint32_t) * kMaxWorld);
+		e = cudaMalloc(&g->flags, sizeof(uint32_t) * 2 * kMaxWorld);
 	if (e == cudaSuccess)
 		e = cudaMalloc(&g->d_peer_flags, sizeof(uint32_t*) * kMaxWorld);
 	if (e == cudaSuccess)
@@ -170,9 +212,9 @@ NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int 
 	if (const char* env = getenv("NVC_GATHER_MODE"))
 		g->mode = (strcmp(env, "sm") == 0) ? 1 : 0;
 	if (e == cudaSuccess)
-		e = cudaMemset(g->counts, 0, sizeof(uint32_t) * 4 * world);
+		e = cudaMemset(g->counts, 0, 2 * sizeof(uint32_t) * 4 * world);
 	if (e == cudaSuccess)
-		e = cudaMemset(g->flags, 0, sizeof(uint32_t) * kMaxWorld);
+		e = cudaMemset(g->flags, 0, sizeof(uint32_t) * 2 * kMaxWorld);
 	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
 	{
 		e = cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking);
@@ -181,6 +223,10 @@ NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int 
 	}
 	if (e == cudaSuccess)
 		e = cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&g->acked, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->count_stage, 32);
 	Ticket t;
 	memset(&t, 0, sizeof(t));
 	if (e == cudaSuccess)
@@ -207,7 +253,18 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets /* world
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
 	if (!g || !all_tickets)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	int previous_device = -1;
+	cudaGetDevice(&previous_device);
 	cudaSetDevice(ctx->device);
+	struct Restore
+	{
+		int d;
+		~Restore()
+		{
+			if (d >= 0)
+				cudaSetDevice(d);
+		}
+	} restore{ previous_device };
 	const Ticket* tickets = static_cast<const Ticket*>(all_tickets);
 	cudaError_t e = cudaSuccess;
 	for (int p = 0; p < g->world && e == cudaSuccess; ++p)
@@ -234,35 +291,75 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets /* world
 	if (e != cudaSuccess)
 	{
 		ctx->last_error = std::string("nvc_gather_connect: ") + cudaGetErrorString(e);
+		// close whatever was opened: a half-connected gather is not usable and must not leak the mappings
+		for (int p = 0; p < g->world; ++p)
+			if (p != g->rank)
+			{
+				if (g->peer_slabs[p])
+					cudaIpcCloseMemHandle(g->peer_slabs[p]);
+				if (g->peer_counts[p])
+					cudaIpcCloseMemHandle(g->peer_counts[p]);
+				if (g->peer_flags[p])
+					cudaIpcCloseMemHandle(g->peer_flags[p]);
+				g->peer_slabs[p] = nullptr;
+				g->peer_counts[p] = nullptr;
+				g->peer_flags[p] = nullptr;
+			}
 		return NVC_ERROR_CUDA;
 	}
 	g->connected = true;
 	return NVC_OK;
 }
 
+static bool on_context_device(NvcContext* ctx)
+{
+	int current = -1;
+	if (cudaGetDevice(&current) != cudaSuccess || current != ctx->device)
+	{
+		ctx->last_error = "the context's CUDA device is not the calling thread's current device";
+		return false;
+	}
+	return true;
+}
+
 // Enqueues (after everything already on `stream`): push of local_slab / local_count4 into slot `rank` of every rank's
-// gathered buffers over the side streams, then the flag raise.  Returns immediately; `stream` itself is not blocked
-// by the copies (call nvc_gather_wait on the stream that consumes the gathered data).
+// gathered buffers (parity of the new frame tag) over the side streams, then the flag raise.  Returns immediately;
+// `stream` itself is not blocked by the copies (call nvc_gather_wait on the stream that consumes the gathered data).
+// local_count4 is snapshotted on `stream` right here; local_slab must stay unchanged until nvc_gather_wait.
 NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4)
 {
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
 	if (!g || !g->connected || !local_slab || !local_count4)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	g->tag += 1;
-	cudaError_t e = cudaEventRecord(g->fork, s);
+	const uint32_t tag = g->tag;
+	const size_t parity = tag & 1u;
+	const size_t slot = parity * size_t(g->world) + size_t(g->rank); // this rank's slot in every receiver's buffers
+	uint32_t* count_stage = g->count_stage + 4 * parity;
+	// the counters are snapshotted in stream order: later passes on `stream` may rewrite local_count4 at once
+	cudaError_t e = cudaMemcpyAsync(count_stage, local_count4, 16, cudaMemcpyDeviceToDevice, s);
+	if (e == cudaSuccess)
+		e = cudaEventRecord(g->fork, s);
+	cudaStream_t lead = g->mode == 1 ? g->hi : g->side[0];
+	if (e == cudaSuccess)
+		e = cudaStreamWaitEvent(lead, g->fork, 0);
+	if (e == cudaSuccess && tag >= 3)
+	{
+		// the parity buffers were last used by frame tag-2: every peer must have acknowledged it
+		wait_flags_kernel<<<1, kMaxWorld, 0, lead>>>(g->flags + kAckBase, g->world, tag - 2);
+		e = cudaGetLastError();
+	}
 	if (g->mode == 1 && e == cudaSuccess)
 	{
 		// SM push: one kernel on the high-priority stream, then the flag raise behind it
-		e = cudaStreamWaitEvent(g->hi, g->fork, 0);
+		push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity));
+		e = cudaGetLastError();
 		if (e == cudaSuccess)
 		{
-			push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), local_count4, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank);
-			e = cudaGetLastError();
-		}
-		if (e == cudaSuccess)
-		{
-			raise_flags_kernel<<<1, kMaxWorld, 0, g->hi>>>(g->d_peer_flags, g->world, g->rank, g->tag);
+			raise_flags_kernel<<<1, kMaxWorld, 0, g->hi>>>(g->d_peer_flags, g->world, g->rank, tag);
 			e = cudaGetLastError();
 		}
 		if (e == cudaSuccess)
@@ -274,15 +371,17 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 		}
 		return NVC_OK;
 	}
-	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
-		e = cudaStreamWaitEvent(g->side[i], g->fork, 0);
+	if (e == cudaSuccess)
+		e = cudaEventRecord(g->acked, g->side[0]);
+	for (int i = 1; i < kSideStreams && e == cudaSuccess; ++i)
+		e = cudaStreamWaitEvent(g->side[i], g->acked, 0);
 	for (int k = 0; k < g->world && e == cudaSuccess; ++k)
 	{
 		int p = (g->rank + k) % g->world; // stagger the targets so that ranks do not all hit the same peer first
 		cudaStream_t ss = g->side[k % kSideStreams];
-		e = cudaMemcpyAsync(g->peer_slabs[p] + size_t(g->rank) * g->slab_bytes, local_slab, g->slab_bytes, cudaMemcpyDeviceToDevice, ss);
+		e = cudaMemcpyAsync(g->peer_slabs[p] + slot * g->slab_bytes, local_slab, g->slab_bytes, cudaMemcpyDeviceToDevice, ss);
 		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(g->peer_counts[p] + 4 * g->rank, local_count4, 16, cudaMemcpyDeviceToDevice, ss);
+			e = cudaMemcpyAsync(g->peer_counts[p] + 4 * slot, count_stage, 16, cudaMemcpyDeviceToDevice, ss);
 	}
 	// flags go out once every copy of this rank has completed: join the side streams on side[0], raise there
 	for (int i = 1; i < kSideStreams && e == cudaSuccess; ++i)
@@ -293,7 +392,7 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	}
 	if (e == cudaSuccess)
 	{
-		raise_flags_kernel<<<1, kMaxWorld, 0, g->side[0]>>>(g->d_peer_flags, g->world, g->rank, g->tag);
+		raise_flags_kernel<<<1, kMaxWorld, 0, g->side[0]>>>(g->d_peer_flags, g->world, g->rank, tag);
 		e = cudaGetLastError();
 	}
 	if (e == cudaSuccess)
@@ -306,15 +405,27 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	return NVC_OK;
 }
 
-// Blocks `stream` (device side) until every rank's slab of the latest push has landed in this rank's gathered buffers,
-// and until this rank's own outgoing copies are done (so the local slab may be overwritten by the next pass).
+// For the latest push (frame tag T): acknowledges frame T-1 to every peer (all work enqueued on `stream` so far has
+// read it), then blocks `stream` (device side) until every rank's slab of frame T has landed in this rank's gathered
+// buffers and this rank's own outgoing copies are done (so the local slab may be overwritten by the next pass).
+// The gathered buffers of frame T (nvc_gather_buffers) stay valid until the next nvc_gather_wait.
 NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 {
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
 	if (!g || !g->connected)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaError_t e = cudaStreamWaitEvent(s, g->join[0], 0);
+	cudaError_t e = cudaSuccess;
+	if (g->tag >= 2 && g->acked_tag != g->tag - 1)
+	{
+		raise_acks_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->world, g->rank, g->tag - 1);
+		e = cudaGetLastError();
+		g->acked_tag = g->tag - 1;
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamWaitEvent(s, g->join[0], 0);
 	if (e == cudaSuccess)
 	{
 		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag);
@@ -342,10 +453,12 @@ NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t*
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
 	if (!g)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	// the buffers of the latest frame (parity of its tag); valid between nvc_gather_wait and the next nvc_gather_wait
+	const size_t parity = g->tag & 1u;
 	if (gathered_slabs)
-		*gathered_slabs = g->slabs;
+		*gathered_slabs = g->slabs + parity * size_t(g->world) * g->slab_bytes;
 	if (gathered_count4)
-		*gathered_count4 = g->counts;
+		*gathered_count4 = g->counts + parity * size_t(g->world) * 4;
 	return NVC_OK;
 }
 

@@ -65,7 +65,6 @@ def main():
     dist.all_gather_into_tensor(everyone, mine)
     check(lib.nvc_gather_connect(g.ctx, (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())), g.ctx, "nvc_gather_connect")
     ce_slabs, ce_counts = ctypes.c_void_p(), ctypes.c_void_p()
-    check(lib.nvc_gather_buffers(g.ctx, ctypes.byref(ce_slabs), ctypes.byref(ce_counts)), g.ctx, "nvc_gather_buffers")
     ce_host = torch.zeros(world * slab_bytes, dtype=torch.uint8).pin_memory()
     ce_counts_host = torch.zeros(world * 4, dtype=torch.int32).pin_memory()
 
@@ -91,6 +90,8 @@ def main():
             check(lib.nvc_gather_push(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), ctypes.c_void_p(g.dccb.data_ptr())), g.ctx, "nvc_gather_push")
             g.render_clusters(cd, late, cluster_backface=True)
             check(lib.nvc_gather_wait(g.ctx, stream), g.ctx, "nvc_gather_wait")
+            # the receive buffers are double-buffered by frame parity: ask for the latest frame's
+            check(lib.nvc_gather_buffers(g.ctx, ctypes.byref(ce_slabs), ctypes.byref(ce_counts)), g.ctx, "nvc_gather_buffers")
             torch.cuda.synchronize()
             # the copy-engine gather must have delivered exactly what NCCL delivered
             ce_view = _device_bytes(torch, ce_slabs.value, world * slab_bytes, dev)
@@ -102,7 +103,7 @@ def main():
             if not same_ce:
                 ok = False
                 print("rank", rank, "CE gather differs from NCCL gather, frame", frame, "late", late)
-            dist.barrier()  # nobody starts the next push before everyone has compared
+            # (no barrier here: the gather's own flow control keeps a fast rank from overwriting what a slow one still reads)
             slabs = gathered.cpu().numpy().reshape(world, slab_bytes)
             counts = gathered_counts.cpu().numpy().reshape(world, 4)
             cmds = shard.globalise_task_commands(list(slabs), list(counts), bases, bit_bases)
@@ -122,6 +123,29 @@ def main():
             if rank == 0 and int(total.item()) != int(o.ccb[0]):
                 ok = False
                 print("cluster count mismatch", int(total.item()), int(o.ccb[0]))
+    # ---- flow-control stress: 24 pushes back to back, no collective / barrier in between, ranks deliberately out of step
+    # (rank r stalls its stream before every r-th push); every frame's gathered slabs must carry that frame's pattern ----
+    pattern = torch.empty(slab_bytes // 4, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for f in range(24):
+        check(lib.nvc_gather_set_mode(g.ctx, (f // 3) % 2), g.ctx, "nvc_gather_set_mode")
+        if (f + rank) % (rank + 2) == 0:
+            torch.cuda._sleep(int(2e8))  # ~0.1 s stall on this rank only
+        pattern.fill_(1000 * f + rank)
+        cnt.fill_(slab_bytes // 20)
+        check(lib.nvc_gather_push(g.ctx, stream, ctypes.c_void_p(pattern.data_ptr()), ctypes.c_void_p(cnt.data_ptr())), g.ctx, "nvc_gather_push")
+        check(lib.nvc_gather_wait(g.ctx, stream), g.ctx, "nvc_gather_wait")
+        check(lib.nvc_gather_buffers(g.ctx, ctypes.byref(ce_slabs), ctypes.byref(ce_counts)), g.ctx, "nvc_gather_buffers")
+        view = _device_bytes(torch, ce_slabs.value, world * slab_bytes, dev).view(torch.int32).view(world, slab_bytes // 4)
+        want = (1000 * f + torch.arange(world, device=dev, dtype=torch.int32)).view(world, 1)
+        bad += (view != want).any().to(torch.int32)  # enqueued on the stream, evaluated after the wait kernel
+    torch.cuda.synchronize()
+    if int(bad.item()) != 0:
+        ok = False
+        print("rank", rank, "flow-control stress: %d frames carried stale or torn slabs" % int(bad.item()))
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checked its own gathered buffers
     dist.barrier()
