@@ -432,6 +432,16 @@ NVC_API int nvc_taskcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	if (s != NVC_OK)
 		return s;
 	uint32_t blocks = uint32_t(ctx->sm_count) * 4u;
+	if (ctx->cluster_filter)
+	{
+		const bool need_occlusion = late && cull->clusterOcclusionEnabled == 1;
+		p.filter = nvc::make_filter_consts(p.cull, p.hiz, need_occlusion);
+		if (p.filter.enabled && (!need_occlusion || p.filter.occ_ok))
+		{
+			p.use_filter = 1;
+			blocks = uint32_t(ctx->sm_count) * uint32_t(late ? ctx->cluster_filter_blocks_late : ctx->cluster_filter_blocks_early);
+		}
+	}
 	cudaError_t e = nvc::launch_taskcull(p, late != 0, payloads, emit_counts, blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_taskcull");
 }

@@ -140,6 +140,9 @@ struct ClusterParams
 	Scratch* scratch;
 	HiZDesc hiz;
 	uint32_t cluster_limit;
+	// task-shading submission mode (meshlet.task.glsl): per-command payloads + emit counts instead of cib / ccb
+	NvcMeshTaskPayload* payloads;
+	uint32_t* emit_counts;
 	FilterConsts filter; // valid when use_filter
 	uint32_t use_filter; // 1: clustercull_filter_kernel (conservative filter + exact fallback), 0: the exact kernel
 	float one, neg_one; // 1.0f / -1.0f as run-time values: see nvc_math2.cuh (keeps ptxas from contracting packed adds)

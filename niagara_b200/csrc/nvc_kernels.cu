@@ -1039,7 +1039,10 @@ struct FilterShared
 
 // TRACK: clusterOcclusionEnabled == 1 && postPass == 0 (the main passes of a frame) as a compile-time fact; the generic
 // instantiation reads the flags at run time.
-template <bool LATE, bool FP, bool TRACK>
+// TASKOUT: meshlet.task.glsl's submission mode — survivors go to their command's payload (slot from an atomic counter per
+// command, aggregated per warp; the reference's order inside a payload is unspecified too: atomicAdd(sharedCount), :137)
+// and the count to emit_counts[command] instead of cib / ccb.
+template <bool LATE, bool FP, bool TRACK, bool TASKOUT>
 __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
 {
 	__shared__ FilterShared sh;
@@ -1072,7 +1075,23 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		const bool out = active && visible && !skip;
 		const uint32_t omask = __ballot_sync(0xffffffffu, out);
 		const uint32_t n = __popc(omask);
-		if (n)
+		if (TASKOUT)
+		{
+			if (n) // warp-uniform: every lane takes part in the collectives, only emitting lanes touch memory
+			{
+				// lanes of one command share ONE atomic: leader = lowest emitting lane of the command's group
+				const uint32_t cmd = code & 0xffffffu;
+				const uint32_t group = __match_any_sync(0xffffffffu, out ? cmd : 0xffffffffu) & omask;
+				const uint32_t leader = group ? uint32_t(__ffs(int(group)) - 1) : 0u;
+				uint32_t base = 0;
+				if (out && lane_id() == leader)
+					base = atomicAdd(p.emit_counts + cmd, uint32_t(__popc(group)));
+				base = __shfl_sync(0xffffffffu, base, int(leader));
+				if (out)
+					p.payloads[cmd].clusterIndices[base + __popc(group & lanemask_lt())] = code; // :137-139
+			}
+		}
+		else if (n)
 		{
 			if (nst + n > uint32_t(kFStage))
 				flush_stage(p, stage, nst);
@@ -1132,6 +1151,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
 			const uint32_t c_late = __ldg(cp + 3);
 			c_mvo = __ldg(cp + 4);
+			if (TASKOUT)
+				p.emit_counts[cid] = 0u; // sharedCount = 0 (:71); ordered before this warp's atomics by the __syncwarp below
 			if (c_count)
 			{
 				const char* dp = reinterpret_cast<const char*>(p.draws + c_draw);
@@ -1287,18 +1308,21 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		return;
 	__threadfence();
 
-	uint32_t clusterCount = *reinterpret_cast<volatile uint32_t*>(&p.scratch->cluster_counter);
-	uint32_t count = min(clusterCount, p.cluster_limit);
-	if (tid == 0)
+	if (!TASKOUT)
 	{
-		p.cluster_count4[0] = clusterCount;
-		p.cluster_count4[1] = NVC_CLUSTER_TILE;
-		p.cluster_count4[2] = min((count + 255) / 256, NVC_MAX_DISPATCH_GROUPS);
-		p.cluster_count4[3] = 256 / NVC_CLUSTER_TILE;
+		uint32_t clusterCount = *reinterpret_cast<volatile uint32_t*>(&p.scratch->cluster_counter);
+		uint32_t count = min(clusterCount, p.cluster_limit);
+		if (tid == 0)
+		{
+			p.cluster_count4[0] = clusterCount;
+			p.cluster_count4[1] = NVC_CLUSTER_TILE;
+			p.cluster_count4[2] = min((count + 255) / 256, NVC_MAX_DISPATCH_GROUPS);
+			p.cluster_count4[3] = 256 / NVC_CLUSTER_TILE;
+		}
+		uint32_t boundary = (count + 255) & ~255u;
+		if (count + tid < boundary)
+			p.cluster_indices[count + tid] = ~0u;
 	}
-	uint32_t boundary = (count + 255) & ~255u;
-	if (count + tid < boundary)
-		p.cluster_indices[count + tid] = ~0u;
 	__syncthreads();
 	if (tid == 0)
 	{
@@ -1871,12 +1895,21 @@ cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t block
 	if (p.use_filter)
 	{
 		const bool track = p.cull.clusterOcclusionEnabled == 1 && p.cull.postPass == 0;
+		const bool taskout = p.payloads != nullptr;
 		void (*kernel)(ClusterParams);
-		if (late)
-			kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true> : clustercull_filter_kernel<true, true, false>)
-			                  : (track ? clustercull_filter_kernel<true, false, true> : clustercull_filter_kernel<true, false, false>);
+		if (taskout)
+		{
+			if (late)
+				kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true, true> : clustercull_filter_kernel<true, true, false, true>)
+				                  : (track ? clustercull_filter_kernel<true, false, true, true> : clustercull_filter_kernel<true, false, false, true>);
+			else
+				kernel = track ? clustercull_filter_kernel<false, false, true, true> : clustercull_filter_kernel<false, false, false, true>;
+		}
+		else if (late)
+			kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true, false> : clustercull_filter_kernel<true, true, false, false>)
+			                  : (track ? clustercull_filter_kernel<true, false, true, false> : clustercull_filter_kernel<true, false, false, false>);
 		else
-			kernel = track ? clustercull_filter_kernel<false, false, true> : clustercull_filter_kernel<false, false, false>;
+			kernel = track ? clustercull_filter_kernel<false, false, true, false> : clustercull_filter_kernel<false, false, false, false>;
 #if NVC_PDL && !defined(NVC_EMU)
 		return launch_pdl(kernel, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
 #else
@@ -1900,6 +1933,13 @@ cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t block
 
 cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream)
 {
+	if (p.use_filter)
+	{
+		ClusterParams q = p; // filtered kernel in task-shading output mode (flattened items, per-command records)
+		q.payloads = payloads;
+		q.emit_counts = emit_counts;
+		return launch_clustercull(q, late, blocks, stream);
+	}
 	if (late)
 		taskcull_kernel<true><<<blocks, kClusterBlock, 0, stream>>>(p, payloads, emit_counts);
 	else
@@ -1937,9 +1977,9 @@ cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_l
 
 cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
 {
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false, false>, kClusterBlock, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false, false, false>, kClusterBlock, 0);
 	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false, false>, kClusterBlock, 0);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false, false, false>, kClusterBlock, 0);
 	return e;
 }
 

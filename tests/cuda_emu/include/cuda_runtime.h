@@ -172,6 +172,16 @@ inline uint32_t __reduce_or_sync(uint32_t mask, uint32_t v)
 			r |= all[i];
 	return r;
 }
+inline uint32_t __match_any_sync(uint32_t mask, uint32_t v)
+{
+	uint32_t l = emu::lane();
+	const uint32_t* all = emu::warp_gather(mask, v);
+	uint32_t r = 0;
+	for (int i = 0; i < 32; ++i)
+		if (((mask >> i) & 1u) && all[i] == all[l])
+			r |= 1u << i;
+	return r;
+}
 inline uint32_t __activemask() { return 0xffffffffu; }
 
 // ---- memory ----------------------------------------------------------------------------------------------------------

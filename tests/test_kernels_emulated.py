@@ -177,7 +177,7 @@ def test_taskcull_payloads(golden_dir):
             ot, et = o.read_task_commands(n), e.read_task_commands(n)
 
             def table(cmds, payloads, counts):
-                return {tuple(cmds[i].tolist()): tuple(int(v) >> 24 for v in payloads[i][: counts[i]]) for i in range(n) if cmds["taskCount"][i]}
+                return {tuple(cmds[i].tolist()): tuple(sorted(int(v) >> 24 for v in payloads[i][: counts[i]])) for i in range(n) if cmds["taskCount"][i]}
 
             assert table(ot, op, oe) == table(et, ep, ee)
             assert np.array_equal(o.mvb, e.mvb)
