@@ -157,16 +157,16 @@ inline FilterConsts make_filter_consts(const NvcCullData& cd, const HiZDesc& hiz
 struct alignas(16) CmdRecord
 {
 	float4 row0, row1, row2; // (M_i0, M_i1, M_i2, T_i)
-	float4 aux;              // s, Em, Et, kC
-	uint4 ids;               // taskOffset, meshletVisibilityOffset, drawId, flags (bit 0 lateDrawVisibility, bit 1 exact-only)
+	float4 aux;              // s, Em, Et, flags as bits (bit 0 lateDrawVisibility, bit 1 exact-only)
+	uint4 ids;               // taskOffset, meshletVisibilityOffset, the command's 64 visibility bits (lo, hi; 0 when the pass does not track them)
 };
 static_assert(sizeof(CmdRecord) == 80, "five 16-byte shared-memory loads");
 
 constexpr uint32_t kRecLate = 1u, kRecExactOnly = 2u;
 
 // Built once per task command by the lane that owns it.  view = CullData.view (column-major).
-__device__ __forceinline__ void build_record(const FilterConsts& fc, const float* __restrict__ view, float znear, float4 d0, float4 d1, uint32_t taskOffset, uint32_t mvo,
-    uint32_t drawId, uint32_t lateVis, CmdRecord& rec)
+__device__ __forceinline__ void build_record(const FilterConsts& fc, const float* __restrict__ view, float4 d0, float4 d1, uint32_t taskOffset, uint32_t mvo, uint32_t bits_lo,
+    uint32_t bits_hi, uint32_t lateVis, CmdRecord& rec)
 {
 	const float x = d1.x, y = d1.y, z = d1.z, w = d1.w, s = d0.w;
 	const float xx = x * x, yy = y * y, zz = z * z, ww = w * w;
@@ -201,9 +201,8 @@ __device__ __forceinline__ void build_record(const FilterConsts& fc, const float
 	rec.aux.x = s;
 	rec.aux.y = 42.f * u * s * fc.vrE;
 	rec.aux.z = nvf_fma(12.f * u, tmax, fc.fr.w) + 7.8886091e-31f /* 2^-100 */;
-	rec.aux.w = 8300.f * s;
-	rec.ids = make_uint4(taskOffset, mvo, drawId, (lateVis == 1u ? kRecLate : 0u) | (sane ? 0u : kRecExactOnly));
-	(void)znear;
+	rec.aux.w = __uint_as_float((lateVis == 1u ? kRecLate : 0u) | (sane ? 0u : kRecExactOnly));
+	rec.ids = make_uint4(taskOffset, mvo, bits_lo, bits_hi);
 }
 
 // Result of the filter for one meshlet
@@ -258,7 +257,7 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 		const float len = nvf_sqrt(nvf_fma(cx, cx, nvf_fma(cy, cy, cz * cz)));
 		const float rhs = aux.x * nvf_fma(ac, len, 127.f * r);
 		const float tc = rhs - dotv; // > 0: not back-facing
-		const float mC = aux.w * E;
+		const float mC = (8300.f * aux.x) * E; // 64 E x 127 s (+2 %)
 		pass = pass && tc > mC;
 		fail = fail || tc < -mC;
 	}

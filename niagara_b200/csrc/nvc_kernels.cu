@@ -1140,46 +1140,43 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		if (batch >= nbatch)
 			break;
 
-		// ---- per command: load, transform record ----
+		// ---- per command: load, visibility window, transform record ----
 		const uint32_t cid = batch * 32u + lane;
-		uint32_t c_count = 0, c_mvo = 0;
+		uint32_t c_count = 0;
+		// early pass with tracking: flatten only the SET visibility bits of every command (see clustercull_kernel)
+		const bool alive_flatten = !LATE && track;
+		uint32_t amask_lo = 0, amask_hi = 0;
 		__syncwarp(); // the previous batch's readers of `recs` are done
 		if (cid < ncmd)
 		{
 			const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + cid);
 			const uint32_t c_draw = __ldg(cp + 0), c_task = __ldg(cp + 1);
 			c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
-			const uint32_t c_late = __ldg(cp + 3);
-			c_mvo = __ldg(cp + 4);
+			const uint32_t c_late = __ldg(cp + 3), c_mvo = __ldg(cp + 4);
 			if (TASKOUT)
 				p.emit_counts[cid] = 0u; // sharedCount = 0 (:71); ordered before this warp's atomics by the __syncwarp below
 			if (c_count)
 			{
+				if (track)
+				{
+					// the command's 64-bit window of visibility bits, read ONCE per command: bit mgi belongs to meshlet mgi.  Late
+					// pass: other warps flip NEIGHBOUR bits of these words concurrently; a lane only ever looks at its own bit,
+					// which nobody else touches during the pass (L2 load: lines of an earlier launch are never stale there).
+					const uint32_t sft = c_mvo & 31u;
+					const uint32_t nwords = (sft + c_count + 31u) >> 5; // 1..3 words hold the command's bits
+					const uint32_t* wp = p.meshlet_visibility + (c_mvo >> 5);
+					uint32_t w0 = __ldcg(wp), w1 = nwords > 1 ? __ldcg(wp + 1) : 0u, w2 = nwords > 2 ? __ldcg(wp + 2) : 0u;
+					amask_lo = __funnelshift_r(w0, w1, sft);
+					amask_hi = __funnelshift_r(w1, w2, sft);
+					amask_lo &= c_count >= 32 ? 0xffffffffu : ((1u << c_count) - 1u);
+					amask_hi &= c_count >= 64 ? 0xffffffffu : (c_count > 32 ? ((1u << (c_count - 32)) - 1u) : 0u);
+				}
 				const char* dp = reinterpret_cast<const char*>(p.draws + c_draw);
 				const float4 d0 = ldg_f4(dp), d1 = ldg_f4(dp + 16);
-				build_record(fc, cd.view, cd.znear, d0, d1, c_task, c_mvo, c_draw, c_late, recs[lane]);
+				build_record(fc, cd.view, d0, d1, c_task, c_mvo, amask_lo, amask_hi, c_late, recs[lane]);
 			}
 		}
-
-		// early pass with tracking: flatten only the SET visibility bits of every command (see clustercull_kernel)
-		const bool alive_flatten = !LATE && track;
-		uint32_t amask_lo = 0, amask_hi = 0;
-		uint32_t eff_count = c_count;
-		if (alive_flatten)
-		{
-			if (c_count)
-			{
-				const uint32_t sft = c_mvo & 31u;
-				const uint32_t nwords = (sft + c_count + 31u) >> 5;
-				const uint32_t* wp = p.meshlet_visibility + (c_mvo >> 5);
-				uint32_t w0 = __ldg(wp), w1 = nwords > 1 ? __ldg(wp + 1) : 0u, w2 = nwords > 2 ? __ldg(wp + 2) : 0u;
-				amask_lo = __funnelshift_r(w0, w1, sft);
-				amask_hi = __funnelshift_r(w1, w2, sft);
-				amask_lo &= c_count >= 32 ? 0xffffffffu : ((1u << c_count) - 1u);
-				amask_hi &= c_count >= 64 ? 0xffffffffu : (c_count > 32 ? ((1u << (c_count - 32)) - 1u) : 0u);
-			}
-			eff_count = __popc(amask_lo) + __popc(amask_hi);
-		}
+		const uint32_t eff_count = alive_flatten ? uint32_t(__popc(amask_lo) + __popc(amask_hi)) : c_count;
 
 		uint32_t incl = eff_count;
 #pragma unroll
@@ -1228,42 +1225,38 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			}
 			j &= 31u;
 			uint32_t mgi = uniform ? item - j * count0 : item - __shfl_sync(0xffffffffu, excl, j);
-			if (alive_flatten)
-			{
-				const uint32_t mlo = __shfl_sync(0xffffffffu, amask_lo, j), mhi = __shfl_sync(0xffffffffu, amask_hi, j);
-				mgi = active ? select_bit64(mlo, mhi, mgi) : 0u;
-			}
-			mgi &= 63u;
 
 			// ---- the command's record, the meshlet, its visibility bit ----
-			const CmdRecord& rec = recs[active ? j : (lane & 0u)];
+			const CmdRecord& rec = recs[active ? j : 0u];
 			const uint4 ids = rec.ids;
+			if (alive_flatten)
+				mgi = active ? select_bit64(ids.z, ids.w, mgi) : 0u; // the rank-th SET bit of the window is the meshlet's lane index
+			mgi &= 63u;
 			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
 			uint2 b0 = make_uint2(0u, 0u);
-			uint32_t b1 = 0u, word = 0u;
+			uint32_t b1 = 0u;
 			if (active)
 			{
 				const char* mp = reinterpret_cast<const char*>(p.meshlets + mi);
 				b0 = __ldg(reinterpret_cast<const uint2*>(mp));
 				b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8));
-				if (track)
-					word = alive_flatten ? 0xffffffffu : (LATE ? __ldcg(p.meshlet_visibility + (mvi >> 5)) : __ldg(p.meshlet_visibility + (mvi >> 5)));
 			}
 			const float4 row0 = rec.row0, row1 = rec.row1, row2 = rec.row2, aux = rec.aux;
+			const uint32_t flags = __float_as_uint(aux.w);
 
 			bool oldbit = false, skip = false, alive = active;
 			if (track)
 			{
-				const bool bit = (word >> (mvi & 31u)) & 1u;
+				const bool bit = (((uint64_t(ids.w) << 32) | ids.z) >> mgi) & 1ull; // mgi < 64
 				oldbit = bit;
 				if (!LATE)
 					alive = alive && bit; // :91-92
 				else
-					skip = (ids.w & kRecLate) != 0u && bit; // :97-98
+					skip = (flags & kRecLate) != 0u && bit; // :97-98
 			}
 
 			const FilterResult fr = filter_meshlet<LATE, FP>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
-			const bool decided = !alive || (fr.decided && (ids.w & kRecExactOnly) == 0u);
+			const bool decided = !alive || (fr.decided && (flags & kRecExactOnly) == 0u);
 			const bool visible = alive && fr.visible;
 
 			// ---- fast exit: nothing undecided, no visibility bit changes, nothing to append (the steady-state chunk) ----
@@ -1277,8 +1270,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			const uint32_t umask = __ballot_sync(0xffffffffu, !decided);
 			if (umask)
 			{
-				if (!decided)
-					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(ids.z, mi, mvi, code | ((ids.w & kRecLate) << 31));
+				if (!decided) // the exact path needs the draw: re-read it from the command (rare)
+					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(__ldg(&p.task_commands[code & 0xffffffu].drawId), mi, mvi, code | ((flags & kRecLate) << 31));
 				nq += __popc(umask);
 				stat_undecided += __popc(umask);
 			}

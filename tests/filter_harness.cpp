@@ -259,8 +259,8 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 				d0 = make_float4(pos[0], pos[1], pos[2], float(sscale));
 			}
 			CmdRecord rec;
-			build_record(fc, cd.view, cd.znear, d0, d1, 0, 0, 0, 0, rec);
-			const bool exact_only = (rec.ids.w & kRecExactOnly) != 0 || fc.enabled == 0 || fc.occ_ok == 0; // (the host launches the exact kernel then)
+			build_record(fc, cd.view, d0, d1, 0, 0, 0, 0, 0, rec);
+			const bool exact_only = (__float_as_uint(rec.aux.w) & kRecExactOnly) != 0 || fc.enabled == 0 || fc.occ_ok == 0; // (the host launches the exact kernel then)
 
 			for (uint32_t k = 0; k < per_draw && i < frame_items; ++k, ++i)
 			{
