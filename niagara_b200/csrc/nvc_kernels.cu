@@ -173,7 +173,14 @@ __device__ __forceinline__ void hiz_stage_wait(uint64_t* bar)
 // ------------------------------------------------------------------------------------------------------
 
 constexpr int kDrawBlock = 256;
-constexpr uint32_t kDrawStage = 512; // commands staged per block before the coalesced write-out
+// Draws per thread.  One draw per thread leaves every CTA with ~1.6 us of streaming between ~1.5 us of fixed latencies (the
+// dependent mesh-head load, the block's atomicAdd round trip, the completion ticket, CTA turnover); with DPT draws per thread
+// all DPT x 3 draw loads are in flight together and the fixed part is paid once per DPT x 256 draws.
+#ifndef NVC_DRAW_PER_THREAD
+#define NVC_DRAW_PER_THREAD 2
+#endif
+constexpr int kDPT = NVC_DRAW_PER_THREAD;
+constexpr uint32_t kDrawStage = 512 * kDPT > 1536 ? 1536 : 512 * kDPT; // commands staged per block before the coalesced write-out (static shared memory <= 48 KB)
 
 template <bool LATE, bool TASK>
 __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
@@ -182,52 +189,91 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
 	__shared__ uint32_t s_block_base, s_block_total;
 	__shared__ uint32_t s_is_last;
-	__shared__ uint32_t s_stage[kDrawStage * 6];
+	__shared__ uint32_t s_stage[kDrawStage * (TASK ? 5 : 6)];
 
 	const NvcCullData& cd = p.cull;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
-	const uint32_t di = blockIdx.x * kDrawBlock + tid;
+	const bool packed = p.mesh_heads != nullptr;
 
-	bool emit = false;
-	uint32_t units = 0; // commands this thread appends: taskGroups (TASK) or 1
-	uint32_t dv = 0;
-	uint32_t meshIndex = 0, lodIndex = 0, mvOffset = 0;
-	uint32_t meshletOffset = 0, meshletCount = 0; // selected LOD's meshlet range (TASK)
+	// per-draw state of this thread's kDPT draws (draw k of the thread: block base + k * 256 + tid, so that every load
+	// instruction of a warp still covers 32 consecutive MeshDraws)
+	uint32_t di[kDPT];
+	float4 d0[kDPT], d1[kDPT];
+	uint4 d2[kDPT];
+	bool reached[kDPT];
+	uint32_t dv[kDPT];
+	bool emit[kDPT];
+	uint32_t units[kDPT]; // commands this draw appends: taskGroups (TASK) or 1
+	uint32_t lodIndex[kDPT], meshletOffset[kDPT], meshletCount[kDPT];
 
-	if (di < cd.drawCount)
+	// ---- phase 1: all MeshDraw loads ----
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
 	{
-		const char* dp = reinterpret_cast<const char*>(p.draws + di);
-		float4 d0 = ldg_f4(dp);      // position.xyz, scale
-		float4 d1 = ldg_f4(dp + 16); // orientation
-		uint4 d2 = ldg_u4(dp + 32);  // meshIndex, meshletVisibilityOffset, postPass, materialIndex
-		meshIndex = d2.x;
-		mvOffset = d2.y;
-
-		bool reached = d2.z == cd.postPass; // :63
-		if (reached)
+		di[k] = (blockIdx.x * kDPT + k) * kDrawBlock + tid;
+		d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
+		d2[k] = make_uint4(0u, 0u, 0u, 0u);
+		reached[k] = false;
+		if (di[k] < cd.drawCount)
 		{
-			dv = p.draw_visibility[di];
-			if (!LATE && dv == 0) // :67
-				reached = false;
+			const char* dp = reinterpret_cast<const char*>(p.draws + di[k]);
+			d0[k] = ldg_f4(dp);      // position.xyz, scale
+			d1[k] = ldg_f4(dp + 16); // orientation
+			d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
+			reached[k] = d2[k].z == cd.postPass; // :63
 		}
-
-		if (reached)
+	}
+	// ---- phase 2: draw visibility ----
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		dv[k] = 0;
+		if (reached[k])
 		{
-			const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
-			const bool packed = p.mesh_heads != nullptr;
+			dv[k] = p.draw_visibility[di[k]];
+			if (!LATE && dv[k] == 0) // :67
+				reached[k] = false;
+		}
+	}
+	// ---- phase 3: mesh heads (dependent on meshIndex) ----
+	float4 m0[kDPT];
+	uint4 h1[kDPT];
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		m0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		h1[k] = make_uint4(0u, 0u, 0u, 0u);
+		if (reached[k])
+		{
+			const char* mp = reinterpret_cast<const char*>(p.meshes + d2[k].x);
 			// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
-			const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + meshIndex) : mp;
-			float4 m0 = ldg_f4(hp); // center.xyz, radius
-			uint4 h1 = make_uint4(0u, 0u, 0u, 0u);
+			const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + d2[k].x) : mp;
+			m0[k] = ldg_f4(hp); // center.xyz, radius
 			if (packed)
-				h1 = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
-
-			f3 mc = { m0.x, m0.y, m0.z };
-			f3 rc = rotate_quat(mc, d1);
-			f3 center = { __fadd_rn(__fmul_rn(rc.x, d0.w), d0.x), __fadd_rn(__fmul_rn(rc.y, d0.w), d0.y), __fadd_rn(__fmul_rn(rc.z, d0.w), d0.z) };
+				h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
+		}
+	}
+	// ---- phase 4: the tests ----
+	uint32_t thread_units = 0;
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		emit[k] = false;
+		units[k] = 0;
+		lodIndex[k] = 0;
+		meshletOffset[k] = 0;
+		meshletCount[k] = 0;
+		if (reached[k])
+		{
+			const uint32_t meshIndex = d2[k].x;
+			const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
+			f3 mc = { m0[k].x, m0[k].y, m0[k].z };
+			f3 rc = rotate_quat(mc, d1[k]);
+			f3 center = { __fadd_rn(__fmul_rn(rc.x, d0[k].w), d0[k].x), __fadd_rn(__fmul_rn(rc.y, d0[k].w), d0[k].y), __fadd_rn(__fmul_rn(rc.z, d0[k].w), d0[k].z) };
 			center = transform_point(cd.view, center);
-			float radius = __fmul_rn(m0.w, d0.w);
+			float radius = __fmul_rn(m0[k].w, d0[k].w);
 
 			bool visible = frustum_visible(cd, center, radius);
 			visible = visible || cd.cullingEnabled == 0; // :85
@@ -236,41 +282,42 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 				visible = occlusion_visible<false>(cd, p.hiz, nullptr, true, center, radius);
 
 			// :108  (TASK_CULL == 1, config.h:8)
-			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv == 0 || cd.postPass != 0))
+			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv[k] == 0 || cd.postPass != 0))
 			{
 				if (cd.lodEnabled == 1) // :112-120
 				{
 					float d = __fsub_rn(length3(center), radius);
 					float distance = d > 0.f ? d : 0.f;
-					float threshold = __fdiv_rn(__fmul_rn(distance, cd.lodTarget), d0.w);
-					uint32_t lodCount = packed ? h1.x : __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
+					float threshold = __fdiv_rn(__fmul_rn(distance, cd.lodTarget), d0[k].w);
+					uint32_t lodCount = packed ? h1[k].x : __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
 					lodCount = min(lodCount, NVC_MAX_LODS);
 					const float* errors = packed ? p.mesh_errors + size_t(meshIndex) * NVC_MAX_LODS : nullptr;
 					for (uint32_t i = 1; i < lodCount; ++i)
 					{
 						float err = packed ? __ldg(errors + i) : __ldg(reinterpret_cast<const float*>(mp + 48 + i * 20 + 16));
 						if (err < threshold)
-							lodIndex = i;
+							lodIndex[k] = i;
 					}
 				}
-				emit = true;
+				emit[k] = true;
 				if (TASK)
 				{
-					meshletCount = (packed && lodIndex == 0) ? h1.z : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 12));
-					meshletOffset = (packed && lodIndex == 0) ? h1.y : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20 + 8));
-					units = (meshletCount + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
+					meshletCount[k] = (packed && lodIndex[k] == 0) ? h1[k].z : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex[k] * 20 + 12));
+					meshletOffset[k] = (packed && lodIndex[k] == 0) ? h1[k].y : __ldg(reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex[k] * 20 + 8));
+					units[k] = (meshletCount[k] + NVC_TASK_WGSIZE - 1) / NVC_TASK_WGSIZE; // :122
 				}
 				else
-					units = 1;
+					units[k] = 1;
 			}
 
 			if (LATE)
-				p.draw_visibility[di] = visible ? 1u : 0u; // :154-155
+				p.draw_visibility[di[k]] = visible ? 1u : 0u; // :154-155
 		}
+		thread_units += units[k];
 	}
 
-	// ---- block-wide exclusive scan of `units`, ONE global atomicAdd per block (the GLSL does one per thread) ----
-	uint32_t incl = units;
+	// ---- block-wide exclusive scan of the threads' command counts, ONE global atomicAdd per block (the GLSL: one per thread) ----
+	uint32_t incl = thread_units;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
@@ -308,39 +355,44 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	// exceed the staging capacity or run into TASK_WGLIMIT take the direct per-thread path. ----
 	constexpr uint32_t kWords = TASK ? 5u : 6u;
 	const uint32_t block_total = s_block_total;
-	const uint32_t local = s_warp_total[warp] + (incl - units);
+	uint32_t local = s_warp_total[warp] + (incl - thread_units);
 	const bool staged = block_total <= kDrawStage && (!TASK || uint64_t(s_block_base) + block_total <= p.task_wglimit);
-	if (emit)
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
 	{
-		const uint32_t dci = s_block_base + local;
-		const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
-		const uint32_t* lp = reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex * 20);
-		if (TASK)
+		if (emit[k])
 		{
-			// :129 drop on overflow; the counter has already advanced
-			if (staged || uint64_t(dci) + units <= p.task_wglimit)
+			const uint32_t dci = s_block_base + local;
+			const char* mp = reinterpret_cast<const char*>(p.meshes + d2[k].x);
+			const uint32_t* lp = reinterpret_cast<const uint32_t*>(mp + 48 + lodIndex[k] * 20);
+			if (TASK)
 			{
-				uint32_t* out = staged ? s_stage + local * 5u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshTaskCommand*>(p.commands) + dci);
-				for (uint32_t i = 0; i < units; ++i, out += 5)
+				// :129 drop on overflow; the counter has already advanced
+				if (staged || uint64_t(dci) + units[k] <= p.task_wglimit)
 				{
-					out[0] = di;                                                          // drawId
-					out[1] = meshletOffset + i * NVC_TASK_WGSIZE;                         // taskOffset
-					out[2] = min(NVC_TASK_WGSIZE, meshletCount - i * NVC_TASK_WGSIZE);    // taskCount
-					out[3] = dv;                                                          // lateDrawVisibility
-					out[4] = mvOffset + i * NVC_TASK_WGSIZE;                              // meshletVisibilityOffset
+					uint32_t* out = staged ? s_stage + local * 5u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshTaskCommand*>(p.commands) + dci);
+					for (uint32_t i = 0; i < units[k]; ++i, out += 5)
+					{
+						out[0] = di[k];                                                             // drawId
+						out[1] = meshletOffset[k] + i * NVC_TASK_WGSIZE;                            // taskOffset
+						out[2] = min(NVC_TASK_WGSIZE, meshletCount[k] - i * NVC_TASK_WGSIZE);       // taskCount
+						out[3] = dv[k];                                                             // lateDrawVisibility
+						out[4] = d2[k].y + i * NVC_TASK_WGSIZE;                                     // meshletVisibilityOffset
+					}
 				}
 			}
+			else
+			{
+				uint32_t* out = staged ? s_stage + local * 6u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshDrawCommand*>(p.commands) + dci);
+				out[0] = di[k];                                                    // drawId
+				out[1] = __ldg(lp + 1);                                            // indexCount
+				out[2] = 1;                                                        // instanceCount
+				out[3] = __ldg(lp + 0);                                            // firstIndex
+				out[4] = __ldg(reinterpret_cast<const uint32_t*>(mp + 16));        // vertexOffset
+				out[5] = 0;                                                        // firstInstance
+			}
 		}
-		else
-		{
-			uint32_t* out = staged ? s_stage + local * 6u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshDrawCommand*>(p.commands) + dci);
-			out[0] = di;                                                       // drawId
-			out[1] = __ldg(lp + 1);                                            // indexCount
-			out[2] = 1;                                                        // instanceCount
-			out[3] = __ldg(lp + 0);                                            // firstIndex
-			out[4] = __ldg(reinterpret_cast<const uint32_t*>(mp + 16));        // vertexOffset
-			out[5] = 0;                                                        // firstInstance
-		}
+		local += units[k];
 	}
 	if (staged && block_total)
 	{
@@ -1854,7 +1906,7 @@ cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cuda
 
 cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
 {
-	uint32_t blocks = (p.cull.drawCount + kDrawBlock - 1) / kDrawBlock;
+	uint32_t blocks = (p.cull.drawCount + kDrawBlock * kDPT - 1) / (kDrawBlock * kDPT);
 	if (blocks == 0)
 		blocks = 1;
 #if NVC_PDL && !defined(NVC_EMU)

@@ -13,7 +13,7 @@ echo "== pending gpu tests"; timeout 600 python -m pytest tests/pending/gpu_end_
 X= q > $O/bench_filter.json; summ filter < $O/bench_filter.json; X=--no-extras
 NVC_PREPARE_HIZ=0 q > $O/bench_filter_nofp.json; summ filter_nofp < $O/bench_filter_nofp.json
 NVC_CLUSTER_FILTER=0 q > $O/bench_exact.json; summ exact < $O/bench_exact.json
-for v in fb3 fb5 fb6 pdl; do NVC_LIB_PATH=$PWD/niagara_b200/variant_$v.so q > $O/bench_$v.json; summ $v < $O/bench_$v.json; done
+for v in fb3 fb5 fb6 pdl dpt1 dpt4; do NVC_LIB_PATH=$PWD/niagara_b200/variant_$v.so q > $O/bench_$v.json; summ $v < $O/bench_$v.json; done
 NVC_CLUSTER_FILTER=0 NVC_LIB_PATH=$PWD/niagara_b200/variant_smem_items.so q > $O/bench_exact_smem_items.json; summ exact_smem_items < $O/bench_exact_smem_items.json
 NVC_CLUSTER_FILTER=0 NVC_LIB_PATH=$PWD/niagara_b200/variant_pdl.so q > $O/bench_exact_pdl.json; summ exact_pdl < $O/bench_exact_pdl.json
 echo "== pytest -m gpu with the PDL build"; NVC_LIB_PATH=$PWD/niagara_b200/variant_pdl.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2 | tee $O/pytest_gpu_pdl.txt
