@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the moving-camera and task-shading regions")
-    ap.add_argument("--gather", default="ce", choices=["ce", "sm", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), nccl = ncclAllGather, none = skip")
+    ap.add_argument("--gather", default="ce", choices=["ce", "sm", "mc", "fused", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), mc = one NVSwitch-multicast store kernel per rank (symmetric memory), fused = the late drawcull itself stores its commands through the multicast mapping, nccl = ncclAllGather, none = skip")
     return ap.parse_args()
 
 
@@ -357,15 +357,51 @@ def main():
 
     # ---- multi-GPU: all-gather of the per-rank visible command slabs + counters ----
     gather = args.gather if world > 1 else "none"
-    sm_push = gather == "sm"
-    if sm_push:
-        gather = "ce"  # same protocol (nvc_gather_*), the slab is pushed by a small kernel instead of the copy engines
+    transport = gather  # what is reported; ce / sm / mc / fused all speak the nvc_gather_* protocol below
     slab_cmds = (D * max(1, (args.meshlets_per_draw + 63) // 64) + 63) // 64 * 64 if args.workload == "C4" else 0
     if not slab_cmds:
-        gather = "none"
+        gather = transport = "none"
     slab_bytes = slab_cmds * layout.MESHTASKCOMMAND_DTYPE.itemsize
     gathered = gathered_counts = None
-    if gather == "nccl":
+    gather_note = None
+    symm_keep = None
+    if gather in ("mc", "fused"):
+        # symmetric memory with an NVSwitch multicast mapping (torch owns the allocation and the handle exchange)
+        err = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            region = int(lib.nvc_gather_region_bytes(slab_bytes, world))
+            t = symm_mem.empty(region, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            mc_ptr = int(hdl.multicast_ptr) if hasattr(hdl, "multicast_ptr") else 0
+            if not mc_ptr:
+                raise RuntimeError("no multicast mapping on this system")
+            peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            check(lib.nvc_gather_attach(path.ctx, slab_bytes, rank, world, peers, ctypes.c_void_p(mc_ptr)), path.ctx, "nvc_gather_attach")
+            check(lib.nvc_gather_set_mode(path.ctx, 3 if gather == "fused" else 2), path.ctx, "nvc_gather_set_mode")
+            symm_keep = (t, hdl)
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same decision
+        if not int(ok.item()):
+            # no symmetric memory / multicast here: the copy-engine transport takes over on every rank
+            gather_note = "%s unavailable (%s): fell back to the copy-engine transport" % (gather, str(err)[:120] if err else "another rank failed")
+            gather = transport = "ce"
+        dist.barrier()
+    sm_push = gather == "sm"
+    if gather in ("ce", "sm"):
+        ticket = (ctypes.c_ubyte * 192)()
+        check(lib.nvc_gather_create(path.ctx, slab_bytes, rank, world, ticket), path.ctx, "nvc_gather_create")
+        mine = torch.tensor(list(ticket), dtype=torch.uint8, device=dev)
+        everyone = torch.zeros(world * 192, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine)
+        tickets = (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())
+        check(lib.nvc_gather_connect(path.ctx, tickets), path.ctx, "nvc_gather_connect")
+        check(lib.nvc_gather_set_mode(path.ctx, int(sm_push)), path.ctx, "nvc_gather_set_mode")
+        dist.barrier()
+    elif gather == "nccl":
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = (ctypes.c_ubyte * 128)()
@@ -377,24 +413,15 @@ def main():
         check(lib.nvc_nccl_init(path.ctx, uid_host, rank, world), path.ctx, "nvc_nccl_init")
         gathered = torch.zeros(world * slab_bytes, dtype=torch.uint8, device=dev)
         gathered_counts = torch.zeros(world * 4, dtype=torch.int32, device=dev)
-        comm_stream = torch.cuda.Stream(dev)
-    elif gather == "ce":
-        ticket = (ctypes.c_ubyte * 192)()
-        check(lib.nvc_gather_create(path.ctx, slab_bytes, rank, world, ticket), path.ctx, "nvc_gather_create")
-        mine = torch.tensor(list(ticket), dtype=torch.uint8, device=dev)
-        everyone = torch.zeros(world * 192, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(everyone, mine)
-        tickets = (ctypes.c_ubyte * (192 * world))(*everyone.cpu().tolist())
-        check(lib.nvc_gather_connect(path.ctx, tickets), path.ctx, "nvc_gather_connect")
-        check(lib.nvc_gather_set_mode(path.ctx, int(sm_push)), path.ctx, "nvc_gather_set_mode")
-        dist.barrier()
+        comm_stream = torch.cuda.Stream(dev, priority=-1)  # high priority: its CTAs are placed before the persistent cluster pass's
+    peer = gather in ("ce", "sm", "mc", "fused")  # the nvc_gather_* protocol
 
     # With the copy-engine gather the late commands go to their own buffer (the C ABI takes the command buffer per
     # call): the slab pushed after drawcull(late) of frame k then stays untouched until drawcull(late) of frame k+1, so
     # the exchange has the late cluster pass AND the next frame's early passes to complete — frames in flight like the
     # reference's MAX_FRAMES = 2 (config.h:31).  The wait sits right before the slab is overwritten (and after the loop).
     dcb_early = path.dcb
-    dcb_late = torch.zeros_like(path.dcb) if gather == "ce" else path.dcb
+    dcb_late = torch.zeros_like(path.dcb) if peer else path.dcb
     pending = {"push": False}
 
     def frame(cull, events=None, task=None):
@@ -419,20 +446,26 @@ def main():
         path.pyramid(depth)
         mark(3)
         path.dcb = dcb_late
-        if gather == "ce" and pending["push"]:
+        if peer and pending["push"]:
             # the previous frame's slab (and every peer's copy of it) must have landed before it is overwritten
             check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
             pending["push"] = False
+            launches["n"] += 2
+        if gather == "fused":
+            # fused compute + collective: the late drawcull stores its commands through the NVSwitch multicast mapping as it
+            # writes them (this call takes the frame tag and waits for the peers' acknowledgements of that parity's buffers)
+            check(lib.nvc_gather_fuse_next_drawcull(path.ctx, path._stream()), path.ctx, "nvc_gather_fuse_next_drawcull")
             launches["n"] += 1
         path.cull(cull, late=True)
         mark(4)
         launches["n"] += 5 + (1 if has_fp else 0)
-        if gather == "ce":
-            # the late command slab is final once drawcull(late) is done: push it to every peer with the copy engines
-            # while the late cluster pass (and the next frame's early passes) run on the SMs
+        if peer:
+            # the late command slab is final once drawcull(late) is done: ce = push it to every peer with the copy engines,
+            # mc = one multicast store kernel, fused = only counters + flags are left; all of it overlaps the late cluster
+            # pass (and the next frame's early passes)
             check(lib.nvc_gather_push(path.ctx, path._stream(), ctypes.c_void_p(path.dcb.data_ptr()), ctypes.c_void_p(path.dccb.data_ptr())), path.ctx, "nvc_gather_push")
             pending["push"] = True
-            launches["n"] += 2 if sm_push else 1
+            launches["n"] += 1 if gather == "ce" else 2
         elif gather == "nccl":
             done = torch.cuda.Event()
             done.record()
@@ -449,7 +482,7 @@ def main():
 
     def drain():
         """end of a timed region: the last frame's exchange must be complete on every rank"""
-        if gather == "ce" and pending["push"]:
+        if peer and pending["push"]:
             check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
             pending["push"] = False
 
@@ -544,7 +577,7 @@ def main():
         frame(cd)
         drain()
         torch.cuda.synchronize()
-        if gather == "ce":
+        if peer:
             slabs_p, counts_p = ctypes.c_void_p(), ctypes.POINTER(ctypes.c_uint32)()
             check(lib.nvc_gather_buffers(path.ctx, ctypes.byref(slabs_p), ctypes.byref(counts_p)), path.ctx, "nvc_gather_buffers")
 
@@ -773,7 +806,7 @@ def main():
             "data": "synthetic",
             "config": {
                 "workload": workload_label(args) + "; per GPU",
-                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid%s, late drawcull+tasksubmit, late clustercull+clustersubmit (%d launches)%s" % (" + footprint image" if has_fp else "", 6 if has_fp else 5, {"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), every frame, pipelined one frame deep: the exchange of frame k must complete before drawcull(late) of frame k+1 overwrites the slab, and the last one before the clock stops", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a side stream", "none": ""}[gather]),
+                "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid%s, late drawcull+tasksubmit, late clustercull+clustersubmit (%d launches)%s" % (" + footprint image" if has_fp else "", 6 if has_fp else 5, {"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), every frame, pipelined one frame deep: the exchange of frame k must complete before drawcull(late) of frame k+1 overwrites the slab, and the last one before the clock stops", "sm": "; + all-gather of the late MeshTaskCommand slabs+counters by a unicast peer-store kernel (nvc_gather_*), every frame, one frame deep", "mc": "; + all-gather of the late MeshTaskCommand slabs+counters by ONE NVSwitch-multicast store kernel per rank (nvc_gather_*, symmetric memory), every frame, one frame deep", "fused": "; + all-gather of the late MeshTaskCommand slabs FUSED into drawcull(late): its command write-out also goes through the NVSwitch multicast mapping (counters + flags follow), every frame, one frame deep", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a high-priority side stream", "none": ""}[gather]),
                 "counting": "value = meshlet instances TESTED by the two cluster passes per second (early %d + late %d per step per GPU); draws_per_s likewise (early %d + late %d)" % (pr["tested_early"], pr["tested_late"], pr["early_reached"], D),
                 "l2": "inputs larger than L2 (Meshlet[] %d MB + MeshDraw[] %d MB + Mesh[] %d MB + depth %d MB per step vs 126 MB L2), no flush" % (scene.meshlets.nbytes >> 20, scene.draws.nbytes >> 20, scene.meshes.nbytes >> 20, scene.depth.nbytes >> 20),
                 "cluster_backface": 1,
@@ -800,7 +833,8 @@ def main():
             },
             "clocks": clocks,
             "gpu_launches": gpu_launches,
-            "gather_transport": ("sm-push" if sm_push else gather),
+            "gather_transport": transport if not gather_note else "ce",
+            **({"gather_note": gather_note} if gather_note else {}),
             "cluster_filter": {
                 "enabled": os.environ.get("NVC_CLUSTER_FILTER", "1") != "0",
                 "footprint_image": has_fp,

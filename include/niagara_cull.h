@@ -351,9 +351,24 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets);
 NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4);
 NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream);
 NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t** gathered_count4);
-/* transport of nvc_gather_push: 0 = copy engines (default), 1 = a 32-CTA kernel on a high-priority stream that writes only
+/* transport of nvc_gather_push: 0 = copy engines (default), 2 / 3 = NVSwitch multicast (below), 1 = a 32-CTA kernel on a high-priority stream that writes only
  * the valid count x 20 bytes with 16-byte peer stores (also selectable with NVC_GATHER_MODE=sm) */
-NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push);
+NVC_API int nvc_gather_set_mode(NvcContext* ctx, int mode);
+
+/* NVSwitch MULTICAST transports (modes 2 and 3).  Every rank allocates ONE region of nvc_gather_region_bytes() with a symmetric
+ * allocator that also yields a multicast mapping of it (CUDA VMM: cuMemCreate + cuMulticastCreate / AddDevice / BindMem, handles
+ * exchanged between the processes; or torch.distributed._symmetric_memory, as bench.py does) and attaches it:
+ *   peer_regions[p]    this process's mapping of rank p's region (p == rank: its own)
+ *   multicast_region   the multicast alias (a store through it lands in EVERY rank's region), or NULL: unicast SM push only
+ * The caller barriers once after every rank has attached.  mode 2: nvc_gather_push launches a kernel that stores the valid part
+ * of the slab ONCE through the multicast mapping (egress 1x instead of world x).  mode 3 (fused compute + collective):
+ *   nvc_gather_fuse_next_drawcull(ctx, stream);   // takes the frame tag, waits for the peers' acknowledgements on `stream`
+ *   nvc_drawcull(ctx, stream, ..., late = 1, task = 1, ...);   // its command write-out also goes through the multicast mapping
+ *   nvc_gather_push(ctx, stream, dcb, dccb);      // counters + flags only
+ *   ...late cluster pass...;  nvc_gather_wait(ctx, stream); */
+NVC_API size_t nvc_gather_region_bytes(size_t slab_bytes, int world_size);
+NVC_API int nvc_gather_attach(NvcContext* ctx, size_t slab_bytes, int rank, int world_size, void* const* peer_regions, void* multicast_region);
+NVC_API int nvc_gather_fuse_next_drawcull(NvcContext* ctx, void* stream);
 
 /* ---- widening N2: scene cache (.cache v7) reader — the on-disk format that feeds the path ----------------
  * Replaces loadSceneCache (src/scenecache.cpp:273-370) for the arrays the visibility path consumes.  Host-only, no

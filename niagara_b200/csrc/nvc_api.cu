@@ -345,6 +345,8 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	p.command_count4 = command_count4;
 	p.scratch = ctx->scratch;
 	p.task_wglimit = ctx->limits.task_wglimit;
+	if (late && task && ctx->gather)
+		p.mc_commands = nvc::gather_fused_target(ctx); // armed by nvc_gather_fuse_next_drawcull, else nullptr
 	bool need_hiz = late && cull->occlusionEnabled == 1;
 	if (!fill_hiz(hiz, p.hiz) && need_hiz)
 		return NVC_ERROR_INVALID_ARGUMENT;

@@ -44,6 +44,7 @@ namespace nvc
 {
 void nccl_destroy(NvcContext* ctx);   // nvc_nccl.cpp
 void gather_destroy(NvcContext* ctx); // nvc_peer.cu
+uint32_t* gather_fused_target(NvcContext* ctx); // nvc_peer.cu: multicast destination of the armed late drawcull, or nullptr (disarms)
 
 // Device-side counters owned by the context.  Each pass's last-block epilogue leaves them zeroed, which replaces
 // the reference's vkCmdFillBuffer resets (niagara.cpp:1541,1586) and keeps every pass a single launch.
@@ -110,6 +111,10 @@ struct DrawCullParams
 	Scratch* scratch;
 	HiZDesc hiz;
 	uint32_t task_wglimit;
+	// multi-GPU, fused all-gather (nvc_gather_fuse_next_drawcull): NVSwitch multicast alias of THIS rank's slot in every
+	// rank's gathered slab buffer; every command the pass writes to `commands` is also stored there (replicated by the
+	// switch to all ranks), so the exchange happens inside the producing kernel.  nullptr: not fused.
+	uint32_t* mc_commands;
 };
 
 // Per-launch constants of the conservative meshlet filter (nvc_filter.cuh; host-computed by make_filter_consts).

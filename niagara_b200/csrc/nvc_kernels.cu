@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 				if (staged || uint64_t(dci) + units[k] <= p.task_wglimit)
 				{
 					uint32_t* out = staged ? s_stage + local * 5u : reinterpret_cast<uint32_t*>(static_cast<NvcMeshTaskCommand*>(p.commands) + dci);
+					uint32_t* mc = (!staged && p.mc_commands) ? p.mc_commands + size_t(dci) * 5u : nullptr; // (staged blocks mirror in the copy-out loop)
 					for (uint32_t i = 0; i < units[k]; ++i, out += 5)
 					{
 						out[0] = di[k];                                                             // drawId
@@ -378,6 +379,12 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 						out[2] = min(NVC_TASK_WGSIZE, meshletCount[k] - i * NVC_TASK_WGSIZE);       // taskCount
 						out[3] = dv[k];                                                             // lateDrawVisibility
 						out[4] = d2[k].y + i * NVC_TASK_WGSIZE;                                     // meshletVisibilityOffset
+						if (mc)
+						{
+							for (int wd = 0; wd < 5; ++wd)
+								mc[wd] = out[wd];
+							mc += 5;
+						}
 					}
 				}
 			}
@@ -400,6 +407,14 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 		uint32_t* out = reinterpret_cast<uint32_t*>(p.commands) + size_t(s_block_base) * kWords;
 		for (uint32_t i = tid; i < block_total * kWords; i += kDrawBlock)
 			out[i] = s_stage[i];
+		if (TASK && p.mc_commands)
+		{
+			// fused all-gather: the same coalesced stream goes once more through the NVSwitch multicast mapping, which
+			// replicates it into this rank's slot of EVERY rank's gathered buffer (one store per word instead of N unicast copies)
+			uint32_t* mc = p.mc_commands + size_t(s_block_base) * kWords;
+			for (uint32_t i = tid; i < block_total * kWords; i += kDrawBlock)
+				mc[i] = s_stage[i];
+		}
 	}
 
 	// ---- last-block epilogue: tasksubmit.comp.glsl:27-47 (TASK) / publish the count (draw path) ----
@@ -432,6 +447,12 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			out->taskCount = 0;
 			out->lateDrawVisibility = 0;
 			out->meshletVisibilityOffset = 0;
+			if (p.mc_commands)
+			{
+				uint32_t* mc = p.mc_commands + size_t(count + tid) * 5u;
+				for (int wd = 0; wd < 5; ++wd)
+					mc[wd] = 0u;
+			}
 		}
 	}
 	else if (tid == 0)

@@ -84,6 +84,29 @@ __global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int ra
 	}
 }
 
+// Multicast variant of the push: every 16-byte unit of the VALID part of the slab is stored ONCE, through the NVSwitch
+// multicast alias of this rank's slot — the switch replicates it into every rank's gathered buffer (egress 1x instead
+// of world x).  Same launch shape and placement as push_kernel.
+__global__ void __launch_bounds__(512) mc_push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* mc_slabs, uint32_t* mc_counts,
+    size_t slab_bytes, int world, int rank, uint32_t parity, int with_slab)
+{
+	const size_t slot = size_t(parity) * world + rank;
+	if (with_slab)
+	{
+		const uint32_t count = local_count4[0];
+		size_t bytes = (size_t(count) + 63) / 64 * 64 * sizeof(NvcMeshTaskCommand); // the zero-padded group the consumer dispatches over
+		bytes = bytes < slab_bytes ? bytes : slab_bytes;
+		const size_t n16 = bytes / 16; // 64 commands = 1280 bytes: a multiple of 16
+		const size_t stride = size_t(gridDim.x) * blockDim.x;
+		uint4* dst = reinterpret_cast<uint4*>(mc_slabs + slot * slab_bytes);
+		for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+			dst[i] = __ldg(local_slab + i);
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		*reinterpret_cast<uint4*>(mc_counts + 4 * slot) = *reinterpret_cast<const uint4*>(local_count4);
+	__threadfence_system();
+}
+
 __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag)
 {
 	int q = threadIdx.x;
@@ -112,7 +135,12 @@ struct NvcGather
 	uint8_t** d_peer_slabs = nullptr;
 	uint32_t** d_peer_counts = nullptr;
 	cudaStream_t hi = nullptr; // high-priority stream of the SM push
-	int mode = 0;              // 0 = copy engines, 1 = SM push kernel
+	int mode = 0;              // 0 = copy engines, 1 = SM unicast push kernel, 2 = SM multicast push kernel, 3 = fused into drawcull
+	bool attached = false;     // buffers live in a caller-owned symmetric region (nvc_gather_attach): never freed / closed here
+	uint8_t* mc_slabs = nullptr;   // NVSwitch multicast aliases of the region (stores land in every rank's copy), or null
+	uint32_t* mc_counts = nullptr;
+	uint32_t fused_tag = 0;    // tag armed by nvc_gather_fuse_next_drawcull (0 = none)
+	bool fused_consumed = false; // the armed late drawcull has been launched
 	cudaStream_t side[kSideStreams] = {};
 	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
 	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity
@@ -124,6 +152,16 @@ struct NvcGather
 namespace nvc
 {
 
+uint32_t* gather_fused_target(NvcContext* ctx)
+{
+	NvcGather* g = static_cast<NvcGather*>(ctx->gather);
+	if (!g || !g->connected || g->mode != 3 || !g->mc_slabs || g->fused_tag == 0 || g->fused_consumed)
+		return nullptr;
+	g->fused_consumed = true;
+	const size_t slot = size_t(g->fused_tag & 1u) * size_t(g->world) + size_t(g->rank);
+	return reinterpret_cast<uint32_t*>(g->mc_slabs + slot * g->slab_bytes);
+}
+
 void gather_destroy(NvcContext* ctx)
 {
 	NvcGather* g = static_cast<NvcGather*>(ctx->gather);
@@ -132,7 +170,7 @@ void gather_destroy(NvcContext* ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	for (int p = 0; p < g->world; ++p)
-		if (p != g->rank && g->connected)
+		if (p != g->rank && g->connected && !g->attached)
 		{
 			if (g->peer_slabs[p])
 				cudaIpcCloseMemHandle(g->peer_slabs[p]);
@@ -153,9 +191,12 @@ void gather_destroy(NvcContext* ctx)
 	if (g->acked)
 		cudaEventDestroy(g->acked);
 	cudaFree(g->count_stage);
-	cudaFree(g->slabs);
-	cudaFree(g->counts);
-	cudaFree(g->flags);
+	if (!g->attached)
+	{
+		cudaFree(g->slabs);
+		cudaFree(g->counts);
+		cudaFree(g->flags);
+	}
 	cudaFree(g->d_peer_flags);
 	cudaFree(g->d_peer_slabs);
 	cudaFree(g->d_peer_counts);
@@ -334,7 +375,18 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	if (!on_context_device(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	g->tag += 1;
+	// fused mode: the tag was taken (and the peers' acknowledgements awaited) by nvc_gather_fuse_next_drawcull, and the slab
+	// has already travelled inside the late drawcull — only the counters and the flags are left
+	const bool fused = g->mode == 3 && g->fused_tag != 0 && g->fused_consumed;
+	if (g->mode == 3 && !fused)
+	{
+		ctx->last_error = "nvc_gather_push in fused mode needs nvc_gather_fuse_next_drawcull + the late nvc_drawcull before it";
+		return NVC_ERROR_INVALID_ARGUMENT;
+	}
+	if (!fused)
+		g->tag += 1;
+	g->fused_tag = 0;
+	g->fused_consumed = false;
 	const uint32_t tag = g->tag;
 	const size_t parity = tag & 1u;
 	const size_t slot = parity * size_t(g->world) + size_t(g->rank); // this rank's slot in every receiver's buffers
@@ -343,19 +395,22 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	cudaError_t e = cudaMemcpyAsync(count_stage, local_count4, 16, cudaMemcpyDeviceToDevice, s);
 	if (e == cudaSuccess)
 		e = cudaEventRecord(g->fork, s);
-	cudaStream_t lead = g->mode == 1 ? g->hi : g->side[0];
+	cudaStream_t lead = g->mode >= 1 ? g->hi : g->side[0];
 	if (e == cudaSuccess)
 		e = cudaStreamWaitEvent(lead, g->fork, 0);
-	if (e == cudaSuccess && tag >= 3)
+	if (e == cudaSuccess && tag >= 3 && !fused)
 	{
 		// the parity buffers were last used by frame tag-2: every peer must have acknowledged it
 		wait_flags_kernel<<<1, kMaxWorld, 0, lead>>>(g->flags + kAckBase, g->world, tag - 2);
 		e = cudaGetLastError();
 	}
-	if (g->mode == 1 && e == cudaSuccess)
+	if (g->mode >= 1 && e == cudaSuccess)
 	{
 		// SM push: one kernel on the high-priority stream, then the flag raise behind it
-		push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity));
+		if (g->mode == 1)
+			push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity));
+		else
+			mc_push_kernel<<<fused ? 1 : 32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->mc_slabs, g->mc_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity), fused ? 0 : 1);
 		e = cudaGetLastError();
 		if (e == cudaSuccess)
 		{
@@ -439,12 +494,148 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 	return NVC_OK;
 }
 
-NVC_API int nvc_gather_set_mode(NvcContext* ctx, int sm_push)
+NVC_API int nvc_gather_set_mode(NvcContext* ctx, int mode)
 {
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
-	if (!g)
+	if (!g || mode < 0 || mode > 3)
 		return NVC_ERROR_INVALID_ARGUMENT;
-	g->mode = sm_push ? 1 : 0;
+	if (mode >= 2 && !g->mc_slabs)
+	{
+		ctx->last_error = "multicast transports need nvc_gather_attach with a multicast mapping";
+		return NVC_ERROR_UNSUPPORTED;
+	}
+	if (mode == 0 && g->attached)
+	{
+		ctx->last_error = "the copy-engine transport needs nvc_gather_create / nvc_gather_connect buffers";
+		return NVC_ERROR_UNSUPPORTED;
+	}
+	g->mode = mode;
+	g->fused_tag = 0;
+	g->fused_consumed = false;
+	return NVC_OK;
+}
+
+// ---- symmetric-memory attachment: NVSwitch multicast ------------------------------------------------------------------------
+// Layout of the region every rank allocates (identically) with a symmetric allocator:
+//   [2][world][slab_bytes] slabs | [2][world][4] u32 counters | [2 x 64] u32 flags + acknowledgements
+static size_t region_counts_offset(size_t slab_bytes, int world) { return 2 * slab_bytes * size_t(world); }
+static size_t region_flags_offset(size_t slab_bytes, int world) { return region_counts_offset(slab_bytes, world) + 2 * 16 * size_t(world); }
+
+NVC_API size_t nvc_gather_region_bytes(size_t slab_bytes, int world_size)
+{
+	if (world_size < 1 || world_size > kMaxWorld || slab_bytes == 0 || slab_bytes % 16 != 0)
+		return 0;
+	return region_flags_offset(slab_bytes, world_size) + sizeof(uint32_t) * 2 * kMaxWorld;
+}
+
+NVC_API int nvc_gather_attach(NvcContext* ctx, size_t slab_bytes, int rank, int world, void* const* peer_regions, void* multicast_region)
+{
+	if (!ctx || !peer_regions || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || nvc_gather_region_bytes(slab_bytes, world) == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	for (int p = 0; p < world; ++p)
+		if (!peer_regions[p] || (reinterpret_cast<uintptr_t>(peer_regions[p]) & 15u))
+			return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	nvc::gather_destroy(ctx);
+	NvcGather* g = new NvcGather();
+	g->world = world;
+	g->rank = rank;
+	g->slab_bytes = slab_bytes;
+	g->attached = true;
+	const size_t co = region_counts_offset(slab_bytes, world), fo = region_flags_offset(slab_bytes, world);
+	for (int p = 0; p < world; ++p)
+	{
+		uint8_t* base = static_cast<uint8_t*>(peer_regions[p]);
+		g->peer_slabs[p] = base;
+		g->peer_counts[p] = reinterpret_cast<uint32_t*>(base + co);
+		g->peer_flags[p] = reinterpret_cast<uint32_t*>(base + fo);
+	}
+	g->slabs = g->peer_slabs[rank];
+	g->counts = g->peer_counts[rank];
+	g->flags = g->peer_flags[rank];
+	if (multicast_region)
+	{
+		g->mc_slabs = static_cast<uint8_t*>(multicast_region);
+		g->mc_counts = reinterpret_cast<uint32_t*>(g->mc_slabs + co);
+	}
+	cudaError_t e = cudaMalloc(&g->d_peer_flags, sizeof(uint32_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->d_peer_slabs, sizeof(uint8_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->d_peer_counts, sizeof(uint32_t*) * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&g->count_stage, 32);
+	if (e == cudaSuccess)
+	{
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		e = cudaStreamCreateWithPriority(&g->hi, cudaStreamNonBlocking, hi);
+	}
+	for (int i = 0; i < kSideStreams && e == cudaSuccess; ++i)
+	{
+		e = cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&g->join[i], cudaEventDisableTiming);
+	}
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&g->acked, cudaEventDisableTiming);
+	// this rank clears ITS OWN counters / flags / acknowledgements; the caller barriers before the first push
+	if (e == cudaSuccess)
+		e = cudaMemset(g->counts, 0, 2 * 16 * size_t(world));
+	if (e == cudaSuccess)
+		e = cudaMemset(g->flags, 0, sizeof(uint32_t) * 2 * kMaxWorld);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_flags, g->peer_flags, sizeof(uint32_t*) * world, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_slabs, g->peer_slabs, sizeof(uint8_t*) * world, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(g->d_peer_counts, g->peer_counts, sizeof(uint32_t*) * world, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaDeviceSynchronize();
+	ctx->gather = g;
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_attach: ") + cudaGetErrorString(e);
+		nvc::gather_destroy(ctx);
+		return e == cudaErrorMemoryAllocation ? NVC_ERROR_OUT_OF_MEMORY : NVC_ERROR_CUDA;
+	}
+	g->connected = true;
+	g->mode = g->mc_slabs ? 2 : 1; // multicast push when the mapping exists, unicast SM push otherwise
+	return NVC_OK;
+}
+
+// Fused all-gather: takes the next frame tag, blocks `stream` until every peer has acknowledged the previous user of that
+// parity's buffers, and arms the NEXT late task-mode nvc_drawcull of this context: that launch stores its commands to the
+// local buffer AND through the multicast mapping into every rank's gathered slab.  Follow with nvc_gather_push (sends the
+// counters and raises the flags only) and nvc_gather_wait as usual.
+NVC_API int nvc_gather_fuse_next_drawcull(NvcContext* ctx, void* stream)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !g->connected || g->mode != 3 || !g->mc_slabs)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (g->fused_tag != 0)
+	{
+		ctx->last_error = "nvc_gather_fuse_next_drawcull: the previous armed frame has not been pushed";
+		return NVC_ERROR_INVALID_ARGUMENT;
+	}
+	g->tag += 1;
+	g->fused_tag = g->tag;
+	g->fused_consumed = false;
+	if (g->tag >= 3)
+	{
+		wait_flags_kernel<<<1, kMaxWorld, 0, static_cast<cudaStream_t>(stream)>>>(g->flags + kAckBase, g->world, g->tag - 2);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+		{
+			ctx->last_error = std::string("nvc_gather_fuse_next_drawcull: ") + cudaGetErrorString(e);
+			return NVC_ERROR_CUDA;
+		}
+	}
 	return NVC_OK;
 }
 

@@ -78,6 +78,9 @@ SIGNATURES = [
     ("nvc_gather_push", ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     ("nvc_gather_wait", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_set_mode", ctypes.c_int, [c_void_p, ctypes.c_int]),
+    ("nvc_gather_region_bytes", ctypes.c_size_t, [ctypes.c_size_t, ctypes.c_int]),
+    ("nvc_gather_attach", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    ("nvc_gather_fuse_next_drawcull", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_buffers", ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
 ]
 

@@ -4,4 +4,5 @@ namespace nvc
 {
 void nccl_destroy(NvcContext*) {}
 void gather_destroy(NvcContext*) {}
+uint32_t* gather_fused_target(NvcContext*) { return nullptr; }
 } // namespace nvc
