@@ -146,12 +146,61 @@ def main():
         ok = False
         print("rank", rank, "flow-control stress: %d frames carried stale or torn slabs" % int(bad.item()))
 
+    # ---- NVSwitch multicast transports over a symmetric region (modes 2 and 3), where the system offers them ----
+    mc_state = "skipped"
+    err = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        region = int(lib.nvc_gather_region_bytes(slab_bytes, world))
+        t = symm_mem.empty(region, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+        mc_ptr = int(hdl.multicast_ptr)
+        if not mc_ptr:
+            raise RuntimeError("no multicast mapping")
+        peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+        check(lib.nvc_gather_attach(g.ctx, slab_bytes, rank, world, peers, ctypes.c_void_p(mc_ptr)), g.ctx, "nvc_gather_attach")
+    except Exception as e:
+        err = e
+    have = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(have, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    if int(have.item()):
+        mc_state = "checked"
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for f in range(6):
+            mode = 2 + (f % 2)  # multicast push kernel / fused into the late drawcull
+            check(lib.nvc_gather_set_mode(g.ctx, mode), g.ctx, "nvc_gather_set_mode")
+            g.cull(cd, False)
+            g.render_clusters(cd, False, cluster_backface=True)
+            g.pyramid(depth)
+            if mode == 3:
+                check(lib.nvc_gather_fuse_next_drawcull(g.ctx, stream), g.ctx, "nvc_gather_fuse_next_drawcull")
+            g.cull(cd, True)
+            check(lib.nvc_allgather_visible(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), slab_bytes, ctypes.c_void_p(g.dccb.data_ptr()), ctypes.c_void_p(gathered.data_ptr()), ctypes.c_void_p(gathered_counts.data_ptr())), g.ctx, "nvc_allgather_visible")
+            check(lib.nvc_gather_push(g.ctx, stream, ctypes.c_void_p(g.dcb.data_ptr()), ctypes.c_void_p(g.dccb.data_ptr())), g.ctx, "nvc_gather_push")
+            g.render_clusters(cd, True, cluster_backface=True)
+            check(lib.nvc_gather_wait(g.ctx, stream), g.ctx, "nvc_gather_wait")
+            check(lib.nvc_gather_buffers(g.ctx, ctypes.byref(ce_slabs), ctypes.byref(ce_counts)), g.ctx, "nvc_gather_buffers")
+            torch.cuda.synchronize()
+            view = _device_bytes(torch, ce_slabs.value, world * slab_bytes, dev)
+            cnt = _device_bytes(torch, ce_counts.value, world * 16, dev).view(torch.int32)
+            same = torch.equal(cnt, gathered_counts)
+            for r in range(world):
+                n = (int(gathered_counts[4 * r].item()) + 63) // 64 * 64 * 20  # incl. the zero padding the consumer dispatches over
+                same = same and torch.equal(view[r * slab_bytes : r * slab_bytes + n], gathered[r * slab_bytes : r * slab_bytes + n])
+            if not same:
+                ok = False
+                print("rank", rank, "multicast gather (mode %d) differs from the NCCL gather, frame" % mode, f)
+    elif rank == 0:
+        print("multicast transports not checked:", str(err)[:200] if err else "unavailable on another rank")
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checked its own gathered buffers
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("MULTI_GPU_CHECK", "OK" if int(flag.item()) == 1 else "FAILED", "world", world)
+        print("MULTI_GPU_CHECK", "OK" if int(flag.item()) == 1 else "FAILED", "world", world, "multicast", mc_state)
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
