@@ -561,10 +561,46 @@ def main():
         sampler.start()
         time.sleep(0.15)
     launches["n"] = 0
-    max_ms = timed(lambda k: frame(cd, ev[k]), K)
+    eager_ms = timed(lambda k: frame(cd, ev[k]), K)
     gpu_launches = launches["n"]
     lib.nvc_filter_stats(path.ctx, filter_stats, 1)
     pass_ms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(5)] for k in range(K)])
+
+    # ---- the same K frames as ONE CUDA-graph launch each (graph replay; no per-launch host work, no timing
+    # events between the passes).  Calls of the C ABI only enqueue, so a frame captures as is.  Single GPU only: the peer
+    # exchange uses side streams and flags across processes. ----
+    graph_ms = None
+    graph_note = None
+    if world == 1 and os.environ.get("NVC_BENCH_GRAPH", "1") != "0":
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                frame(cd)  # warm the side stream
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                frame(cd)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            per = []
+            for rep in range(3):  # three regions of K replays: median and min reported
+                torch.cuda.synchronize()
+                g0.record()
+                for _ in range(K):
+                    graph.replay()
+                g1.record()
+                torch.cuda.synchronize()
+                per.append(g0.elapsed_time(g1))
+            graph_ms = {"median": float(np.median(per)), "min": float(min(per))}
+            del graph
+        except Exception as e:
+            graph_note = str(e)[:160]
+            torch.cuda.synchronize()
+    # headline = graph replay when it ran (that is how a host would drive the frame), eager otherwise
+    max_ms = graph_ms["median"] if graph_ms else eager_ms
 
     counts = torch.tensor([tested_per_step, draws_per_step], dtype=torch.float64, device=dev)
     if world > 1:
@@ -832,6 +868,12 @@ def main():
                 "kernel_ms": k_ms,
             },
             "clocks": clocks,
+            "timing": {
+                "headline": "CUDA-graph replay of the frame (median of 3 regions of %d replays)" % K if graph_ms else "eager launches from the host (%d frames)" % K,
+                "graph_ms_per_step": ({k: v / K for k, v in graph_ms.items()} if graph_ms else None),
+                "eager_ms_per_step": eager_ms / K,
+                **({"graph_unavailable": graph_note} if graph_note else {}),
+            },
             "gpu_launches": gpu_launches,
             "gather_transport": transport if not gather_note else "ce",
             **({"gather_note": gather_note} if gather_note else {}),

@@ -284,13 +284,14 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			// :108  (TASK_CULL == 1, config.h:8)
 			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv[k] == 0 || cd.postPass != 0))
 			{
-				if (cd.lodEnabled == 1) // :112-120
+				uint32_t lodCount = 0;
+				if (cd.lodEnabled == 1)
+					lodCount = min(packed ? h1[k].x : __ldg(reinterpret_cast<const uint32_t*>(mp + 32)), NVC_MAX_LODS);
+				if (lodCount > 1) // :112-120 (with a single LOD the loop below is empty and lodIndex stays 0: the distance is not needed)
 				{
 					float d = __fsub_rn(length3(center), radius);
 					float distance = d > 0.f ? d : 0.f;
 					float threshold = __fdiv_rn(__fmul_rn(distance, cd.lodTarget), d0[k].w);
-					uint32_t lodCount = packed ? h1[k].x : __ldg(reinterpret_cast<const uint32_t*>(mp + 32));
-					lodCount = min(lodCount, NVC_MAX_LODS);
 					const float* errors = packed ? p.mesh_errors + size_t(meshIndex) * NVC_MAX_LODS : nullptr;
 					for (uint32_t i = 1; i < lodCount; ++i)
 					{
