@@ -493,6 +493,19 @@ typedef struct NvcVertex
 	uint16_t tu, tv;
 } NvcVertex;
 
+/* Depth-only consumer of cib / ccb / dcb on the device (new; stands in for what the reference's mesh stage and fixed-function
+ * rasteriser do to depthTarget between the cull passes, niagara.cpp:1576-1701 with meshlet.mesh.glsl:89-206): every cluster slot of
+ * the (16, Y, 16) dispatch is decoded like the mesh shader does, its vertices are transformed with the shader's arithmetic
+ * (strict IEEE, GLSL operation order) by `projection16 * (pass->view * vec4(world, 1))`, and its front-facing triangles are sampled at
+ * pixel centres into `depth` (float, width x height, reverse Z, test GREATER: depth = max).  The caller clears `depth` to 0 before
+ * the early pass; the late pass adds to it.  Meshlets whose references fall outside meshletdata / vertices are skipped and counted.
+ * stats4 (may be NULL): clusters drawn, triangles sampled, clusters rejected, depth updates issued.  The image is deterministic
+ * (max is order independent) and equals the sequential test rasteriser's (oracle/refshader) bit for bit. */
+NVC_API int nvc_raster_depth(NvcContext* ctx, void* stream, const float* projection16, const NvcCullData* pass,
+    const uint32_t* cluster_indices, const uint32_t* cluster_count4, const NvcMeshTaskCommand* task_commands,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, const uint32_t* meshletdata, uint32_t meshletdata_words,
+    const NvcVertex* vertices, uint32_t vertex_count, float* depth, uint32_t width, uint32_t height, uint32_t* stats4);
+
 /* Recomputes center / radius / cone_axis / cone_cutoff of meshlets[0..meshlet_count) from geometry, bit-identical to
  * what the reference's cooker stores (scene.cpp:69-80 appendMeshlet -> meshopt_computeMeshletBounds,
  * meshletutils.cpp:133-272,314-339): one thread per meshlet reads its references and triangles from

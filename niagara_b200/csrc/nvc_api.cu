@@ -459,6 +459,21 @@ NVC_API int nvc_decode_clusters(NvcContext* ctx, void* stream, const uint32_t* c
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_decode_clusters");
 }
 
+NVC_API int nvc_raster_depth(NvcContext* ctx, void* stream, const float* projection16, const NvcCullData* pass, const uint32_t* cluster_indices, const uint32_t* cluster_count4,
+    const NvcMeshTaskCommand* task_commands, const NvcMeshDraw* draws, const NvcMeshlet* meshlets, const uint32_t* meshletdata, uint32_t meshletdata_words, const NvcVertex* vertices,
+    uint32_t vertex_count, float* depth, uint32_t width, uint32_t height, uint32_t* stats4)
+{
+	if (!ctx || !projection16 || !pass || !cluster_indices || !cluster_count4 || !task_commands || !draws || !meshlets || !meshletdata || !vertices || !depth || width == 0 || height == 0)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (uint64_t(width) * height >= (1ull << 31))
+		return NVC_ERROR_UNSUPPORTED;
+	if (!device_is_current(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	cudaError_t e = nvc::launch_raster_depth(projection16, *pass, cluster_indices, cluster_count4, task_commands, draws, meshlets, meshletdata, meshletdata_words, vertices, vertex_count, depth,
+	    width, height, stats4, uint32_t(ctx->sm_count) * 16u, static_cast<cudaStream_t>(stream));
+	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_raster_depth");
+}
+
 NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
     uint32_t depth_width, uint32_t depth_height, const NvcHiZ* hiz)
 {

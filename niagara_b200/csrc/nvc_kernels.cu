@@ -15,6 +15,7 @@
 #include "nvc_filter.cuh"
 
 #include <cuda_runtime.h>
+#include <string.h>
 
 namespace nvc
 {
@@ -1759,6 +1760,227 @@ cudaError_t launch_decode_clusters(const uint32_t* cluster_indices, const uint32
 	if (e != cudaSuccess)
 		return e;
 	decode_clusters_kernel<<<blocks, 256, 0, stream>>>(cluster_indices, cluster_count4, task_commands, meshlets, records, stats4);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Depth-only consumer of cib / ccb / dcb: what the reference's mesh stage + rasteriser do to the depth target between the
+// cull passes (niagara.cpp:1576-1701: vkCmdDrawMeshTasksIndirectEXT(ccb, 4) -> meshlet.mesh.glsl:89-206 -> fixed-function
+// raster, depth test GREATER on the reverse-Z buffer).  One warp per cluster slot: the lanes transform the <= 64 vertices
+// exactly as the mesh shader does (strict IEEE, GLSL operation order) into shared memory, then each lane rasterises its
+// share of the <= 96 triangles with the sampling rule of the test rasteriser (oracle/refshader/driver.cpp rasterTriangle:
+// pixel centres, edge functions and depth interpolation in binary64, back faces / w <= 0 dropped) and merges depth with
+// atomicMax — max is order independent, so the image is bit-identical to the sequential CPU rasteriser's.
+// This is what lets the two-phase path run on PRODUCED depth on the device (BASELINE configs[2]).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kRasterWarps = 4;
+
+__device__ __forceinline__ float4 mat4_mul_vec4(const float* __restrict__ m, float x, float y, float z, float w)
+{
+	// GLSL mat4 * vec4, column-major: ((col0 * x + col1 * y) + col2 * z) + col3 * w, every operation rounded
+	float4 r;
+	r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[4], y)), __fmul_rn(m[8], z)), __fmul_rn(m[12], w));
+	r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[1], x), __fmul_rn(m[5], y)), __fmul_rn(m[9], z)), __fmul_rn(m[13], w));
+	r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[2], x), __fmul_rn(m[6], y)), __fmul_rn(m[10], z)), __fmul_rn(m[14], w));
+	r.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[3], x), __fmul_rn(m[7], y)), __fmul_rn(m[11], z)), __fmul_rn(m[15], w));
+	return r;
+}
+
+struct RasterParams
+{
+	float projection[16];
+	float view[16];
+	const uint32_t* cluster_indices;
+	const uint32_t* cluster_count4;
+	const NvcMeshTaskCommand* task_commands;
+	const NvcMeshDraw* draws;
+	const NvcMeshlet* meshlets;
+	const uint32_t* meshletdata;
+	uint32_t meshletdata_words;
+	const NvcVertex* vertices;
+	uint32_t vertex_count;
+	float* depth;
+	uint32_t width, height;
+	uint32_t* stats4; // clusters drawn, triangles rasterised, clusters rejected (data out of range), pixels written (approximate: updates)
+};
+
+__global__ void __launch_bounds__(kRasterWarps * 32) raster_depth_kernel(const RasterParams p)
+{
+	__shared__ float4 s_clip[kRasterWarps][64];
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	const uint32_t gx = p.cluster_count4[1], gy = p.cluster_count4[2], gz = p.cluster_count4[3];
+	const uint32_t slots = gx * gy * gz;
+	float4* clip = s_clip[warp];
+	uint32_t drawn = 0, tris = 0, rejected = 0, writes = 0;
+	const double fw = double(p.width), fh = double(p.height);
+
+	for (uint32_t w = blockIdx.x * kRasterWarps + warp; w < slots; w += gridDim.x * kRasterWarps)
+	{
+		const uint32_t x = w % gx, z = (w / gx) % gz, y = w / (gx * gz);
+		const uint32_t slot = x + y * 256u + z * NVC_CLUSTER_TILE; // meshlet.mesh.glsl:94
+		const uint32_t ci = __ldg(p.cluster_indices + slot);
+		if (ci == ~0u)
+			continue; // SetMeshOutputsEXT(0, 0)
+		const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + (ci & 0xffffffu));
+		const uint32_t drawId = __ldg(cp + 0), mi = __ldg(cp + 1) + (ci >> 24);
+		const NvcMeshlet& ml = p.meshlets[mi];
+		const uint32_t vertexCount = ml.vertexCount, triangleCount = ml.triangleCount;
+		const uint32_t dataOffset = ml.dataOffset, baseVertex = ml.baseVertex;
+		const bool shortRefs = ml.shortRefs == 1;
+		const uint32_t indexOffset = dataOffset + (shortRefs ? (vertexCount + 1) / 2 : vertexCount);
+		// the meshlet's references / triangle bytes must lie inside meshletdata (robustBufferAccess in the reference; here: skip)
+		const uint64_t end_words = uint64_t(indexOffset) + (uint64_t(triangleCount) * 3 + 3) / 4;
+		if (vertexCount > 64 || triangleCount > 96 || end_words > p.meshletdata_words)
+		{
+			rejected += lane == 0;
+			continue;
+		}
+		const char* dp = reinterpret_cast<const char*>(p.draws + drawId);
+		const float4 d0 = ldg_f4(dp), d1 = ldg_f4(dp + 16);
+
+		// ---- vertices: meshlet.mesh.glsl:126-147 ----
+		bool bad = false;
+		for (uint32_t i = lane; i < vertexCount; i += 32)
+		{
+			uint32_t ref = shortRefs ? uint32_t(reinterpret_cast<const uint16_t*>(p.meshletdata)[size_t(dataOffset) * 2 + i]) : __ldg(p.meshletdata + dataOffset + i);
+			uint32_t vi = ref + baseVertex;
+			if (vi >= p.vertex_count)
+			{
+				bad = true;
+				break;
+			}
+			const uint2 vv = __ldg(reinterpret_cast<const uint2*>(p.vertices + vi)); // vx, vy | vz, tp
+			f3 pos = { half_bits_to_float(vv.x & 0xffffu), half_bits_to_float(vv.x >> 16), half_bits_to_float(vv.y & 0xffffu) };
+			f3 r = rotate_quat(pos, d1);
+			const float wx = __fadd_rn(__fmul_rn(r.x, d0.w), d0.x), wy = __fadd_rn(__fmul_rn(r.y, d0.w), d0.y), wz = __fadd_rn(__fmul_rn(r.z, d0.w), d0.z);
+			const float4 v = mat4_mul_vec4(p.view, wx, wy, wz, 1.0f);
+			clip[i] = mat4_mul_vec4(p.projection, v.x, v.y, v.z, v.w);
+		}
+		if (__any_sync(0xffffffffu, bad))
+		{
+			rejected += lane == 0;
+			__syncwarp();
+			continue;
+		}
+		__syncwarp();
+		drawn += lane == 0;
+
+		// ---- triangles ----
+		const uint8_t* tri8 = reinterpret_cast<const uint8_t*>(p.meshletdata) + size_t(indexOffset) * 4;
+		for (uint32_t t = lane; t < triangleCount; t += 32)
+		{
+			const uint32_t ia = tri8[t * 3 + 0], ib = tri8[t * 3 + 1], ic = tri8[t * 3 + 2];
+			if (ia >= vertexCount || ib >= vertexCount || ic >= vertexCount)
+				continue;
+			const float4 pc[3] = { clip[ia], clip[ib], clip[ic] };
+			double sx[3], sy[3], sz[3];
+			bool front = true;
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+			{
+				front = front && pc[c].w > 0.0f;
+				const float fx = __fmul_rn(__fadd_rn(__fmul_rn(__fdiv_rn(pc[c].x, pc[c].w), 0.5f), 0.5f), float(p.width));
+				const float fy = __fmul_rn(__fadd_rn(__fmul_rn(__fdiv_rn(pc[c].y, pc[c].w), 0.5f), 0.5f), float(p.height));
+				sx[c] = double(fx);
+				sy[c] = double(fy);
+				sz[c] = double(__fdiv_rn(pc[c].z, pc[c].w));
+			}
+			if (!front)
+				continue;
+			const double ebx = __dsub_rn(sx[1], sx[0]), eby = __dsub_rn(sy[1], sy[0]), ecx = __dsub_rn(sx[2], sx[0]), ecy = __dsub_rn(sy[2], sy[0]);
+			const double area = __dsub_rn(__dmul_rn(ebx, ecy), __dmul_rn(eby, ecx));
+			if (!(area > 0.0))
+				continue; // back facing or zero area
+			// flipped viewport: rows count from the top; swapping two corners keeps the edge functions positive inside
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+				sy[c] = __dsub_rn(fh, sy[c]);
+			{
+				double tx = sx[1], ty = sy[1], tz = sz[1];
+				sx[1] = sx[2], sy[1] = sy[2], sz[1] = sz[2];
+				sx[2] = tx, sy[2] = ty, sz[2] = tz;
+			}
+			const double minx = fmin(sx[0], fmin(sx[1], sx[2])), maxx = fmax(sx[0], fmax(sx[1], sx[2]));
+			const double miny = fmin(sy[0], fmin(sy[1], sy[2])), maxy = fmax(sy[0], fmax(sy[1], sy[2]));
+			if (!(maxx >= 0.0 && maxy >= 0.0 && minx <= fw && miny <= fh))
+				continue;
+			const int x0 = int(fmax(0.0, floor(__dsub_rn(minx, 0.5)))), x1 = int(fmin(__dsub_rn(fw, 1.0), ceil(__dsub_rn(maxx, 0.5))));
+			const int y0 = int(fmax(0.0, floor(__dsub_rn(miny, 0.5)))), y1 = int(fmin(__dsub_rn(fh, 1.0), ceil(__dsub_rn(maxy, 0.5))));
+			++tris;
+			for (int yy = y0; yy <= y1; ++yy)
+				for (int xx = x0; xx <= x1; ++xx)
+				{
+					const double px = __dadd_rn(double(xx), 0.5), py = __dadd_rn(double(yy), 0.5);
+					const double w0 = __dsub_rn(__dmul_rn(__dsub_rn(sx[1], px), __dsub_rn(sy[2], py)), __dmul_rn(__dsub_rn(sy[1], py), __dsub_rn(sx[2], px)));
+					const double w1 = __dsub_rn(__dmul_rn(__dsub_rn(sx[2], px), __dsub_rn(sy[0], py)), __dmul_rn(__dsub_rn(sy[2], py), __dsub_rn(sx[0], px)));
+					const double w2 = __dsub_rn(__dmul_rn(__dsub_rn(sx[0], px), __dsub_rn(sy[1], py)), __dmul_rn(__dsub_rn(sy[0], py), __dsub_rn(sx[1], px)));
+					if (w0 < 0.0 || w1 < 0.0 || w2 < 0.0)
+						continue;
+					const double num = __dadd_rn(__dadd_rn(__dmul_rn(w0, sz[0]), __dmul_rn(w1, sz[1])), __dmul_rn(w2, sz[2]));
+					const double den = __dadd_rn(__dadd_rn(w0, w1), w2);
+					const float zf = float(__ddiv_rn(num, den));
+					// depth test GREATER on a buffer cleared to 0: only positive, ordered values can win; for those the float
+					// order is the order of their bit patterns
+					if (zf > 0.0f)
+					{
+						atomicMax(reinterpret_cast<int*>(p.depth) + size_t(yy) * p.width + xx, __float_as_int(zf));
+						++writes;
+					}
+				}
+		}
+		__syncwarp(); // the next cluster reuses clip[]
+	}
+	if (p.stats4)
+	{
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1)
+		{
+			drawn += __shfl_xor_sync(0xffffffffu, drawn, o);
+			tris += __shfl_xor_sync(0xffffffffu, tris, o);
+			rejected += __shfl_xor_sync(0xffffffffu, rejected, o);
+			writes += __shfl_xor_sync(0xffffffffu, writes, o);
+		}
+		if (lane == 0)
+		{
+			if (drawn)
+				atomicAdd(p.stats4 + 0, drawn);
+			if (tris)
+				atomicAdd(p.stats4 + 1, tris);
+			if (rejected)
+				atomicAdd(p.stats4 + 2, rejected);
+			if (writes)
+				atomicAdd(p.stats4 + 3, writes);
+		}
+	}
+}
+
+cudaError_t launch_raster_depth(const float* projection16, const NvcCullData& pass, const uint32_t* cluster_indices, const uint32_t* cluster_count4, const NvcMeshTaskCommand* task_commands,
+    const NvcMeshDraw* draws, const NvcMeshlet* meshlets, const uint32_t* meshletdata, uint32_t meshletdata_words, const NvcVertex* vertices, uint32_t vertex_count, float* depth, uint32_t width,
+    uint32_t height, uint32_t* stats4, uint32_t blocks, cudaStream_t stream)
+{
+	RasterParams p;
+	memcpy(p.projection, projection16, sizeof(p.projection));
+	memcpy(p.view, pass.view, sizeof(p.view));
+	p.cluster_indices = cluster_indices;
+	p.cluster_count4 = cluster_count4;
+	p.task_commands = task_commands;
+	p.draws = draws;
+	p.meshlets = meshlets;
+	p.meshletdata = meshletdata;
+	p.meshletdata_words = meshletdata_words;
+	p.vertices = vertices;
+	p.vertex_count = vertex_count;
+	p.depth = depth;
+	p.width = width;
+	p.height = height;
+	p.stats4 = stats4;
+	if (stats4)
+	{
+		cudaError_t e = cudaMemsetAsync(stats4, 0, 16, stream);
+		if (e != cudaSuccess)
+			return e;
+	}
+	raster_depth_kernel<<<blocks, kRasterWarps * 32, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 

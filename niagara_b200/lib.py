@@ -29,6 +29,7 @@ SIGNATURES = [
     ("nvc_set_hiz_staging", ctypes.c_int, [c_void_p, ctypes.c_uint32]),
     ("nvc_prepare_hiz", ctypes.c_int, [c_void_p, ctypes.POINTER(HiZ)]),
     ("nvc_set_cluster_filter", ctypes.c_int, [c_void_p, ctypes.c_int]),
+    ("nvc_raster_depth", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(CullData), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, ctypes.c_uint32, c_void_p]),
     ("nvc_filter_stats", ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     ("nvc_previous_pow2", ctypes.c_uint32, [ctypes.c_uint32]),
     ("nvc_image_mip_levels", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),

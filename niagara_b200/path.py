@@ -154,6 +154,19 @@ class VisibilityPath:
         assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.numel() == self.depth_width * self.depth_height
         check(self.lib.nvc_depth_pyramid(self.ctx, self._stream(), _ptr(depth), self.depth_width, self.depth_height, ctypes.byref(self.hiz)), self.ctx, "nvc_depth_pyramid")
 
+    def raster_depth(self, cull_data, projection16, vertices, meshletdata, depth, stats=None):
+        """Depth-only consumer of this path's cib / ccb / dcb on the device (nvc_raster_depth): what the reference's mesh stage +
+        rasteriser do to the depth target between the cull passes.  vertices: uint8 device tensor of 16-byte Vertex records;
+        meshletdata: int32 device tensor; depth: float32 device tensor [height, width], cleared by the caller before the early pass."""
+        pass_data = layout.CullData()
+        self.lib.nvc_host_pass_data(ctypes.byref(cull_data), 0, 0, ctypes.byref(pass_data))
+        proj = (ctypes.c_float * 16)(*[float(v) for v in projection16])
+        check(
+            self.lib.nvc_raster_depth(self.ctx, self._stream(), proj, ctypes.byref(pass_data), _ptr(self.cib), _ptr(self.ccb), _ptr(self.dcb), _ptr(self.db), _ptr(self.mlb), _ptr(meshletdata), meshletdata.numel(), _ptr(vertices), vertices.numel() // 16, _ptr(depth), depth.shape[1], depth.shape[0], _ptr(stats)),
+            self.ctx,
+            "nvc_raster_depth",
+        )
+
     def frame(self, cull_data, depth, post_passes=False, cluster_backface=None):
         """One frame of the hot path in the reference's order (niagara.cpp:1765-1788).  `depth` stands in for the
         depth target the early render would have produced."""

@@ -202,6 +202,7 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline uint32_t atomicAnd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }
+inline int atomicMax(int* p, int v) { int o = *p; *p = o > v ? o : v; return o; }
 inline uint32_t atomicMax(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o > v ? o : v; return o; }
 inline uint32_t atomicMin(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o < v ? o : v; return o; }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
@@ -213,6 +214,10 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 inline float __frcp_rn(float a) { return 1.0f / a; }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

@@ -88,6 +88,19 @@ class EmuPath(oracle_lib.OraclePath):
         depth = np.ascontiguousarray(depth, dtype=np.float32)
         self._check(self.emu.nvc_depth_pyramid(self.ctx, None, _p(depth), self.depth_width, self.depth_height, ctypes.byref(self.hiz)), "nvc_depth_pyramid")
 
+    def raster_depth(self, cull_data, projection16, vertices, meshletdata, depth, cib=None, ccb=None, dcb=None):
+        """nvc_raster_depth over (cib, ccb) (default: this path's own); returns stats[4]"""
+        cib = self.cib if cib is None else np.ascontiguousarray(cib, dtype=np.uint32)
+        ccb = self.ccb if ccb is None else np.ascontiguousarray(ccb, dtype=np.uint32)
+        dcb = self.dcb if dcb is None else dcb
+        pd = self._pass_data(cull_data, 0, 0)
+        proj = np.ascontiguousarray(projection16, dtype=np.float32)
+        md = np.ascontiguousarray(meshletdata, dtype=np.uint32)
+        vb = np.ascontiguousarray(vertices)
+        stats = np.zeros(4, np.uint32)
+        self._check(self.emu.nvc_raster_depth(self.ctx, None, _p(proj), ctypes.byref(pd), _p(cib), _p(ccb), _p(dcb), _p(self.draws), _p(self.meshlets), _p(md), len(md), _p(vb), vb.nbytes // 16, _p(depth), depth.shape[1], depth.shape[0], _p(stats)), "nvc_raster_depth")
+        return stats
+
     def close(self):
         if self.ctx:
             self.emu.nvc_destroy(self.ctx)

@@ -321,3 +321,42 @@ def test_animated_cache_scene_with_post_pass(golden_dir):
             owners_total += len(owner_pairs)
         assert (truth > 0).mean() > 0.02
     assert moved >= 9 and post_total > 0 and owners_total > 100
+
+
+def test_device_rasteriser_matches_the_test_rasteriser(golden_dir):
+    """nvc_raster_depth (the product's kernel, under the CPU emulation) against the reference's mesh shader + the sequential test
+    rasteriser on the same cib / ccb / dcb: identical depth images bit for bit, early and late pass, moving camera."""
+    screen = (320, 240)
+    s, vertices, meshletdata = _kitten_scene(golden_dir, 120, screen)
+    o = emu_lib.EmuPath(s.meshes, s.meshlets, s.draws, *screen, threads=4)
+    o.set_visibility_bits(s.visibility_bits)
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((2.5, -1.0, 2.0), host.quat_from_axis_angle((0, 1, 0), 0.2))]
+    drawn_total = 0
+    for cam in cams:
+        s.camera = cam
+        cd = s.cull_data()
+        proj = host.projection(cam, *screen)
+        ms = refshader_lib.MeshStage(o, vertices, meshletdata, proj)
+        want = np.zeros((screen[1], screen[0]), np.float32)
+        got = np.zeros_like(want)
+        for late in (False, True):
+            if late:
+                o.pyramid(want)
+            o.cull(cd, late)
+            o.render_clusters(cd, late)
+            rec, pos, tri = ms.run(cd)
+            ms.rasterize(rec, pos, tri, want)
+            stats = o.raster_depth(cd, proj, vertices, meshletdata, got)
+            assert int(stats[0]) == int(o.ccb[0]) and int(stats[2]) == 0
+            drawn_total += int(stats[0])
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (late, int((want != got).sum()))
+    assert drawn_total > 300 and (want > 0).mean() > 0.05
+    # hostile geometry references are skipped and counted, never read
+    bad = o.meshlets.copy()
+    bad["dataOffset"][:] = 0x7FFFFFF0
+    good, o.meshlets = o.meshlets, bad
+    depth = np.zeros_like(want)
+    stats = o.raster_depth(cd, proj, vertices, meshletdata, depth)
+    assert int(stats[0]) == 0 and int(stats[2]) == int(o.ccb[0]) and not depth.any()
+    o.meshlets = good
+    o.close()

@@ -515,3 +515,53 @@ def test_c3_bistro_standin_two_pass(golden_dir):
         rec, stats = g.decode_clusters()
         assert stats[2] == 0 and stats[0] == gc[0]
     assert int(o.read_counts()[1][0]) >= 0 and len(early) + len(late) > 10000
+
+
+def test_two_phase_on_device_produced_depth(golden_dir):
+    """The whole loop on the device with NO synthetic depth: early cull -> nvc_raster_depth -> pyramid of that depth -> late cull ->
+    nvc_raster_depth, over a moving camera — against the oracle culling + the reference's mesh shader + the sequential test
+    rasteriser (oracle/refshader) doing the same on the CPU.  Depth images, cluster sets and visibility state must be identical."""
+    import refshader_lib
+
+    if not refshader_lib.available():
+        pytest.skip("needs a prebuilt oracle/_ref/librefshader.so")
+    torch = _torch()
+    from test_end_to_end_raster import _kitten_scene
+
+    screen = (512, 384)
+    s, vertices, meshletdata = _kitten_scene(golden_dir, 300, screen)
+    g, o, _ = _paths(s)
+    vb = torch.from_numpy(np.ascontiguousarray(vertices)).cuda()
+    md = torch.from_numpy(np.ascontiguousarray(meshletdata, dtype=np.uint32).view(np.int32)).cuda()
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    cams = [host.make_camera((0, 0, 0)), host.make_camera((0, 0, 0)), host.make_camera((3.5, -1.0, 2.0), host.quat_from_axis_angle((0, 1, 0), 0.18)),
+            host.make_camera((7.0, 1.5, 5.0), host.quat_from_axis_angle((0.1, 1, 0), 0.42))]
+    late_total = 0
+    for f, cam in enumerate(cams):
+        s.camera = cam
+        cd = s.cull_data()
+        proj = host.projection(cam, *screen)
+        ms = refshader_lib.MeshStage(o, vertices, meshletdata, proj)
+        want = np.zeros((screen[1], screen[0]), np.float32)
+        got = torch.zeros((screen[1], screen[0]), dtype=torch.float32, device="cuda")
+        for late in (False, True):
+            if late:
+                g.pyramid(got)
+                o.pyramid(want)
+                _compare_pyramid(g, o, ("pyramid of produced depth", f))
+            g.cull(cd, late)
+            o.cull(cd, late)
+            _compare_draw_pass(g, o, True, ("cull", f, late))
+            g.render_clusters(cd, late)
+            o.render_clusters(cd, late)
+            _compare_cluster_pass(g, o, ("clusters", f, late))
+            rec, pos, tri = ms.run(cd)
+            ms.rasterize(rec, pos, tri, want)
+            g.raster_depth(cd, proj, vb, md, got, stats)
+            torch.cuda.synchronize()
+            st = stats.cpu().numpy()
+            assert int(st[0]) == int(o.ccb[0]) and int(st[2]) == 0, (f, late, st)
+            assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32)), ("depth image", f, late)
+            if late:
+                late_total += int(o.ccb[0])
+    assert late_total > 0 and (want > 0).mean() > 0.2
