@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-shaders"])
-    ap.add_argument("--workload", default="C4", choices=["C4", "C2"])
+    ap.add_argument("--workload", default="C4", choices=["C4", "C2", "C3"], help="C4 = BASELINE configs[3] (default), C2 = configs[1], C3 = configs[2] stand-in: real cooked geometry, ~3M LOD-0 meshlets, the prior-frame depth is PRODUCED on the device (nvc_raster_depth) instead of synthesised")
     ap.add_argument("--draws", type=int, default=1_000_000)
     ap.add_argument("--meshlets-per-draw", type=int, default=10)
     ap.add_argument("--depth", type=int, default=4096)
@@ -117,6 +117,8 @@ def build_scene(args, rank, helpers=None):
     if scene is None:
         if args.workload == "C4":
             scene = scenes.config4_scene(args.draws, args.meshlets_per_draw, screen=(args.depth, args.depth), seed=21 + 100 * rank, helpers=helpers)
+        elif args.workload == "C3":
+            scene = scenes.config3_scene(os.path.join(ROOT, "tests", "golden"), screen=(args.depth, args.depth), seed=31 + 100 * rank)
         else:
             scene = scenes.config2_scene(args.draws, screen=(args.depth, args.depth), seed=11 + 100 * rank)
         try:
@@ -133,6 +135,8 @@ def workload_label(args, draws=None):
     draws = args.draws if draws is None else draws
     if args.workload == "C4":
         return "C4: %d draws x %d unique meshlets each (%d meshlet instances), all inside the frustum, %dx%d depth" % (draws, args.meshlets_per_draw, draws * args.meshlets_per_draw, args.depth, args.depth)
+    if args.workload == "C3":
+        return "C3 stand-in: kitten.obj cooked by the reference (309 LOD-0 meshlets, LOD chain) x 10000 draws = 3.1M LOD-0 meshlet instances, LOD selection on, two-pass Hi-Z occlusion + cone cull on depth PRODUCED on the device (nvc_raster_depth), %dx%d" % (args.depth, args.depth)
     return "C2: %d draws (reference PCG32 scene), 1024 meshes x 4 LODs, %dx%d depth" % (draws, args.depth, args.depth)
 
 
@@ -353,6 +357,14 @@ def main():
     depth = depth_host.to(dev)
     lib = path.lib
     launches = {"n": 0}  # kernels of OUR library launched (counted at the call sites below)
+    produced = None
+    if args.workload == "C3":
+        produced = {
+            "proj": host.projection(scene.camera, *scene.screen),
+            "vertices": torch.from_numpy(scene.vertices).to(dev),
+            "meshletdata": torch.from_numpy(scene.meshletdata.view(np.int32)).to(dev),
+        }
+        depth.zero_()
     has_fp = os.environ.get("NVC_PREPARE_HIZ", "1") != "0"
 
     # ---- multi-GPU: all-gather of the per-rank visible command slabs + counters ----
@@ -443,8 +455,15 @@ def main():
         mark(1)
         clusters(False)
         mark(2)
-        path.pyramid(depth)
+        if produced is not None:
+            # C3: the early pass's clusters are rasterised into a cleared depth target on the device; its pyramid is what
+            # the late pass culls against (niagara.cpp:1576-1733) — no synthetic depth
+            depth.zero_()
+            path.raster_depth(cull, produced["proj"], produced["vertices"], produced["meshletdata"], depth)
+            launches["n"] += 2
         mark(3)
+        path.pyramid(depth)
+        mark(4)
         path.dcb = dcb_late
         if peer and pending["push"]:
             # the previous frame's slab (and every peer's copy of it) must have landed before it is overwritten
@@ -457,7 +476,7 @@ def main():
             check(lib.nvc_gather_fuse_next_drawcull(path.ctx, path._stream()), path.ctx, "nvc_gather_fuse_next_drawcull")
             launches["n"] += 1
         path.cull(cull, late=True)
-        mark(4)
+        mark(5)
         launches["n"] += 5 + (1 if has_fp else 0)
         if peer:
             # the late command slab is final once drawcull(late) is done: ce = push it to every peer with the copy engines,
@@ -476,9 +495,25 @@ def main():
                 "nvc_allgather_visible",
             )
         clusters(True)
-        mark(5)
+        mark(6)
+        if produced is not None:
+            path.raster_depth(cull, produced["proj"], produced["vertices"], produced["meshletdata"], depth)
+            launches["n"] += 1
+        mark(7)
         if gather == "nccl":
             torch.cuda.current_stream().wait_stream(comm_stream)
+
+    NEV = 8  # timing marks per frame: start, cull e, clusters e, raster e, pyramid, cull l, clusters l, raster l
+
+    def new_events(n):
+        return [[torch.cuda.Event(enable_timing=True) for _ in range(NEV)] for _ in range(n)]
+
+    def passes_of(evs):
+        """[steps, 5] ms of the five cull-path passes (NAMES order) and [steps, 2] ms of the two raster passes (C3 only)"""
+        idx = [(0, 1), (1, 2), (3, 4), (4, 5), (5, 6)]
+        a = np.array([[e[i].elapsed_time(e[j]) for i, j in idx] for e in evs])
+        r = np.array([[e[2].elapsed_time(e[3]), e[6].elapsed_time(e[7])] for e in evs])
+        return a, r
 
     def drain():
         """end of a timed region: the last frame's exchange must be complete on every rank"""
@@ -525,6 +560,9 @@ def main():
         path.render_clusters(cull, late=False, cluster_backface=True)
         torch.cuda.synchronize()
         ccb_e = path.ccb.cpu().numpy().astype(np.uint32)
+        if produced is not None:
+            depth.zero_()
+            path.raster_depth(cull, produced["proj"], produced["vertices"], produced["meshletdata"], depth)
         path.pyramid(depth)
         path.dcb = dcb_late
         path.cull(cull, late=True)
@@ -534,6 +572,8 @@ def main():
         path.render_clusters(cull, late=True, cluster_backface=True)
         torch.cuda.synchronize()
         ccb_l = path.ccb.cpu().numpy().astype(np.uint32)
+        if produced is not None:
+            path.raster_depth(cull, produced["proj"], produced["vertices"], produced["meshletdata"], depth)
         return {
             "early_reached": reached,
             "tested_early": int(cmds_e["taskCount"].sum()),
@@ -554,7 +594,7 @@ def main():
     filter_stats = (ctypes.c_uint64 * 2)()
     lib.nvc_filter_stats(path.ctx, filter_stats, 1)  # reset the filter's diagnostic counters
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    ev = new_events(K)
     sampler = ClockSampler(local_rank)
     sync_all()
     if rank == 0:
@@ -564,7 +604,7 @@ def main():
     eager_ms = timed(lambda k: frame(cd, ev[k]), K)
     gpu_launches = launches["n"]
     lib.nvc_filter_stats(path.ctx, filter_stats, 1)
-    pass_ms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(5)] for k in range(K)])
+    pass_ms, raster_ms = passes_of(ev)
 
     # ---- the same K frames as ONE CUDA-graph launch each (graph replay; no per-launch host work, no timing
     # events between the passes).  Calls of the C ABI only enqueue, so a frame captures as is.  Single GPU only: the peer
@@ -651,9 +691,9 @@ def main():
         cams = [host.make_camera(orientation=host.quat_from_axis_angle((0.0, 1.0, 0.0), np.radians(0.2 * (k + 1)))) for k in range(KM)]
         cds = [host.cull_data(c, scene.screen[0], scene.screen[1], D) for c in cams]
         dvb0, mvb0 = path.dvb.clone(), path.mvb.clone()
-        evm = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(KM)]
+        evm = new_events(KM)
         mv_ms = timed(lambda k: frame(cds[k], evm[k]), KM)
-        mv_pass = np.array([[evm[k][i].elapsed_time(evm[k][i + 1]) for i in range(5)] for k in range(KM)])
+        mv_pass, _ = passes_of(evm)
         # replay the same camera path from the same state, untimed, reading the work counts of every step
         path.dvb.copy_(dvb0)
         path.mvb.copy_(mvb0)
@@ -683,9 +723,9 @@ def main():
         KT = max(5, min(20, K))
         for _ in range(2):
             frame(cd, task=(payloads, emit_counts))
-        evt = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(KT)]
+        evt = new_events(KT)
         t_ms = timed(lambda k: frame(cd, evt[k], task=(payloads, emit_counts)), KT)
-        t_pass = np.array([[evt[k][i].elapsed_time(evt[k][i + 1]) for i in range(5)] for k in range(KT)])
+        t_pass, _ = passes_of(evt)
         tk_ms = float(t_pass[:, 4].mean())
         tk_bytes = pr["tested_late"] * 24 + pr["cmds_late"] * 20 + pr["draws_late"] * 48 + 2 * pr["tested_late"] / 8.0 + 4 * pr["emitted_late"] + 4 * pr["cmds_late"]
         return {
@@ -698,7 +738,7 @@ def main():
         }
 
     extras = {}
-    if not args.no_extras:
+    if not args.no_extras and args.workload == "C4":
         for key, fn in (("moving_camera", run_moving_camera), ("task_shading", run_task_shading)):
             try:
                 extras[key] = fn()
@@ -849,7 +889,9 @@ def main():
                 "parallelism": "draw-sharded x%d" % world,
             },
             "draws_per_s": draws_all * K / (max_ms * 1e-3),
+            **({"cull_only_value": tested_all / (mean_ms.sum() * 1e-3), "cull_only_note": "meshlets tested per second over the five cull-path passes alone (the step above also contains the two raster passes that produce the depth)"} if produced is not None else {}),
             "passes_ms": {n: float(mean_ms[i]) for i, n in enumerate(NAMES)},
+            **({"raster_ms": {"early": float(raster_ms[:, 0].mean()), "late": float(raster_ms[:, 1].mean()), "what": "nvc_raster_depth (stand-in for the reference's mesh stage + rasteriser): produces the depth the late pass culls against; not part of the cull path"}} if produced is not None else {}),
             "passes_share": {n: float(share[i]) for i, n in enumerate(NAMES)},
             "passes_hbm_frac": {n: float(alg[n] / (mean_ms[i] * 1e-3) / 1e9 / peak_gbs) for i, n in enumerate(NAMES)},
             "frame_hbm_frac": float(sum(alg.values()) / (mean_ms.sum() * 1e-3) / 1e9 / peak_gbs),

@@ -179,6 +179,38 @@ def config4_scene(draw_count=1_000_000, meshlets_per_draw=10, screen=(4096, 4096
     return s
 
 
+def config3_scene(golden_dir, draw_count=10000, screen=(4096, 4096), seed=31):
+    """BASELINE configs[2] stand-in (no bistro.gltf in the image): the reference-cooked kitten.obj (309 LOD-0 meshlets, 792 over its LOD chain,
+    tests/golden/kitten.nvcg + its vertex / meshlet data) instanced `draw_count` times inside the frustum = ~3.1M LOD-0 meshlet
+    instances, with the geometry the device rasteriser needs (scene.vertices: uint8 view of 16-byte Vertex records,
+    scene.meshletdata: uint32).  The prior-frame depth is produced on the device, so scene.depth is all zeros."""
+    import os
+
+    meshes, meshlets, _ = layout.load_nvcg(os.path.join(golden_dir, "kitten.nvcg"))
+    z = np.load(os.path.join(golden_dir, "kitten_cook.npz"))
+    positions, meshletdata = z["positions"], z["meshletdata"]
+    vertices = np.zeros((len(positions), 8), dtype=np.uint16)
+    vertices[:, :3] = positions
+    rng = np.random.default_rng(seed)
+    cam = host.make_camera()
+    ty = math.tan(cam.fovY / 2) * 0.95
+    tx = ty * screen[0] / screen[1]
+    depth_z = rng.uniform(8.0**3, 190.0**3, draw_count) ** (1.0 / 3.0)
+    d = np.zeros(draw_count, dtype=layout.MESHDRAW_DTYPE)
+    d["position"][:, 0] = (rng.uniform(-1, 1, draw_count) * tx * depth_z).astype(np.float32)
+    d["position"][:, 1] = (rng.uniform(-1, 1, draw_count) * ty * depth_z).astype(np.float32)
+    d["position"][:, 2] = (-depth_z).astype(np.float32)  # the camera looks down -Z (niagara.cpp:1492)
+    d["scale"] = rng.uniform(1.5, 4.5, draw_count).astype(np.float32)
+    q = rng.standard_normal((draw_count, 4))
+    d["orientation"] = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    bits, _ = host.visibility_offsets(d, meshes)
+    s = Scene("C3", meshes, meshlets, d, np.zeros((screen[1], screen[0]), np.float32), cam, screen, bits)
+    s.vertices = np.ascontiguousarray(vertices).view(np.uint8).reshape(-1)
+    s.meshletdata = np.ascontiguousarray(meshletdata, dtype=np.uint32)
+    s.note = "%d draws of the reference-cooked kitten (%d LOD-0 meshlets each), %dx%d, depth produced on the device" % (draw_count, int(meshes["lods"]["meshletCount"][0, 0]), screen[0], screen[1])
+    return s
+
+
 def instanced_scene(nvcg_path, draw_count, screen=(1024, 768), name="instanced"):
     """C1 / C3 stand-in: geometry cooked by the reference's own scene.cpp (tests/golden/*.nvcg) instanced with the
     reference's random-scene recipe."""

@@ -23,3 +23,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"clu
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 20 --csv --log-file $O/launches.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > /dev/null 2>&1
 ls -la $O
 python bench.py --steps 50 --warmup 3 2>>$O/err.log | tail -1 > $O/bench_full.json; summ full < $O/bench_full.json
+python bench.py --workload C3 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --no-extras 2>>$O/err.log | tail -1 > $O/bench_c3.json; summ C3 < $O/bench_c3.json
