@@ -493,6 +493,29 @@ typedef struct NvcVertex
 	uint16_t tu, tv;
 } NvcVertex;
 
+/* ---- N3: glTF 2.0 scene import for the visibility path (loadScene, src/scene.cpp:473-853) -----------------------------------------
+ * MeshDraw[] (world transform of every mesh node decomposed as scene.cpp:295-340 does, meshIndex = first_mesh_index + running index of
+ * the indexed triangle primitives, materialIndex = material_offset + material, postPass 1 for non-opaque / 2 for transmissive materials),
+ * Animation[] + Keyframe[] (LINEAR TRS samplers baked per key through the node hierarchy, scene.cpp:713-830), camera, sun direction,
+ * and per primitive the quantised Vertex[] / index arrays of loadVertices (scene.cpp:342-405) — bit-identical to what the reference's
+ * importer produces from the same file.  Host only; .gltf (data: URIs or external buffers under base_dir) and .glb.  Sparse accessors
+ * and EXT_meshopt_compression: NVC_ERROR_UNSUPPORTED.  Malformed files: NVC_ERROR_CORRUPT, never read outside the buffers. */
+typedef struct NvcGltfScene NvcGltfScene;
+typedef struct NvcGltfInfo
+{
+	uint32_t node_count, mesh_count, primitive_count, draw_count, animation_count, keyframe_count, material_count, point_light_count;
+	uint32_t has_camera, has_sun;
+	NvcCamera camera;        /* position, orientation, fovY of the (last) camera node; znear stays 0: the application sets it */
+	float sun_direction[3];  /* local +Z of the (last) directional light node */
+} NvcGltfInfo;
+NVC_API int nvc_gltf_import(const void* file, size_t file_size, const char* base_dir, uint32_t first_mesh_index, uint32_t material_offset, NvcGltfScene** out_scene);
+NVC_API void nvc_gltf_free(NvcGltfScene* scene);
+NVC_API int nvc_gltf_info(const NvcGltfScene* scene, NvcGltfInfo* out);
+/* any output may be NULL; sizes from nvc_gltf_info; mesh_scale[primitive_count] = the scale appendMesh receives (scene.cpp:503-519) */
+NVC_API int nvc_gltf_scene_arrays(const NvcGltfScene* scene, NvcMeshDraw* draws, NvcAnimation* animations, NvcKeyframe* keyframes, float* mesh_scale);
+NVC_API int nvc_gltf_primitive_size(const NvcGltfScene* scene, uint32_t primitive, uint32_t* vertex_count, uint32_t* index_count);
+NVC_API int nvc_gltf_primitive_data(const NvcGltfScene* scene, uint32_t primitive, NvcVertex* vertices, uint32_t* indices);
+
 /* Depth-only consumer of cib / ccb / dcb on the device (new; stands in for what the reference's mesh stage and fixed-function
  * rasteriser do to depthTarget between the cull passes, niagara.cpp:1576-1701 with meshlet.mesh.glsl:89-206): every cluster slot of
  * the (16, Y, 16) dispatch is decoded like the mesh shader does, its vertices are transformed with the shader's arithmetic

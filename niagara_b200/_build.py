@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libniagara_cull.so")
 
-SOURCES = ["nvc_kernels.cu", "nvc_api.cu", "nvc_peer.cu", "nvc_host.cpp", "nvc_scene_cache.cpp", "nvc_meshopt_decode.cpp", "nvc_nccl.cpp"]
+SOURCES = ["nvc_kernels.cu", "nvc_api.cu", "nvc_peer.cu", "nvc_host.cpp", "nvc_scene_cache.cpp", "nvc_meshopt_decode.cpp", "nvc_gltf.cpp", "nvc_nccl.cpp"]
 HEADERS = ["nvc_internal.h", "nvc_math.cuh", "nvc_math2.cuh", "nvc_filter.cuh", "nvc_cook.cuh", "nvc_tma.cuh", os.path.join(ROOT, "include", "niagara_cull.h")]
 
 NVCC_FLAGS = [

@@ -176,6 +176,23 @@ class Camera(ctypes.Structure):
     ]
 
 
+class GltfInfo(ctypes.Structure):
+    _fields_ = [
+        ("node_count", ctypes.c_uint32),
+        ("mesh_count", ctypes.c_uint32),
+        ("primitive_count", ctypes.c_uint32),
+        ("draw_count", ctypes.c_uint32),
+        ("animation_count", ctypes.c_uint32),
+        ("keyframe_count", ctypes.c_uint32),
+        ("material_count", ctypes.c_uint32),
+        ("point_light_count", ctypes.c_uint32),
+        ("has_camera", ctypes.c_uint32),
+        ("has_sun", ctypes.c_uint32),
+        ("camera", Camera),
+        ("sun_direction", ctypes.c_float * 3),
+    ]
+
+
 class CullOptions(ctypes.Structure):
     _fields_ = [
         ("draw_distance", ctypes.c_float),

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 from . import _build
-from .layout import Camera, CullData, CullOptions, HiZ, Limits, SceneCacheInfo
+from .layout import Camera, CullData, CullOptions, GltfInfo, HiZ, Limits, SceneCacheInfo
 
 _LIB = None
 
@@ -29,6 +29,12 @@ SIGNATURES = [
     ("nvc_set_hiz_staging", ctypes.c_int, [c_void_p, ctypes.c_uint32]),
     ("nvc_prepare_hiz", ctypes.c_int, [c_void_p, ctypes.POINTER(HiZ)]),
     ("nvc_set_cluster_filter", ctypes.c_int, [c_void_p, ctypes.c_int]),
+    ("nvc_gltf_import", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(c_void_p)]),
+    ("nvc_gltf_free", None, [c_void_p]),
+    ("nvc_gltf_info", ctypes.c_int, [c_void_p, ctypes.POINTER(GltfInfo)]),
+    ("nvc_gltf_scene_arrays", ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("nvc_gltf_primitive_size", ctypes.c_int, [c_void_p, ctypes.c_uint32, c_u32_p, c_u32_p]),
+    ("nvc_gltf_primitive_data", ctypes.c_int, [c_void_p, ctypes.c_uint32, c_void_p, c_void_p]),
     ("nvc_raster_depth", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(CullData), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, ctypes.c_uint32, c_void_p]),
     ("nvc_filter_stats", ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     ("nvc_previous_pow2", ctypes.c_uint32, [ctypes.c_uint32]),
