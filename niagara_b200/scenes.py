@@ -148,9 +148,10 @@ def reference_random_scene(meshes, meshlets, draw_count, screen=(1024, 768), dep
     return Scene(name, meshes, meshlets, draws, depth, cam, screen, bits)
 
 
-def config2_scene(draw_count=1_000_000, num_meshes=1024, screen=(4096, 4096), seed=11):
-    """BASELINE configs[1]: 1M synthetic MeshDraws (reference PCG32 recipe), 4 LODs, 4Kx4K synthetic prior-frame depth."""
-    meshes, nmeshlets = synthetic_meshes(num_meshes, 4, 64, seed=seed)
+def config2_scene(draw_count=1_000_000, num_meshes=1024, screen=(4096, 4096), seed=11, lod0_meshlets=64):
+    """BASELINE configs[1]: 1M synthetic MeshDraws (reference PCG32 recipe), 4 LODs, 4Kx4K synthetic prior-frame depth.
+    num_meshes is SURVEY §8(d)'s knob (1024: the mesh table is L2 resident; 1 000 000: every draw gathers its own Mesh)."""
+    meshes, nmeshlets = synthetic_meshes(num_meshes, 4, lod0_meshlets, seed=seed)
     meshlets = synthetic_meshlets(nmeshlets, seed=seed + 1)
     s = reference_random_scene(meshes, meshlets, draw_count, screen=screen, depth_seed=seed + 2, occluders=200, name="C2")
     s.note = "%d draws (reference PCG32 scene), %d meshes x 4 LODs, %dx%d depth" % (draw_count, num_meshes, screen[0], screen[1])

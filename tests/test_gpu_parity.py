@@ -565,3 +565,28 @@ def test_two_phase_on_device_produced_depth(golden_dir):
             if late:
                 late_total += int(o.ccb[0])
     assert late_total > 0 and (want > 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("num_meshes,lod0", [(1024, 64), (1_000_000, 8)])
+def test_c2_full_size_bit_exact(num_meshes, lod0):
+    """BASELINE configs[1] at FULL size: the reference's own PCG32 scene with 1M draws over 4-LOD meshes, 4096^2 depth, both
+    settings of SURVEY §8(d)'s mesh-count knob (1024 = L2-resident mesh table, 1 000 000 = one Mesh gather per draw) — two frames,
+    CUDA vs the multi-threaded oracle, bit-exact incl. the selected LOD of every surviving draw (carried by the task commands)."""
+    s = scenes.config2_scene(draw_count=1_000_000, num_meshes=num_meshes, lod0_meshlets=lod0)
+    g, o, depth = _paths(s)
+    o.threads = os.cpu_count() or 8
+    cd = s.cull_data()
+    survivors = 0
+    for f in range(2):
+        for late in (False, True):
+            if late:
+                g.pyramid(depth)
+                o.pyramid(s.depth)
+            g.cull(cd, late)
+            o.cull(cd, late)
+            _compare_draw_pass(g, o, True, ("c2 cull", num_meshes, f, late))
+            g.render_clusters(cd, late, cluster_backface=True)
+            o.render_clusters(cd, late, cluster_backface=True)
+            _compare_cluster_pass(g, o, ("c2 clusters", num_meshes, f, late))
+            survivors += int(o.read_counts()[0][0])
+    assert survivors > 1000
