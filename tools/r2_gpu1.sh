@@ -27,5 +27,5 @@ python bench.py --workload C3 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline -
 echo "== compute-sanitizer (filtered kernels, drawcull DPT, raster, footprint)"
 SEL="kitten_4096 or tiny or pyramid_sizes or overflow or taskcull or hostile or big_meshes or decode or without_prepared or produced_depth"
 for tool in memcheck racecheck; do
-  timeout 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|Error|error:|hazard" | head -8 | sed "s/^/$tool: /" | tee -a $O/sanitizer.txt
+  timeout 240 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|Error|error:|hazard" | head -8 | sed "s/^/$tool: /" | tee -a $O/sanitizer.txt
 done
