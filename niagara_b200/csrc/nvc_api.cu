@@ -420,8 +420,12 @@ NVC_API int nvc_clustercull(NvcContext* ctx, void* stream, const NvcCullData* cu
 	}
 	// multi-GPU: the persistent grid would otherwise own every register of every SM for the whole pass, and the exchange's
 	// one-block helper kernels (acknowledgement wait, flag raise) could not start before it ends — leave two CTA slots free
-	if (ctx->gather && blocks > 16)
-		blocks -= 2;
+	if (ctx->gather)
+	{
+		const uint32_t reserve = nvc::gather_reserved_blocks(ctx);
+		if (blocks > 4 * reserve)
+			blocks -= reserve;
+	}
 	cudaError_t e = nvc::launch_clustercull(p, late != 0, blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_clustercull");
 }

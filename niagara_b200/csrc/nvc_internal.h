@@ -44,7 +44,8 @@ namespace nvc
 {
 void nccl_destroy(NvcContext* ctx);   // nvc_nccl.cpp
 void gather_destroy(NvcContext* ctx); // nvc_peer.cu
-uint32_t* gather_fused_target(NvcContext* ctx); // nvc_peer.cu: multicast destination of the armed late drawcull, or nullptr (disarms)
+uint32_t* gather_fused_target(NvcContext* ctx);
+uint32_t gather_reserved_blocks(NvcContext* ctx); // nvc_peer.cu: CTA slots the persistent cluster grid leaves to the exchange's kernels // nvc_peer.cu: multicast destination of the armed late drawcull, or nullptr (disarms)
 
 // Device-side counters owned by the context.  Each pass's last-block epilogue leaves them zeroed, which replaces
 // the reference's vkCmdFillBuffer resets (niagara.cpp:1541,1586) and keeps every pass a single launch.

@@ -47,7 +47,7 @@ __global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int r
 // SM variant of the push: a few CTAs stream the VALID part of the local slab (count x 20 bytes, known only on the
 // device) to every rank's slot with 16-byte peer stores.  Launched on a high-priority stream right before the late
 // cluster pass so that its CTAs are placed first; the persistent cluster kernel fills the remaining slots.
-__global__ void __launch_bounds__(512) push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* const* peer_slabs,
+__global__ void __launch_bounds__(256) push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* const* peer_slabs,
     uint32_t* const* peer_counts, size_t slab_bytes, int world, int rank, uint32_t parity)
 {
 	const size_t slot = size_t(parity) * world + rank;
@@ -87,7 +87,7 @@ __global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int ra
 // Multicast variant of the push: every 16-byte unit of the VALID part of the slab is stored ONCE, through the NVSwitch
 // multicast alias of this rank's slot — the switch replicates it into every rank's gathered buffer (egress 1x instead
 // of world x).  Same launch shape and placement as push_kernel.
-__global__ void __launch_bounds__(512) mc_push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* mc_slabs, uint32_t* mc_counts,
+__global__ void __launch_bounds__(256) mc_push_kernel(const uint4* __restrict__ local_slab, const uint32_t* __restrict__ local_count4, uint8_t* mc_slabs, uint32_t* mc_counts,
     size_t slab_bytes, int world, int rank, uint32_t parity, int with_slab)
 {
 	const size_t slot = size_t(parity) * world + rank;
@@ -151,6 +151,16 @@ struct NvcGather
 
 namespace nvc
 {
+
+// CTA slots the persistent cluster grid leaves free so that the exchange's kernels can run beside it: the one-block
+// helpers (acknowledgement wait, flag raise) always; the 16-CTA push kernels of the SM / multicast transports too.
+uint32_t gather_reserved_blocks(NvcContext* ctx)
+{
+	NvcGather* g = static_cast<NvcGather*>(ctx->gather);
+	if (!g || !g->connected)
+		return 0;
+	return (g->mode == 1 || g->mode == 2) ? 18u : 2u;
+}
 
 uint32_t* gather_fused_target(NvcContext* ctx)
 {
@@ -408,9 +418,9 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	{
 		// SM push: one kernel on the high-priority stream, then the flag raise behind it
 		if (g->mode == 1)
-			push_kernel<<<32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity));
+			push_kernel<<<16, 256, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->d_peer_slabs, g->d_peer_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity));
 		else
-			mc_push_kernel<<<fused ? 1 : 32, 512, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->mc_slabs, g->mc_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity), fused ? 0 : 1);
+			mc_push_kernel<<<fused ? 1 : 16, 256, 0, g->hi>>>(static_cast<const uint4*>(local_slab), count_stage, g->mc_slabs, g->mc_counts, g->slab_bytes, g->world, g->rank, uint32_t(parity), fused ? 0 : 1);
 		e = cudaGetLastError();
 		if (e == cudaSuccess)
 		{

@@ -5,4 +5,5 @@ namespace nvc
 void nccl_destroy(NvcContext*) {}
 void gather_destroy(NvcContext*) {}
 uint32_t* gather_fused_target(NvcContext*) { return nullptr; }
+uint32_t gather_reserved_blocks(NvcContext*) { return 0; }
 } // namespace nvc
