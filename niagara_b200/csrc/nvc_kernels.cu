@@ -1105,11 +1105,15 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 constexpr int kFStage = 128;  // staged cluster indices per warp
 constexpr int kFQueue = 64;   // undecided items per warp (drained 32 at a time)
 
+constexpr uint32_t kFItems = 1024; // early pass: set-bit positions of one batch that fit the per-warp table (larger batches: select_bit64)
+
+template <bool LATE>
 struct FilterShared
 {
 	CmdRecord rec[kClusterWarps][32];
 	uint4 queue[kClusterWarps][kFQueue];
 	uint32_t stage[kClusterWarps][kFStage];
+	uint8_t items[kClusterWarps][LATE ? 16 : kFItems]; // early pass with visibility tracking: meshlet lane (0..63) of every flattened item
 };
 
 // TRACK: clusterOcclusionEnabled == 1 && postPass == 0 (the main passes of a frame) as a compile-time fact; the generic
@@ -1120,7 +1124,7 @@ struct FilterShared
 template <bool LATE, bool FP, bool TRACK, bool TASKOUT>
 __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
 {
-	__shared__ FilterShared sh;
+	__shared__ FilterShared<LATE> sh;
 	__shared__ uint32_t s_is_last;
 
 	NVC_GRID_DEPENDENCY_SYNC();
@@ -1268,7 +1272,18 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		const uint32_t count0 = __shfl_sync(0xffffffffu, eff_count, 0);
 		const bool uniform = count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0);
 		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u;
-		__syncwarp(); // records visible to the whole warp
+		// early pass: every command lane lists the positions of its set bits ONCE; its items then read one byte instead of
+		// selecting the rank-th set bit of the 64-bit window (25 instructions) per item
+		const bool use_table = alive_flatten && total <= kFItems;
+		if (use_table)
+		{
+			uint8_t* tbl = sh.items[warp] + excl;
+			for (uint32_t m = amask_lo; m; m &= m - 1u)
+				*tbl++ = uint8_t(__ffs(int(m)) - 1);
+			for (uint32_t m = amask_hi; m; m &= m - 1u)
+				*tbl++ = uint8_t(32 + __ffs(int(m)) - 1);
+		}
+		__syncwarp(); // records (and the item table) visible to the whole warp
 		stat_items += total;
 
 		for (uint32_t base = 0; base < total; base += 32)
@@ -1304,8 +1319,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			// ---- the command's record, the meshlet, its visibility bit ----
 			const CmdRecord& rec = recs[active ? j : 0u];
 			const uint4 ids = rec.ids;
-			if (alive_flatten)
-				mgi = active ? select_bit64(ids.z, ids.w, mgi) : 0u; // the rank-th SET bit of the window is the meshlet's lane index
+			if (alive_flatten) // the rank-th SET bit of the window is the meshlet's lane index
+				mgi = !active ? 0u : use_table ? uint32_t(sh.items[warp][item]) : select_bit64(ids.z, ids.w, mgi);
 			mgi &= 63u;
 			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
 			uint2 b0 = make_uint2(0u, 0u);
