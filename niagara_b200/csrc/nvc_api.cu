@@ -350,6 +350,13 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	bool need_hiz = late && cull->occlusionEnabled == 1;
 	if (!fill_hiz(hiz, p.hiz) && need_hiz)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (need_hiz && ctx->cluster_filter)
+	{
+		// the occlusion stage as a conservative filter (same switch and the same validity domain as the cluster pass)
+		attach_footprints(ctx, hiz, p.hiz);
+		p.filter = nvc::make_filter_consts(p.cull, p.hiz, true);
+		p.use_filter = (p.filter.enabled && p.filter.occ_ok) ? 1u : 0u;
+	}
 
 	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_drawcull");

@@ -221,55 +221,20 @@ struct FilterResult
 	bool visible; // the GLSL's `visible` after all tests (meaningful when decided)
 };
 
-// One meshlet through the filter.  `b0`, `b1`: first 12 bytes of the Meshlet (center/radius halves, cone s8 x 4).
-// LATE && occlusion: the Hi-Z stage runs; `backface`: clusterBackfaceEnabled != 0.
-template <bool LATE, bool FP>
-__device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, const NvcCullData& cd, const HiZDesc& hiz, const float4 row0, const float4 row1, const float4 row2,
-    const float4 aux, uint2 b0, uint32_t b1, bool backface, bool occlusion)
+// The occlusion stage of the filter (drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123) for a view-space sphere whose
+// centre is known to within E per component of the exact path's (E must also satisfy u |c_i| <= E / 12 and u r <= E / 42; with an
+// EXACT centre, E = 12 u max|c_i| + 42 u |r| does).  mF: margin of the near-plane test.  Outputs: occ_vis / occ_hid = the exact
+// path surely returns visible / occluded; neither = undecided.
+template <bool FP>
+__device__ __forceinline__ void filter_occlusion(const FilterConsts& fc, const NvcCullData& cd, const HiZDesc& hiz, float cx, float cy, float cz, float r, float E, float mF, bool& occ_vis,
+    bool& occ_hid
+#ifdef NVF_DEBUG
+    ,
+    FilterDebug* dbg
+#endif
+)
 {
-	FilterResult res;
-	const float lx = half_bits_to_float(b0.x & 0xffffu), ly = half_bits_to_float(b0.x >> 16), lz = half_bits_to_float(b0.y & 0xffffu), rl = half_bits_to_float(b0.y >> 16);
-	const float cx = nvf_fma(row0.x, lx, nvf_fma(row0.y, ly, nvf_fma(row0.z, lz, row0.w)));
-	const float cy = nvf_fma(row1.x, lx, nvf_fma(row1.y, ly, nvf_fma(row1.z, lz, row1.w)));
-	const float cz = nvf_fma(row2.x, lx, nvf_fma(row2.y, ly, nvf_fma(row2.z, lz, row2.w)));
-	const float r = __fmul_rn(rl, aux.x); // identical to the exact path's radius
-	const float l1 = (fabsf(lx) + fabsf(ly)) + (fabsf(lz) + fabsf(rl));
-	const float E = nvf_fma(aux.y, l1, aux.z); // inf / NaN when any meshlet field is not finite: nothing below is "sure" then
-
-	// ---- frustum: every test has the form  b > -r --------------------------------------------------------------
-	const float mF = fc.fr.x * E;
-	const float bx = nvf_fma(-fabsf(cx), cd.frustum[0], cz * cd.frustum[1]);
-	const float by = nvf_fma(-fabsf(cy), cd.frustum[2], cz * cd.frustum[3]);
 	const float bn = cz - cd.znear;
-	const float m3 = fminf(fminf(bx, by), bn); // operands are finite (sane record, finite meshlet) or E is not
-	const float rp = mF - r, rm = -mF - r;
-	bool pass = fminf(m3, fc.fr.y - cz) > rp;
-	bool fail = m3 < rm || (fc.fr.z - cz) < rm;
-
-	// ---- cone, scaled by 127 s -------------------------------------------------------------------------------------
-	if (backface)
-	{
-		const float ax = (float)(int8_t)(b1 & 0xffu), ay = (float)(int8_t)((b1 >> 8) & 0xffu), az = (float)(int8_t)((b1 >> 16) & 0xffu), ac = (float)(int8_t)(b1 >> 24);
-		const float Ax = nvf_fma(row0.x, ax, nvf_fma(row0.y, ay, row0.z * az));
-		const float Ay = nvf_fma(row1.x, ax, nvf_fma(row1.y, ay, row1.z * az));
-		const float Az = nvf_fma(row2.x, ax, nvf_fma(row2.y, ay, row2.z * az));
-		const float dotv = nvf_fma(cx, Ax, nvf_fma(cy, Ay, cz * Az));
-		const float len = nvf_sqrt(nvf_fma(cx, cx, nvf_fma(cy, cy, cz * cz)));
-		const float rhs = aux.x * nvf_fma(ac, len, 127.f * r);
-		const float tc = rhs - dotv; // > 0: not back-facing
-		const float mC = (8300.f * aux.x) * E; // 64 E x 127 s (+2 %)
-		pass = pass && tc > mC;
-		fail = fail || tc < -mC;
-	}
-
-	if (!LATE || !occlusion)
-	{
-		res.decided = pass || fail;
-		res.visible = pass;
-		return res;
-	}
-
-	// ---- occlusion (drawcull.comp.glsl:88-103 == clustercull.comp.glsl:112-123) ----------------------------------------
 	const float tn = bn - r; // ok = !(cz < r + znear)
 	const bool sure_ok = tn > mF, sure_not_ok = tn < -mF;
 	const float D = cz - r, Sz = cz + r;
@@ -344,8 +309,75 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	const float dS = cd.znear * iD;
 	const float dd = dS - depth;
 	const float md = dS * (2.f * relE);
-	const bool occ_vis = sure_not_ok || (robust && dd > md);
-	const bool occ_hid = robust && dd < -md;
+	occ_vis = sure_not_ok || (robust && dd > md);
+	occ_hid = robust && dd < -md;
+
+#ifdef NVF_DEBUG
+	if (dbg)
+	{
+		FilterDebug& d = *dbg;
+		d.aabb[0] = aabb_x, d.aabb[1] = aabb_y, d.aabb[2] = aabb_z, d.aabb[3] = aabb_w;
+		d.gr = gr, d.m = m, d.dm = dm, d.ef = ef, d.efp = efp, d.dS = dS, d.depth = depth, d.level = int(level);
+		d.stage = (!(sure_ok || sure_not_ok) ? 2 : 0) | (!dom_ok ? 4 : 0) | (!lev_ok ? 8 : 0) | (!fit_ok ? 16 : 0) | (!fp_ok ? 32 : 0) | (!(dd > md || dd < -md) ? 64 : 0);
+	}
+#endif
+}
+
+// One meshlet through the filter.  `b0`, `b1`: first 12 bytes of the Meshlet (center/radius halves, cone s8 x 4).
+// LATE && occlusion: the Hi-Z stage runs; `backface`: clusterBackfaceEnabled != 0.
+template <bool LATE, bool FP>
+__device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, const NvcCullData& cd, const HiZDesc& hiz, const float4 row0, const float4 row1, const float4 row2,
+    const float4 aux, uint2 b0, uint32_t b1, bool backface, bool occlusion)
+{
+	FilterResult res;
+	const float lx = half_bits_to_float(b0.x & 0xffffu), ly = half_bits_to_float(b0.x >> 16), lz = half_bits_to_float(b0.y & 0xffffu), rl = half_bits_to_float(b0.y >> 16);
+	const float cx = nvf_fma(row0.x, lx, nvf_fma(row0.y, ly, nvf_fma(row0.z, lz, row0.w)));
+	const float cy = nvf_fma(row1.x, lx, nvf_fma(row1.y, ly, nvf_fma(row1.z, lz, row1.w)));
+	const float cz = nvf_fma(row2.x, lx, nvf_fma(row2.y, ly, nvf_fma(row2.z, lz, row2.w)));
+	const float r = __fmul_rn(rl, aux.x); // identical to the exact path's radius
+	const float l1 = (fabsf(lx) + fabsf(ly)) + (fabsf(lz) + fabsf(rl));
+	const float E = nvf_fma(aux.y, l1, aux.z); // inf / NaN when any meshlet field is not finite: nothing below is "sure" then
+
+	// ---- frustum: every test has the form  b > -r --------------------------------------------------------------
+	const float mF = fc.fr.x * E;
+	const float bx = nvf_fma(-fabsf(cx), cd.frustum[0], cz * cd.frustum[1]);
+	const float by = nvf_fma(-fabsf(cy), cd.frustum[2], cz * cd.frustum[3]);
+	const float bn = cz - cd.znear;
+	const float m3 = fminf(fminf(bx, by), bn); // operands are finite (sane record, finite meshlet) or E is not
+	const float rp = mF - r, rm = -mF - r;
+	bool pass = fminf(m3, fc.fr.y - cz) > rp;
+	bool fail = m3 < rm || (fc.fr.z - cz) < rm;
+
+	// ---- cone, scaled by 127 s -------------------------------------------------------------------------------------
+	if (backface)
+	{
+		const float ax = (float)(int8_t)(b1 & 0xffu), ay = (float)(int8_t)((b1 >> 8) & 0xffu), az = (float)(int8_t)((b1 >> 16) & 0xffu), ac = (float)(int8_t)(b1 >> 24);
+		const float Ax = nvf_fma(row0.x, ax, nvf_fma(row0.y, ay, row0.z * az));
+		const float Ay = nvf_fma(row1.x, ax, nvf_fma(row1.y, ay, row1.z * az));
+		const float Az = nvf_fma(row2.x, ax, nvf_fma(row2.y, ay, row2.z * az));
+		const float dotv = nvf_fma(cx, Ax, nvf_fma(cy, Ay, cz * Az));
+		const float len = nvf_sqrt(nvf_fma(cx, cx, nvf_fma(cy, cy, cz * cz)));
+		const float rhs = aux.x * nvf_fma(ac, len, 127.f * r);
+		const float tc = rhs - dotv; // > 0: not back-facing
+		const float mC = (8300.f * aux.x) * E; // 64 E x 127 s (+2 %)
+		pass = pass && tc > mC;
+		fail = fail || tc < -mC;
+	}
+
+	if (!LATE || !occlusion)
+	{
+		res.decided = pass || fail;
+		res.visible = pass;
+		return res;
+	}
+
+	// ---- occlusion ----
+	bool occ_vis, occ_hid;
+#ifdef NVF_DEBUG
+	filter_occlusion<FP>(fc, cd, hiz, cx, cy, cz, r, E, mF, occ_vis, occ_hid, nvf_debug);
+#else
+	filter_occlusion<FP>(fc, cd, hiz, cx, cy, cz, r, E, mF, occ_vis, occ_hid);
+#endif
 
 	res.decided = fail || occ_hid || (pass && occ_vis);
 	res.visible = pass && occ_vis && !fail && !occ_hid;
@@ -354,9 +386,7 @@ __device__ __forceinline__ FilterResult filter_meshlet(const FilterConsts& fc, c
 	{
 		FilterDebug& d = *nvf_debug;
 		d.c[0] = cx, d.c[1] = cy, d.c[2] = cz, d.r = r, d.E = E;
-		d.aabb[0] = aabb_x, d.aabb[1] = aabb_y, d.aabb[2] = aabb_z, d.aabb[3] = aabb_w;
-		d.gr = gr, d.m = m, d.dm = dm, d.ef = ef, d.efp = efp, d.dS = dS, d.depth = depth, d.level = int(level);
-		d.stage = (!(pass || fail) ? 1 : 0) | (!(sure_ok || sure_not_ok) ? 2 : 0) | (!dom_ok ? 4 : 0) | (!lev_ok ? 8 : 0) | (!fit_ok ? 16 : 0) | (!fp_ok ? 32 : 0) | (!(dd > md || dd < -md) ? 64 : 0);
+		d.stage |= !(pass || fail) ? 1 : 0;
 	}
 #endif
 	return res;

@@ -99,6 +99,21 @@ struct MeshCullHead
 };
 static_assert(sizeof(MeshCullHead) == 32, "one sector");
 
+// Per-launch constants of the conservative meshlet filter (nvc_filter.cuh; host-computed by make_filter_consts).
+// Grouped in 16-byte vectors in the order the kernel consumes them, so that each group is ONE uniform load per chunk.
+struct FilterConsts
+{
+	float4 fr;        // mFk (frustum margin = mFk * E), zfarLo, zfarHi (zfar (1 -+ 2^-20)), zn4u (4 u znear, enters Et)
+	float4 pr;        // hPx, hPyn (0.5 P00, -0.5 P11), sxk, syk (size.x * pyramidWidth = r vx icz sxk, sxk = 2 hPx pw; same for y)
+	float4 cg;        // kGx, kGrx, kGy, kGry: validity cone per axis |cx| + r kGrx <= kGx cz (kGx = 1 / hPx, kGrx = sqrt(1 + kGx^2))
+	float4 mk;        // Km1, Km2 (dm = gr (Km1 + Km2 m)), KuvP (max(pw, ph) Kuv 1.05), Kfp (footprint margin = Kfp whf gr)
+	uint4 lv;         // float bits of 2^levels, 2^(levels-1), (float)hiz.width, (float)hiz.height
+	float vrE;        // max(max row abs sum of V3, 1)
+	float Kuv;        // uv error = Kuv g relE (informational; folded into KuvP / Kfp)
+	uint32_t enabled; // 0: every item is undecided (unusual view / projection: the exact path does everything)
+	uint32_t occ_ok;  // 0: the occlusion stage is never decided here (non power-of-two pyramid, ...)
+};
+
 struct DrawCullParams
 {
 	NvcCullData cull;
@@ -116,21 +131,9 @@ struct DrawCullParams
 	// rank's gathered slab buffer; every command the pass writes to `commands` is also stored there (replicated by the
 	// switch to all ranks), so the exchange happens inside the producing kernel.  nullptr: not fused.
 	uint32_t* mc_commands;
-};
-
-// Per-launch constants of the conservative meshlet filter (nvc_filter.cuh; host-computed by make_filter_consts).
-// Grouped in 16-byte vectors in the order the kernel consumes them, so that each group is ONE uniform load per chunk.
-struct FilterConsts
-{
-	float4 fr;        // mFk (frustum margin = mFk * E), zfarLo, zfarHi (zfar (1 -+ 2^-20)), zn4u (4 u znear, enters Et)
-	float4 pr;        // hPx, hPyn (0.5 P00, -0.5 P11), sxk, syk (size.x * pyramidWidth = r vx icz sxk, sxk = 2 hPx pw; same for y)
-	float4 cg;        // kGx, kGrx, kGy, kGry: validity cone per axis |cx| + r kGrx <= kGx cz (kGx = 1 / hPx, kGrx = sqrt(1 + kGx^2))
-	float4 mk;        // Km1, Km2 (dm = gr (Km1 + Km2 m)), KuvP (max(pw, ph) Kuv 1.05), Kfp (footprint margin = Kfp whf gr)
-	uint4 lv;         // float bits of 2^levels, 2^(levels-1), (float)hiz.width, (float)hiz.height
-	float vrE;        // max(max row abs sum of V3, 1)
-	float Kuv;        // uv error = Kuv g relE (informational; folded into KuvP / Kfp)
-	uint32_t enabled; // 0: every item is undecided (unusual view / projection: the exact path does everything)
-	uint32_t occ_ok;  // 0: the occlusion stage is never decided here (non power-of-two pyramid, ...)
+	// late pass: the occlusion stage runs as a conservative filter on the exact centre; undecided draws take the exact path
+	FilterConsts filter;
+	uint32_t use_filter;
 };
 
 struct ClusterParams

@@ -181,6 +181,7 @@ constexpr int kDrawBlock = 256;
 #define NVC_DRAW_PER_THREAD 2
 #endif
 constexpr int kDPT = NVC_DRAW_PER_THREAD;
+constexpr uint32_t kDrawQueue = 128; // undecided draws per block that go through the shared queue (more: evaluated in place)
 constexpr uint32_t kDrawStage = 512 * kDPT > 1536 ? 1536 : 512 * kDPT; // commands staged per block before the coalesced write-out (static shared memory <= 48 KB)
 
 template <bool LATE, bool TASK>
@@ -191,11 +192,19 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	__shared__ uint32_t s_block_base, s_block_total;
 	__shared__ uint32_t s_is_last;
 	__shared__ uint32_t s_stage[kDrawStage * (TASK ? 5 : 6)];
+	// late pass, filtered occlusion: draws the filter could not decide, re-evaluated exactly by the first threads of the block
+	__shared__ float4 s_qsphere[LATE ? kDrawQueue : 1];
+	__shared__ uint8_t s_qresult[LATE ? kDrawQueue : 1];
+	__shared__ uint32_t s_qcount;
 
 	const NvcCullData& cd = p.cull;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	const bool packed = p.mesh_heads != nullptr;
+	if (LATE && tid == 0)
+		s_qcount = 0;
+	if (LATE)
+		__syncthreads();
 
 	// per-draw state of this thread's kDPT draws (draw k of the thread: block base + k * 256 + tid, so that every load
 	// instruction of a warp still covers 32 consecutive MeshDraws)
@@ -256,7 +265,83 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 				h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
 		}
 	}
-	// ---- phase 4: the tests ----
+	// ---- phase 4a: view-space sphere, frustum, occlusion ----
+	f3 centers[kDPT];
+	float radii[kDPT];
+	bool vis[kDPT];
+	int qslot[kDPT];
+	const bool filtered = LATE && p.use_filter != 0u && cd.occlusionEnabled == 1;
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		vis[k] = false;
+		qslot[k] = -1;
+		centers[k] = { 0.f, 0.f, 0.f };
+		radii[k] = 0.f;
+		if (reached[k])
+		{
+			f3 mc = { m0[k].x, m0[k].y, m0[k].z };
+			f3 rc = rotate_quat(mc, d1[k]);
+			f3 center = { __fadd_rn(__fmul_rn(rc.x, d0[k].w), d0[k].x), __fadd_rn(__fmul_rn(rc.y, d0[k].w), d0[k].y), __fadd_rn(__fmul_rn(rc.z, d0[k].w), d0[k].z) };
+			center = transform_point(cd.view, center);
+			float radius = __fmul_rn(m0[k].w, d0[k].w);
+			centers[k] = center;
+			radii[k] = radius;
+
+			bool visible = frustum_visible(cd, center, radius);
+			visible = visible || cd.cullingEnabled == 0; // :85
+
+			if (LATE && visible && cd.occlusionEnabled == 1) // :87
+			{
+				if (filtered)
+				{
+					// conservative filter on the EXACT centre (nvc_filter.cuh): E covers only rounding
+					const float u = 5.9604645e-8f;
+					const float E = nvf_fma(12.f * u, fmaxf(fmaxf(fabsf(center.x), fabsf(center.y)), fabsf(center.z)), nvf_fma(42.f * u, fabsf(radius), 7.8886091e-31f));
+					bool occ_vis, occ_hid;
+					if (p.hiz.fp)
+						filter_occlusion<true>(p.filter, cd, p.hiz, center.x, center.y, center.z, radius, E, p.filter.fr.x * E, occ_vis, occ_hid);
+					else
+						filter_occlusion<false>(p.filter, cd, p.hiz, center.x, center.y, center.z, radius, E, p.filter.fr.x * E, occ_vis, occ_hid);
+					if (occ_vis || occ_hid)
+						visible = occ_vis;
+					else
+					{
+						const uint32_t slot = atomicAdd(&s_qcount, 1u);
+						if (slot < kDrawQueue)
+						{
+							s_qsphere[slot] = make_float4(center.x, center.y, center.z, radius);
+							qslot[k] = int(slot);
+						}
+						else
+							visible = occlusion_visible<false>(cd, p.hiz, nullptr, true, center, radius); // queue full: in place
+					}
+				}
+				else
+					visible = occlusion_visible<false>(cd, p.hiz, nullptr, true, center, radius);
+			}
+			vis[k] = visible;
+		}
+	}
+	if (LATE && filtered)
+	{
+		// the undecided draws of the block, exactly, on its first threads (whole warps instead of scattered lanes)
+		__syncthreads();
+		const uint32_t nq = min(s_qcount, kDrawQueue);
+		if (tid < nq)
+		{
+			const float4 sp = s_qsphere[tid];
+			f3 c = { sp.x, sp.y, sp.z };
+			s_qresult[tid] = occlusion_visible<false>(cd, p.hiz, nullptr, true, c, sp.w) ? 1 : 0;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < kDPT; ++k)
+			if (qslot[k] >= 0)
+				vis[k] = s_qresult[qslot[k]] != 0;
+	}
+
+	// ---- phase 4b: LOD selection and the command counts ----
 	uint32_t thread_units = 0;
 #pragma unroll
 	for (int k = 0; k < kDPT; ++k)
@@ -270,17 +355,9 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 		{
 			const uint32_t meshIndex = d2[k].x;
 			const char* mp = reinterpret_cast<const char*>(p.meshes + meshIndex);
-			f3 mc = { m0[k].x, m0[k].y, m0[k].z };
-			f3 rc = rotate_quat(mc, d1[k]);
-			f3 center = { __fadd_rn(__fmul_rn(rc.x, d0[k].w), d0[k].x), __fadd_rn(__fmul_rn(rc.y, d0[k].w), d0[k].y), __fadd_rn(__fmul_rn(rc.z, d0[k].w), d0[k].z) };
-			center = transform_point(cd.view, center);
-			float radius = __fmul_rn(m0[k].w, d0[k].w);
-
-			bool visible = frustum_visible(cd, center, radius);
-			visible = visible || cd.cullingEnabled == 0; // :85
-
-			if (LATE && visible && cd.occlusionEnabled == 1) // :87
-				visible = occlusion_visible<false>(cd, p.hiz, nullptr, true, center, radius);
+			const f3 center = centers[k];
+			const float radius = radii[k];
+			const bool visible = vis[k];
 
 			// :108  (TASK_CULL == 1, config.h:8)
 			if (visible && (!LATE || cd.clusterOcclusionEnabled == 1 || dv[k] == 0 || cd.postPass != 0))

@@ -77,6 +77,7 @@ static bool exact_visible(const NvcCullData& cd, const HiZDesc& hiz, float4 d0, 
 struct Stats
 {
 	uint64_t items = 0, undecided = 0, wrong = 0, visible = 0, exact_only = 0;
+	uint64_t xc_items = 0, xc_undecided = 0, xc_wrong = 0; // occlusion stage alone on the EXACT centre (the drawcull use)
 	uint64_t stage[7] = { 0, 0, 0, 0, 0, 0, 0 };
 	double max_c_ratio = 0, max_uv_ratio = 0;
 };
@@ -326,6 +327,30 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 						fprintf(stderr, "MISMATCH %s: exact %d filter %d  c=(%g %g %g) r=%g E=%g aabb_e=(%g %g %g %g) aabb_a=(%g %g %g %g) level %d stage %d\n", sc.name, int(ve), int(fr.visible), dbg.c[0], dbg.c[1],
 						    dbg.c[2], dbg.r, dbg.E, ae[0], ae[1], ae[2], ae[3], dbg.aabb[0], dbg.aabb[1], dbg.aabb[2], dbg.aabb[3], dbg.level, dbg.stage);
 				}
+				// ---- the drawcull use of the occlusion stage: exact centre, rounding-only error scale ----
+				if (ce[0] == ce[0] && ce[1] == ce[1] && ce[2] == ce[2])
+				{
+					const float rr = __fmul_rn(half_bits_to_float(b0.y >> 16), d0.w);
+					const float E2 = 12.f * 5.9604645e-8f * fmaxf(fmaxf(fabsf(ce[0]), fabsf(ce[1])), fabsf(ce[2])) + 42.f * 5.9604645e-8f * fabsf(rr) + 7.8886091e-31f;
+					bool ov, oh;
+					FilterDebug keep = dbg;
+					filter_occlusion<false>(fc, cd, hiz, ce[0], ce[1], ce[2], rr, E2, fc.fr.x * E2, ov, oh, nullptr);
+					dbg = keep;
+					// the exact occlusion verdict for this sphere (independent of the frustum / cone outcome)
+					f3 c3 = { ce[0], ce[1], ce[2] };
+					float4 aabb;
+					bool ok2 = project_sphere(c3, rr, cd.znear, cd.P00, cd.P11, aabb);
+					int level = occlusion_mip(aabb, cd.pyramidWidth, cd.pyramidHeight, int(hiz.levels) - 1);
+					uint32_t w = max(1u, hiz.width >> level), h = max(1u, hiz.height >> level);
+					HiZLoadHost load = { hiz.texels, hiz.level_offset[level] };
+					float depth = sample_min(load, w, h, __fmul_rn(__fadd_rn(aabb.x, aabb.z), 0.5f), __fmul_rn(__fadd_rn(aabb.y, aabb.w), 0.5f));
+					bool occ_exact = !ok2 || __fdiv_rn(cd.znear, __fsub_rn(ce[2], rr)) > depth;
+					++st.xc_items;
+					if (!(ov || oh))
+						++st.xc_undecided;
+					else if (ov != occ_exact || (oh && occ_exact))
+						++st.xc_wrong;
+				}
 				// margins vs what they bound (only where the filter's domain conditions hold)
 				if (dbg.E == dbg.E && dbg.E < 1e30f && dbg.E > 0)
 				{
@@ -376,17 +401,19 @@ int main(int argc, char** argv)
 		for (const Stats& t : stats)
 		{
 			s.items += t.items, s.undecided += t.undecided, s.wrong += t.wrong, s.visible += t.visible, s.exact_only += t.exact_only;
+			s.xc_items += t.xc_items, s.xc_undecided += t.xc_undecided, s.xc_wrong += t.xc_wrong;
 			for (int k = 0; k < 7; ++k)
 				s.stage[k] += t.stage[k];
 			s.max_c_ratio = std::max(s.max_c_ratio, t.max_c_ratio);
 			s.max_uv_ratio = std::max(s.max_uv_ratio, t.max_uv_ratio);
 		}
 		printf("{\"scenario\": \"%s\", \"items\": %llu, \"wrong\": %llu, \"undecided\": %.6f, \"exact_only\": %.6f, \"visible\": %.4f, \"undecided_by_stage\": {\"frustum_cone\": %.6f, \"near_plane\": %.6f, \"domain\": %.6f, "
-		       "\"level\": %.6f, \"fits\": %.6f, \"footprint\": %.6f, \"depth\": %.6f}, \"max_center_err_over_E\": %.4f, \"max_uv_err_over_margin\": %.4f}\n",
+		       "\"level\": %.6f, \"fits\": %.6f, \"footprint\": %.6f, \"depth\": %.6f}, \"max_center_err_over_E\": %.4f, \"max_uv_err_over_margin\": %.4f, \"exact_centre_occlusion\": {\"items\": %llu, \"wrong\": %llu, \"undecided\": %.6f}}\n",
 		    sc.name, (unsigned long long)s.items, (unsigned long long)s.wrong, double(s.undecided) / double(s.items), double(s.exact_only) / double(s.items), double(s.visible) / double(s.items),
 		    double(s.stage[0]) / double(s.items), double(s.stage[1]) / double(s.items), double(s.stage[2]) / double(s.items), double(s.stage[3]) / double(s.items), double(s.stage[4]) / double(s.items),
-		    double(s.stage[5]) / double(s.items), double(s.stage[6]) / double(s.items), s.max_c_ratio, s.max_uv_ratio);
-		if (s.wrong || s.max_c_ratio >= 1.0 || s.max_uv_ratio >= 1.0)
+		    double(s.stage[5]) / double(s.items), double(s.stage[6]) / double(s.items), s.max_c_ratio, s.max_uv_ratio, (unsigned long long)s.xc_items, (unsigned long long)s.xc_wrong,
+		    s.xc_items ? double(s.xc_undecided) / double(s.xc_items) : 0.0);
+		if (s.wrong || s.xc_wrong || s.max_c_ratio >= 1.0 || s.max_uv_ratio >= 1.0)
 			rc = 1;
 	}
 	return rc;

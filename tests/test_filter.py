@@ -39,6 +39,7 @@ def test_filter_never_disagrees_with_the_exact_test(seed):
     by = {l["scenario"]: l for l in lines}
     for name, l in by.items():
         assert l["wrong"] == 0, (name, l)
+        assert l["exact_centre_occlusion"]["wrong"] == 0 and l["exact_centre_occlusion"]["items"] > 100000, (name, l)  # the drawcull use
         assert l["max_center_err_over_E"] < 1.0 and l["max_uv_err_over_margin"] < 1.0, (name, l)
     assert res.returncode == 0
     # the bench-like scene: only a few per cent may need the exact path; hostile transforms are sent there wholesale
