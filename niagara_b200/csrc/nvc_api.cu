@@ -197,6 +197,8 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		e = nvc::clustercull_filter_occupancy(&ctx->cluster_filter_blocks_early, &ctx->cluster_filter_blocks_late);
 	if (const char* env = getenv("NVC_CLUSTER_FILTER"))
 		ctx->cluster_filter = atoi(env) != 0;
+	if (const char* env = getenv("NVC_DRAW_FILTER"))
+		ctx->draw_filter = atoi(env) != 0;
 	if (e == cudaSuccess)
 		e = cudaDeviceSynchronize();
 	if (e != cudaSuccess)
@@ -350,7 +352,7 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 	bool need_hiz = late && cull->occlusionEnabled == 1;
 	if (!fill_hiz(hiz, p.hiz) && need_hiz)
 		return NVC_ERROR_INVALID_ARGUMENT;
-	if (need_hiz && ctx->cluster_filter)
+	if (need_hiz && ctx->cluster_filter && ctx->draw_filter)
 	{
 		// the occlusion stage as a conservative filter (same switch and the same validity domain as the cluster pass)
 		attach_footprints(ctx, hiz, p.hiz);

@@ -12,6 +12,7 @@ echo "== pytest -m gpu (filtered kernel default)"; timeout 900 python -m pytest 
 echo "== pending gpu tests"; timeout 600 python -m pytest tests/pending/gpu_end_to_end.py -q -o python_functions='pending_test_*' 2>&1 | tail -4 | tee $O/pytest_pending.txt
 X= q > $O/bench_filter.json; summ filter < $O/bench_filter.json; X=--no-extras
 NVC_PREPARE_HIZ=0 q > $O/bench_filter_nofp.json; summ filter_nofp < $O/bench_filter_nofp.json
+NVC_DRAW_FILTER=0 q > $O/bench_nodrawfilter.json; summ no_draw_filter < $O/bench_nodrawfilter.json
 NVC_CLUSTER_FILTER=0 q > $O/bench_exact.json; summ exact < $O/bench_exact.json
 for v in fb3 fb5 fb6 pdl dpt1 dpt4; do NVC_LIB_PATH=$PWD/niagara_b200/variant_$v.so q > $O/bench_$v.json; summ $v < $O/bench_$v.json; done
 NVC_CLUSTER_FILTER=0 NVC_LIB_PATH=$PWD/niagara_b200/variant_smem_items.so q > $O/bench_exact_smem_items.json; summ exact_smem_items < $O/bench_exact_smem_items.json
