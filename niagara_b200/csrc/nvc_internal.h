@@ -19,7 +19,7 @@ struct NvcContext
 	int sm_count = 0;
 	int cluster_blocks_early = 0, cluster_blocks_late = 0, cluster_blocks_late_staged = 0;
 	int cluster_filter_blocks_early = 0, cluster_filter_blocks_late = 0;
-	bool draw_filter = true;    // env NVC_DRAW_FILTER: filtered occlusion stage of the late drawcull (follows cluster_filter when that is off)
+	bool draw_filter = false;   // env NVC_DRAW_FILTER=1: filtered occlusion stage of the late drawcull (measured: no gain on B200, the pass is not issue bound)
 	bool cluster_filter = true; // nvc_set_cluster_filter / env NVC_CLUSTER_FILTER: filtered cluster kernel (default) or the exact one
 	uint32_t hiz_stage_budget = 0; // texels (24 KB) of coarse Hi-Z mips staged per CTA; 0 = off (env NVC_HIZ_STAGE_TEXELS)
 	NvcLimits limits = { NVC_TASK_WGLIMIT, NVC_CLUSTER_LIMIT };

@@ -54,6 +54,49 @@ __device__ __forceinline__ uint4 ldg_u4(const void* p)
 	return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
+// Read-once streams (meshlet bounds, task commands): read-only path with an L2 evict-first policy, so that the hundreds of MB a pass
+// streams through do not push the depth pyramid / footprint image (read at random, many times) out of L2.
+// NVC_STREAM_HINTS=0 builds plain read-only loads (A/B, profiles/r2_variants.md).
+#ifndef NVC_STREAM_HINTS
+#define NVC_STREAM_HINTS 1
+#endif
+#if NVC_STREAM_HINTS && !defined(NVC_EMU)
+__device__ __forceinline__ uint64_t stream_policy()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p, uint64_t pol)
+{
+	uint2 v;
+	asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p, uint64_t pol)
+{
+	uint32_t v;
+	asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+	return v;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const void* p, uint64_t pol)
+{
+	float4 v;
+	asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+	return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#else
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+__device__ __forceinline__ uint64_t stream_policy() { return 0; }
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p, uint64_t) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p, uint64_t) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ float4 ldg_stream_f4(const void* p, uint64_t) { return __ldg(reinterpret_cast<const float4*>(p)); }
+#endif
+
 // The numeric per-pass constants the per-item math reads.  They stay in the kernel-parameter constant bank: ptxas
 // re-materialises them as uniform loads (LDCU) inside the persistent loop; pinning them in registers was tried and is
 // not expressible at the PTX level (ptxas sees through register copies), see DESIGN.md "things that did not help".
@@ -174,11 +217,12 @@ __device__ __forceinline__ void hiz_stage_wait(uint64_t* bar)
 // ------------------------------------------------------------------------------------------------------
 
 constexpr int kDrawBlock = 256;
-// Draws per thread.  One draw per thread leaves every CTA with ~1.6 us of streaming between ~1.5 us of fixed latencies (the
-// dependent mesh-head load, the block's atomicAdd round trip, the completion ticket, CTA turnover); with DPT draws per thread
-// all DPT x 3 draw loads are in flight together and the fixed part is paid once per DPT x 256 draws.
+// Draws per thread.  The idea of DPT > 1: all DPT x 3 draw loads are in flight together and the fixed part of a CTA (dependent
+// mesh-head load, the block's atomicAdd round trip, completion ticket, turnover) is paid once per DPT x 256 draws.  Measured on
+// B200 (C4, 1M draws, profiles/r2_variants.md): early / late 31.5 / 38.9 us at DPT 1, 35.4 / 43.4 at 2, 42.9 / 61.0 at 4 — the
+// registers and the longer tail cost more than the amortisation wins, so the default stays at one draw per thread.
 #ifndef NVC_DRAW_PER_THREAD
-#define NVC_DRAW_PER_THREAD 2
+#define NVC_DRAW_PER_THREAD 1
 #endif
 constexpr int kDPT = NVC_DRAW_PER_THREAD;
 constexpr uint32_t kDrawQueue = 128; // undecided draws per block that go through the shared queue (more: evaluated in place)
@@ -1179,6 +1223,14 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 #ifndef NVC_FILTER_MIN_BLOCKS
 #define NVC_FILTER_MIN_BLOCKS 4
 #endif
+#ifndef NVC_FILTER_PIPELINE
+#define NVC_FILTER_PIPELINE 1
+#endif
+// NVC_FILTER_BATCH_PREFETCH=1: batch tickets are taken one batch ahead, and the next batch's task commands (then its draws) are
+// pulled into L2 while the current batch is evaluated, so the command -> draw -> record chain of the next batch starts from L2.
+#ifndef NVC_FILTER_BATCH_PREFETCH
+#define NVC_FILTER_BATCH_PREFETCH 0
+#endif
 constexpr int kFStage = 128;  // staged cluster indices per warp
 constexpr int kFQueue = 64;   // undecided items per warp (drained 32 at a time)
 
@@ -1215,6 +1267,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 	CmdRecord* const recs = sh.rec[warp];
 	uint32_t nst = 0, nq = 0;
 	uint32_t stat_items = 0, stat_undecided = 0; // per warp (uniform)
+	const uint64_t spol = stream_policy();
 
 	const uint32_t ncmd = p.command_count4[1] * 64u; // niagara.cpp:1599: commandId < X * 64
 	const uint32_t nbatch = (ncmd + 31u) / 32u;
@@ -1263,7 +1316,7 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		const uint4 q = queue[lane < n ? lane : 0u];
 		ItemRef r;
 		r.active = lane < n;
-		r.drawId = q.x;
+		r.drawId = r.active ? __ldg(&p.task_commands[q.w & 0xffffffu].drawId) : 0u; // the exact path needs the draw: re-read the command (rare)
 		r.mi = q.y;
 		r.mvi = q.z;
 		r.code = q.w & 0x7fffffffu;
@@ -1287,14 +1340,35 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		__syncwarp();
 	};
 
+#if NVC_FILTER_BATCH_PREFETCH
+	uint32_t batch = 0, batch_next = 0;
+	if (lane == 0)
+	{
+		batch = atomicAdd(&p.scratch->cluster_batch, 1u);
+		batch_next = atomicAdd(&p.scratch->cluster_batch, 1u);
+	}
+	batch = __shfl_sync(0xffffffffu, batch, 0);
+	batch_next = __shfl_sync(0xffffffffu, batch_next, 0);
+#endif
 	for (;;)
 	{
+#if NVC_FILTER_BATCH_PREFETCH
+		if (batch >= nbatch)
+			break;
+		uint32_t ticket = 0;
+		if (lane == 0)
+			ticket = atomicAdd(&p.scratch->cluster_batch, 1u); // consumed at the end of this batch
+		const uint32_t cid_next = batch_next * 32u + lane;
+		if (batch_next < nbatch && cid_next < ncmd)
+			prefetch_l2(p.task_commands + cid_next);
+#else
 		uint32_t batch = 0;
 		if (lane == 0)
 			batch = atomicAdd(&p.scratch->cluster_batch, 1u);
 		batch = __shfl_sync(0xffffffffu, batch, 0);
 		if (batch >= nbatch)
 			break;
+#endif
 
 		// ---- per command: load, visibility window, transform record ----
 		const uint32_t cid = batch * 32u + lane;
@@ -1306,9 +1380,9 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		if (cid < ncmd)
 		{
 			const uint32_t* cp = reinterpret_cast<const uint32_t*>(p.task_commands + cid);
-			const uint32_t c_draw = __ldg(cp + 0), c_task = __ldg(cp + 1);
-			c_count = min(__ldg(cp + 2), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
-			const uint32_t c_late = __ldg(cp + 3), c_mvo = __ldg(cp + 4);
+			const uint32_t c_draw = ldg_stream_u32(cp + 0, spol), c_task = ldg_stream_u32(cp + 1, spol);
+			c_count = min(ldg_stream_u32(cp + 2, spol), NVC_TASK_WGSIZE); // valid = mgi < taskCount with mgi < 64
+			const uint32_t c_late = ldg_stream_u32(cp + 3, spol), c_mvo = ldg_stream_u32(cp + 4, spol);
 			if (TASKOUT)
 				p.emit_counts[cid] = 0u; // sharedCount = 0 (:71); ordered before this warp's atomics by the __syncwarp below
 			if (c_count)
@@ -1363,20 +1437,22 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		__syncwarp(); // records (and the item table) visible to the whole warp
 		stat_items += total;
 
-		for (uint32_t base = 0; base < total; base += 32)
-		{
-			// ---- item -> (command lane j, rank inside the command) ----
-			const uint32_t item = base + lane;
+		// ---- item -> (command lane j, meshlet lane mgi) and the meshlet's loads, for the chunk starting at `b` ----
+		// Software pipeline (NVC_FILTER_PIPELINE): the loads of chunk k+1 are issued before chunk k is evaluated, so their DRAM
+		// latency (~1000 cycles under load: 23% of the stall samples of the unpipelined kernel, profiles/r2_*) overlaps ~260
+		// instructions of arithmetic.  Carried state: one packed word + the 12 loaded bytes.
+		auto fetch = [&](uint32_t b, uint32_t& jm, uint2& b0, uint32_t& b1) {
+			const uint32_t item = b + lane;
 			const bool active = item < total;
 			uint32_t j;
 			if (uniform)
 				j = __umulhi(item, recip);
 			else if (nz_prefix)
 			{
-				uint32_t rel = excl - base;
+				uint32_t rel = excl - b;
 				uint32_t hbit = (eff_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
 				uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
-				uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && incl <= base));
+				uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && incl <= b));
 				j = first + __popc(heads & lanemask_le());
 			}
 			else
@@ -1392,22 +1468,52 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			}
 			j &= 31u;
 			uint32_t mgi = uniform ? item - j * count0 : item - __shfl_sync(0xffffffffu, excl, j);
-
-			// ---- the command's record, the meshlet, its visibility bit ----
-			const CmdRecord& rec = recs[active ? j : 0u];
-			const uint4 ids = rec.ids;
+			if (!active)
+				j = 0u;
+			const CmdRecord& rec = recs[j];
 			if (alive_flatten) // the rank-th SET bit of the window is the meshlet's lane index
-				mgi = !active ? 0u : use_table ? uint32_t(sh.items[warp][item]) : select_bit64(ids.z, ids.w, mgi);
+				mgi = !active ? 0u : use_table ? uint32_t(sh.items[warp][item]) : select_bit64(rec.ids.z, rec.ids.w, mgi);
 			mgi &= 63u;
-			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
-			uint2 b0 = make_uint2(0u, 0u);
-			uint32_t b1 = 0u;
+			jm = j | (mgi << 8) | (active ? 0x80000000u : 0u);
+			b0 = make_uint2(0u, 0u);
+			b1 = 0u;
 			if (active)
 			{
-				const char* mp = reinterpret_cast<const char*>(p.meshlets + mi);
-				b0 = __ldg(reinterpret_cast<const uint2*>(mp));
-				b1 = __ldg(reinterpret_cast<const uint32_t*>(mp + 8));
+				const char* mp = reinterpret_cast<const char*>(p.meshlets + (rec.ids.x + mgi));
+				b0 = ldg_stream_u2(mp, spol);
+				b1 = ldg_stream_u32(mp + 8, spol);
 			}
+		};
+
+		uint32_t n_jm = 0, n_b1 = 0;
+		uint2 n_b0 = make_uint2(0u, 0u);
+#if NVC_FILTER_PIPELINE
+		if (total)
+			fetch(0u, n_jm, n_b0, n_b1);
+#endif
+		for (uint32_t base = 0; base < total; base += 32)
+		{
+#if NVC_FILTER_PIPELINE
+			const uint32_t jm = n_jm, b1 = n_b1;
+			const uint2 b0 = n_b0;
+			if (base + 32u < total)
+				fetch(base + 32u, n_jm, n_b0, n_b1);
+#else
+			fetch(base, n_jm, n_b0, n_b1);
+			const uint32_t jm = n_jm, b1 = n_b1;
+			const uint2 b0 = n_b0;
+#endif
+			const bool active = (jm >> 31) != 0u;
+			const uint32_t j = jm & 31u, mgi = (jm >> 8) & 63u;
+#if NVC_FILTER_BATCH_PREFETCH
+			if (base == 96u && batch_next < nbatch && cid_next < ncmd) // the commands have reached L2 by now: pull the draws
+				prefetch_l2(p.draws + __ldg(&p.task_commands[cid_next].drawId));
+#endif
+
+			// ---- the command's record, its visibility bit ----
+			const CmdRecord& rec = recs[j];
+			const uint4 ids = rec.ids;
+			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
 			const float4 row0 = rec.row0, row1 = rec.row1, row2 = rec.row2, aux = rec.aux;
 			const uint32_t flags = __float_as_uint(aux.w);
 
@@ -1437,8 +1543,8 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			const uint32_t umask = __ballot_sync(0xffffffffu, !decided);
 			if (umask)
 			{
-				if (!decided) // the exact path needs the draw: re-read it from the command (rare)
-					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(__ldg(&p.task_commands[code & 0xffffffu].drawId), mi, mvi, code | ((flags & kRecLate) << 31));
+				if (!decided)
+					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(0u, mi, mvi, code | ((flags & kRecLate) << 31));
 				nq += __popc(umask);
 				stat_undecided += __popc(umask);
 			}
@@ -1446,6 +1552,10 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 			if (nq >= 32u)
 				drain(32u);
 		}
+#if NVC_FILTER_BATCH_PREFETCH
+		batch = batch_next;
+		batch_next = __shfl_sync(0xffffffffu, ticket, 0);
+#endif
 	}
 	while (nq)
 		drain(min(nq, 32u));
@@ -2203,39 +2313,75 @@ static cudaError_t launch_pdl(void (*kernel)(P, Extra...), dim3 grid, dim3 block
 
 // ------------------------------------------------------------------------------------------------------
 // footprint image: F_l(i, j) = min over the clamped 2 x 2 footprint (i, i+1) x (j, j+1) of mip l, i in [-1, w-1]
-// (see HiZDesc).  One thread per entry over all levels; the pyramid was just written and is read from L2.
-// With it a sampler access whose four texels all count (fract != 0 on both axes — the only case the filter decides)
-// is ONE load instead of four scattered ones.
+// (see HiZDesc).  With it a sampler access whose four texels all count (fract != 0 on both axes — the only case the
+// filter decides) is ONE load instead of four scattered ones.
+// A CTA owns kFpRows consecutive rows of one level's image and walks them in x: per column it reads the two texels of
+// kFpRows + 1 pyramid rows (written by the previous launch, served by L2 / L1), takes the horizontal minima once and
+// combines vertically adjacent ones — 10 loads and ~50 instructions for 4 entries.  (The first version, one thread
+// per entry with a level search and an integer division, was instruction bound at 24.5 us for a 2048^2 pyramid;
+// profiles/r2_variants.md.)
 // ------------------------------------------------------------------------------------------------------
+constexpr uint32_t kFpRows = 4;
+
+__host__ __device__ __forceinline__ uint32_t footprint_row_groups(uint32_t h)
+{
+	return (h + 1u + kFpRows - 1u) / kFpRows;
+}
+
 __global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float* __restrict__ fp, uint32_t total)
 {
 	NVC_GRID_DEPENDENCY_SYNC();
-	const uint32_t g = blockIdx.x * 256u + threadIdx.x;
-	if (g >= total)
-		return;
-	uint32_t l = 0;
-	while (l + 1 < hz.levels && g >= hz.fp_offset[l + 1])
+	(void)total;
+	// block -> (level, row group): uniform walk over <= 16 levels
+	uint32_t l = 0, rg = blockIdx.x;
+	for (;;)
+	{
+		const uint32_t n = footprint_row_groups(max(1u, hz.height >> l));
+		if (rg < n || l + 1u >= hz.levels)
+			break;
+		rg -= n;
 		++l;
+	}
 	const uint32_t w = max(1u, hz.width >> l), h = max(1u, hz.height >> l);
-	const uint32_t i = g - hz.fp_offset[l];
 	const uint32_t pitch = w + 1u;
-	const uint32_t iy = i / pitch, ix = i - iy * pitch;
-	const uint32_t x0 = ix ? ix - 1u : 0u, x1 = min(ix, w - 1u);
-	const uint32_t y0 = iy ? iy - 1u : 0u, y1 = min(iy, h - 1u);
-	const float* t = hz.texels + hz.level_offset[l];
-	// written by pyramid_kernel in the previous launch: plain loads are coherent across kernel boundaries
-	const float a = __ldg(t + y0 * w + x0), b = __ldg(t + y0 * w + x1), c = __ldg(t + y1 * w + x0), d = __ldg(t + y1 * w + x1);
-	fp[g] = fminf(fminf(a, b), fminf(c, d));
+	const uint32_t iy0 = rg * kFpRows;
+	if (iy0 > h)
+		return;
+	const float* __restrict__ t = hz.texels + hz.level_offset[l];
+	float* __restrict__ out = fp + hz.fp_offset[l] + iy0 * pitch;
+	// pyramid rows clamp(iy0 - 1 + k, 0, h - 1), k = 0..kFpRows
+	uint32_t rowoff[kFpRows + 1];
+#pragma unroll
+	for (uint32_t k = 0; k <= kFpRows; ++k)
+	{
+		const uint32_t iy = iy0 + k; // row iy - 1, clamped
+		rowoff[k] = min(iy ? iy - 1u : 0u, h - 1u) * w;
+	}
+	for (uint32_t ix = threadIdx.x; ix < pitch; ix += 256u)
+	{
+		const uint32_t x0 = ix ? ix - 1u : 0u, x1 = min(ix, w - 1u);
+		float m[kFpRows + 1];
+#pragma unroll
+		for (uint32_t k = 0; k <= kFpRows; ++k)
+			m[k] = fminf(__ldg(t + rowoff[k] + x0), __ldg(t + rowoff[k] + x1));
+#pragma unroll
+		for (uint32_t k = 0; k < kFpRows; ++k)
+			if (iy0 + k <= h)
+				out[k * pitch + ix] = fminf(m[k], m[k + 1]);
+	}
 }
 
 cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cudaStream_t stream)
 {
 	if (total == 0)
 		return cudaSuccess;
+	uint32_t blocks = 0;
+	for (uint32_t l = 0; l < hiz.levels; ++l)
+		blocks += footprint_row_groups(hiz.height >> l ? hiz.height >> l : 1u);
 #if NVC_PDL && !defined(NVC_EMU)
-	return launch_pdl(footprint_kernel, dim3((total + 255u) / 256u), dim3(256), 0, stream, hiz, fp, total);
+	return launch_pdl(footprint_kernel, dim3(blocks), dim3(256), 0, stream, hiz, fp, total);
 #else
-	footprint_kernel<<<(total + 255u) / 256u, 256, 0, stream>>>(hiz, fp, total);
+	footprint_kernel<<<blocks, 256, 0, stream>>>(hiz, fp, total);
 	return cudaGetLastError();
 #endif
 }
