@@ -28,22 +28,43 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "niagara_b200", "libniagara_cull.so")], cwd=tmp, capture_output=True)
     cubin = os.path.join(tmp, "nvc_kernels.sm_100a.cubin")
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
     # split into functions
     funcs = defaultdict(list)
-    cur, line = None, None
+    cur, line, last_frame, chain_open = None, None, None, False
+
+    def helper(fl):
+        f, n = fl
+        if f == "nvc_filter.cuh":
+            return n < 93
+        if f == "nvc_math.cuh":
+            return n < 50
+        return f not in ("nvc_kernels.cu", "nvc_math.cuh", "nvc_tma.cuh", "nvc_cook.cuh", "nvc_math2.cuh")
+
     for l in dis:
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
         if m:
             cur = m.group(1)
             continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        m = re.search(r'//## File "([^"]+)", line (\d+)( inlined at "([^"]+)", line (\d+))?', l)
         if m:
-            line = (os.path.basename(m.group(1)), int(m.group(2)))
+            # -gi prints the inlining chain innermost first, one line per frame; an instruction is attributed to the first
+            # frame that is not a one-line helper (nvf_fma / nvf_rcp / half conversion / CUDA headers)
+            here = (os.path.basename(m.group(1)), int(m.group(2)))
+            if not chain_open:
+                line, chain_open = None, True
+            if line is None and not helper(here):
+                line = here
+            if line is None and m.group(4):
+                up = (os.path.basename(m.group(4)), int(m.group(5)))
+                if not helper(up):
+                    line = up
+            last_frame = here
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if m and cur:
-            funcs[cur].append((line, m.group(2).strip()))
+            funcs[cur].append((line or last_frame, m.group(2).strip()))
+            chain_open = False
     # pick the function whose instruction count matches
     cand = [f for f, ins in funcs.items() if len(ins) == len(body)]
     want = rows[idx[k]][1]
