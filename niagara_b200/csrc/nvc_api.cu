@@ -111,6 +111,7 @@ void attach_footprints(const NvcContext* ctx, const NvcHiZ* in, nvc::HiZDesc& ou
 	if (!ctx->hiz_fp || !ctx->hiz_fp_valid || !in || ctx->hiz_fp_key != in->texels || ctx->hiz_fp_width != in->width || ctx->hiz_fp_height != in->height || ctx->hiz_fp_levels != in->levels)
 		return;
 	out.fp = ctx->hiz_fp;
+	out.fp_first = ctx->hiz_fp_first;
 	memcpy(out.fp_offset, ctx->hiz_fp_offset, sizeof(out.fp_offset));
 }
 
@@ -195,6 +196,8 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 	}
 	if (e == cudaSuccess)
 		e = nvc::clustercull_filter_occupancy(&ctx->cluster_filter_blocks_early, &ctx->cluster_filter_blocks_late);
+	if (e == cudaSuccess)
+		e = nvc::drawcull_occupancy(ctx->draw_blocks);
 	if (const char* env = getenv("NVC_CLUSTER_FILTER"))
 		ctx->cluster_filter = atoi(env) != 0;
 	if (const char* env = getenv("NVC_DRAW_FILTER"))
@@ -219,6 +222,9 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		ctx->cluster_filter_blocks_early = 1;
 	if (ctx->cluster_filter_blocks_late < 1)
 		ctx->cluster_filter_blocks_late = 1;
+	for (int i = 0; i < 4; ++i)
+		if (ctx->draw_blocks[i >> 1][i & 1] < 1)
+			ctx->draw_blocks[i >> 1][i & 1] = 1;
 
 	*out_ctx = ctx;
 	return NVC_OK;
@@ -360,7 +366,8 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 		p.use_filter = (p.filter.enabled && p.filter.occ_ok) ? 1u : 0u;
 	}
 
-	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, static_cast<cudaStream_t>(stream));
+	const uint32_t max_blocks = uint32_t(ctx->sm_count) * uint32_t(ctx->draw_blocks[late != 0][task != 0]);
+	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, max_blocks, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_drawcull");
 }
 
@@ -515,6 +522,7 @@ NVC_API int nvc_depth_pyramid(NvcContext* ctx, void* stream, const float* depth,
 	{
 		// derived footprint image of the pyramid just built (nvc_prepare_hiz), one more launch on the same stream
 		memcpy(p.hiz.fp_offset, ctx->hiz_fp_offset, sizeof(p.hiz.fp_offset));
+		p.hiz.fp_first = ctx->hiz_fp_first;
 		e = nvc::launch_footprint(p.hiz, ctx->hiz_fp, ctx->hiz_fp_total, static_cast<cudaStream_t>(stream));
 		ctx->hiz_fp_valid = e == cudaSuccess;
 	}
@@ -540,13 +548,18 @@ NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz)
 	if (!hiz->texels || hiz->levels == 0 || hiz->levels > NVC_MAX_HIZ_LEVELS || hiz->width == 0 || hiz->height == 0 || hiz->width > 65536 || hiz->height > 65536)
 		return NVC_ERROR_INVALID_ARGUMENT;
 	uint64_t total = 0;
+	if (const char* env = getenv("NVC_FP_FIRST_LEVEL"))
+		ctx->hiz_fp_first = uint32_t(strtoul(env, nullptr, 10));
+	if (ctx->hiz_fp_first >= hiz->levels)
+		ctx->hiz_fp_first = hiz->levels - 1; // at least the coarsest mip has an image
 	for (uint32_t l = 0; l < hiz->levels; ++l)
 	{
 		uint32_t w = hiz->width >> l, h = hiz->height >> l;
 		w = w ? w : 1;
 		h = h ? h : 1;
 		ctx->hiz_fp_offset[l] = uint32_t(total);
-		total += uint64_t(w + 1) * (h + 1);
+		if (l >= ctx->hiz_fp_first)
+			total += uint64_t(w + 1) * (h + 1);
 	}
 	if (total >= (1ull << 31))
 		return NVC_ERROR_UNSUPPORTED;

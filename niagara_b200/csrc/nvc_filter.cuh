@@ -288,7 +288,7 @@ __device__ __forceinline__ void filter_occlusion(const FilterConsts& fc, const N
 	const float wmax = wf - 1.f, hmax = hf2 - 1.f;
 	const uint32_t wi = max(1u, hiz.width >> level);
 	float depth;
-	if (FP)
+	if (FP && level >= hiz.fp_first)
 	{
 		// fract != 0 on both axes here, so all four texels of the footprint count: one load from the footprint image
 		const uint32_t ix = (uint32_t)(fminf(fmaxf(flx, -1.f), wmax) + 1.f), iy = (uint32_t)(fminf(fmaxf(fly, -1.f), hmax) + 1.f);

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace nvc
 {
 
@@ -228,8 +230,20 @@ constexpr int kDPT = NVC_DRAW_PER_THREAD;
 constexpr uint32_t kDrawQueue = 128; // undecided draws per block that go through the shared queue (more: evaluated in place)
 constexpr uint32_t kDrawStage = 512 * kDPT > 1536 ? 1536 : 512 * kDPT; // commands staged per block before the coalesced write-out (static shared memory <= 48 KB)
 
+// Persistent grid (NVC_DRAW_MIN_BLOCKS CTAs per SM, launch_drawcull): a CTA walks tiles of 256 draws.  The pass is a chain of
+// dependent DRAM round trips (MeshDraw -> mesh head -> block atomic -> write-out), so the next tile's MeshDraw / dvb loads are
+// issued before the current tile is evaluated and its mesh heads as soon as the current tile's arithmetic is done: the loads
+// of tile k+1 travel while tile k computes, scans and writes (profiles/r2_variants.md: one tile per CTA = 29 / 34 us, latency bound
+// at 38 % of the HBM peak).
+#ifndef NVC_DRAW_MIN_BLOCKS
+#define NVC_DRAW_MIN_BLOCKS 4
+#endif
+#ifndef NVC_DRAW_PERSISTENT
+#define NVC_DRAW_PERSISTENT 1
+#endif
+
 template <bool LATE, bool TASK>
-__global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
+__global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kernel(const DrawCullParams p)
 {
 	NVC_GRID_DEPENDENCY_SYNC(); // nothing of the previous pass (scratch counters, dvb, pyramid) is touched before this point
 	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
@@ -245,13 +259,60 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	const bool packed = p.mesh_heads != nullptr;
+	const uint32_t ntiles = (cd.drawCount + kDrawBlock * kDPT - 1) / (kDrawBlock * kDPT);
 	if (LATE && tid == 0)
 		s_qcount = 0;
 	if (LATE)
 		__syncthreads();
 
-	// per-draw state of this thread's kDPT draws (draw k of the thread: block base + k * 256 + tid, so that every load
-	// instruction of a warp still covers 32 consecutive MeshDraws)
+	// ---- the prefetched tile: MeshDraw, draw visibility, mesh head of this thread's kDPT draws (draw k of the thread: tile base
+	// + k * 256 + tid, so that every load instruction of a warp covers 32 consecutive MeshDraws) ----
+	float4 n_d0[kDPT], n_d1[kDPT], n_m0[kDPT];
+	uint4 n_d2[kDPT], n_h1[kDPT];
+	uint32_t n_dv[kDPT];
+	bool n_reached[kDPT];
+	auto fetch_draws = [&](uint32_t tile) {
+#pragma unroll
+		for (int k = 0; k < kDPT; ++k)
+		{
+			const uint32_t di = (tile * kDPT + k) * kDrawBlock + tid;
+			n_d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+			n_d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
+			n_d2[k] = make_uint4(0u, 0u, ~cd.postPass, 0u);
+			n_dv[k] = 0u;
+			if (tile < ntiles && di < cd.drawCount)
+			{
+				const char* dp = reinterpret_cast<const char*>(p.draws + di);
+				n_d0[k] = ldg_f4(dp);      // position.xyz, scale
+				n_d1[k] = ldg_f4(dp + 16); // orientation
+				n_d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
+				n_dv[k] = p.draw_visibility[di]; // (read for every draw: independent of the MeshDraw loads, one round trip less)
+			}
+		}
+	};
+	auto fetch_heads = [&]() {
+#pragma unroll
+		for (int k = 0; k < kDPT; ++k)
+		{
+			n_reached[k] = n_d2[k].z == cd.postPass && (LATE || n_dv[k] != 0u); // :63, :67 (out-of-range lanes carry ~postPass)
+			n_m0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+			n_h1[k] = make_uint4(0u, 0u, 0u, 0u);
+			if (n_reached[k])
+			{
+				const char* mp = reinterpret_cast<const char*>(p.meshes + n_d2[k].x);
+				// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
+				const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + n_d2[k].x) : mp;
+				n_m0[k] = ldg_f4(hp); // center.xyz, radius
+				if (packed)
+					n_h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
+			}
+		}
+	};
+	fetch_draws(blockIdx.x);
+	fetch_heads();
+
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
 	uint32_t di[kDPT];
 	float4 d0[kDPT], d1[kDPT];
 	uint4 d2[kDPT];
@@ -260,55 +321,18 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	bool emit[kDPT];
 	uint32_t units[kDPT]; // commands this draw appends: taskGroups (TASK) or 1
 	uint32_t lodIndex[kDPT], meshletOffset[kDPT], meshletCount[kDPT];
-
-	// ---- phase 1: all MeshDraw loads ----
-#pragma unroll
-	for (int k = 0; k < kDPT; ++k)
-	{
-		di[k] = (blockIdx.x * kDPT + k) * kDrawBlock + tid;
-		d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-		d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
-		d2[k] = make_uint4(0u, 0u, 0u, 0u);
-		reached[k] = false;
-		if (di[k] < cd.drawCount)
-		{
-			const char* dp = reinterpret_cast<const char*>(p.draws + di[k]);
-			d0[k] = ldg_f4(dp);      // position.xyz, scale
-			d1[k] = ldg_f4(dp + 16); // orientation
-			d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
-			reached[k] = d2[k].z == cd.postPass; // :63
-		}
-	}
-	// ---- phase 2: draw visibility ----
-#pragma unroll
-	for (int k = 0; k < kDPT; ++k)
-	{
-		dv[k] = 0;
-		if (reached[k])
-		{
-			dv[k] = p.draw_visibility[di[k]];
-			if (!LATE && dv[k] == 0) // :67
-				reached[k] = false;
-		}
-	}
-	// ---- phase 3: mesh heads (dependent on meshIndex) ----
 	float4 m0[kDPT];
 	uint4 h1[kDPT];
 #pragma unroll
 	for (int k = 0; k < kDPT; ++k)
 	{
-		m0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-		h1[k] = make_uint4(0u, 0u, 0u, 0u);
-		if (reached[k])
-		{
-			const char* mp = reinterpret_cast<const char*>(p.meshes + d2[k].x);
-			// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
-			const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + d2[k].x) : mp;
-			m0[k] = ldg_f4(hp); // center.xyz, radius
-			if (packed)
-				h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
-		}
+		di[k] = (tile * kDPT + k) * kDrawBlock + tid;
+		d0[k] = n_d0[k], d1[k] = n_d1[k], d2[k] = n_d2[k], dv[k] = n_dv[k], m0[k] = n_m0[k], h1[k] = n_h1[k];
+		reached[k] = n_reached[k];
 	}
+#if NVC_DRAW_PERSISTENT
+	fetch_draws(tile + gridDim.x); // in flight while this tile is evaluated
+#endif
 	// ---- phase 4a: view-space sphere, frustum, occlusion ----
 	f3 centers[kDPT];
 	float radii[kDPT];
@@ -451,6 +475,9 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 	if (lane == 31)
 		s_warp_total[warp] = incl;
 	__syncthreads();
+#if NVC_DRAW_PERSISTENT
+	fetch_heads(); // the next tile's MeshDraws have had this tile's arithmetic to arrive; its heads travel during the scan / write-out
+#endif
 	if (warp == 0)
 	{
 		uint32_t t = lane < kDrawBlock / 32 ? s_warp_total[lane] : 0;
@@ -539,6 +566,15 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 				mc[i] = s_stage[i];
 		}
 	}
+
+	if (LATE && tid == 0)
+		s_qcount = 0;
+	__syncthreads(); // the tile's shared state (scan totals, staged commands, queue) is free again
+#if !NVC_DRAW_PERSISTENT
+	fetch_draws(tile + gridDim.x);
+	fetch_heads();
+#endif
+	} // tiles
 
 	// ---- last-block epilogue: tasksubmit.comp.glsl:27-47 (TASK) / publish the count (draw path) ----
 	__threadfence();
@@ -1224,36 +1260,42 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 #define NVC_FILTER_MIN_BLOCKS 4
 #endif
 #ifndef NVC_FILTER_PIPELINE
-#define NVC_FILTER_PIPELINE 1
+#define NVC_FILTER_PIPELINE 2
 #endif
 // NVC_FILTER_BATCH_PREFETCH=1: batch tickets are taken one batch ahead, and the next batch's task commands (then its draws) are
 // pulled into L2 while the current batch is evaluated, so the command -> draw -> record chain of the next batch starts from L2.
 #ifndef NVC_FILTER_BATCH_PREFETCH
 #define NVC_FILTER_BATCH_PREFETCH 0
 #endif
-constexpr int kFStage = 128;  // staged cluster indices per warp
-constexpr int kFQueue = 64;   // undecided items per warp (drained 32 at a time)
+constexpr int kFFlush = 128;           // cluster indices written out per flush: ONE atomicAdd + four coalesced 128-byte stores per warp
+constexpr int kFStage = kFFlush + 32;  // staged cluster indices per warp (a chunk appends <= 32 before the next flush)
+constexpr int kFQueue = 64;            // undecided items per warp (drained 32 at a time)
+// early pass: (command lane, meshlet lane) of every flattened item of one (sub-)batch; batches with more set bits are
+// processed as four sub-batches of 8 commands (<= 512 items)
+constexpr uint32_t kFItems = 896;
 
-constexpr uint32_t kFItems = 1024; // early pass: set-bit positions of one batch that fit the per-warp table (larger batches: select_bit64)
-
+// One block of shared memory per warp: every field sits at a compile-time offset from the warp's base address.
 template <bool LATE>
-struct FilterShared
+struct alignas(16) FilterWarpShared
 {
-	CmdRecord rec[kClusterWarps][32];
-	uint4 queue[kClusterWarps][kFQueue];
-	uint32_t stage[kClusterWarps][kFStage];
-	uint8_t items[kClusterWarps][LATE ? 16 : kFItems]; // early pass with visibility tracking: meshlet lane (0..63) of every flattened item
+	CmdRecord rec[32];
+	uint4 queue[kFQueue];
+	uint32_t stage[kFStage];
+	uint16_t items[LATE ? 8 : kFItems];
 };
+static_assert(sizeof(FilterWarpShared<false>) * (256 / 32) + 16 <= 48 * 1024, "static shared memory");
 
 // TRACK: clusterOcclusionEnabled == 1 && postPass == 0 (the main passes of a frame) as a compile-time fact; the generic
 // instantiation reads the flags at run time.
 // TASKOUT: meshlet.task.glsl's submission mode — survivors go to their command's payload (slot from an atomic counter per
 // command, aggregated per warp; the reference's order inside a payload is unspecified too: atomicAdd(sharedCount), :137)
 // and the count to emit_counts[command] instead of cib / ccb.
-template <bool LATE, bool FP, bool TRACK, bool TASKOUT>
+// BF: clusterBackfaceEnabled as a compile-time fact (0 / 1; -1 = read at run time).  With it the cone arithmetic is
+// scheduled between the Hi-Z load and its use instead of behind a branch.
+template <bool LATE, bool FP, bool TRACK, bool TASKOUT, int BF>
 __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
 {
-	__shared__ FilterShared<LATE> sh;
+	__shared__ FilterWarpShared<LATE> sh_all[kClusterWarps];
 	__shared__ uint32_t s_is_last;
 
 	NVC_GRID_DEPENDENCY_SYNC();
@@ -1262,9 +1304,10 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 	const FilterConsts& fc = p.filter;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
-	uint32_t* const stage = sh.stage[warp];
-	uint4* const queue = sh.queue[warp];
-	CmdRecord* const recs = sh.rec[warp];
+	FilterWarpShared<LATE>& sh = sh_all[warp];
+	uint32_t* const stage = sh.stage;
+	uint4* const queue = sh.queue;
+	CmdRecord* const recs = sh.rec;
 	uint32_t nst = 0, nq = 0;
 	uint32_t stat_items = 0, stat_undecided = 0; // per warp (uniform)
 	const uint64_t spol = stream_policy();
@@ -1274,8 +1317,31 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 	const bool track = TRACK || (cd.clusterOcclusionEnabled == 1 && cd.postPass == 0); // clustercull.comp.glsl:86
 	const bool track_late = LATE && (TRACK || cd.clusterOcclusionEnabled == 1);
 	const bool bits_known = TRACK || cd.postPass == 0;
-	const bool backface = cd.clusterBackfaceEnabled != 0;
+	const bool backface = BF >= 0 ? BF != 0 : cd.clusterBackfaceEnabled != 0;
 	const bool occlusion = LATE && (TRACK || cd.clusterOcclusionEnabled == 1);
+
+	// cluster indices (:133-139): staged per warp, written out 128 at a time
+	auto flush_full = [&]() {
+		__syncwarp();
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(&p.scratch->cluster_counter, uint32_t(kFFlush)); // :135, aggregated
+		base = __shfl_sync(0xffffffffu, base, 0) + lane;
+#pragma unroll
+		for (int k = 0; k < kFFlush / 32; ++k)
+		{
+			const uint32_t v = stage[k * 32 + lane];
+			if (base + k * 32 < p.cluster_limit) // :137
+				p.cluster_indices[base + k * 32] = v;
+		}
+		const uint32_t rest = nst - uint32_t(kFFlush); // < 32
+		const uint32_t t = stage[kFFlush + lane];
+		__syncwarp();
+		if (lane < rest)
+			stage[lane] = t;
+		nst = rest;
+		__syncwarp();
+	};
 
 	// bookkeeping of one group of <= 32 verdicts: visibility bits (late, :126-131) and compaction (:133-139)
 	auto commit = [&](bool active, bool visible, bool skip, bool oldbit, uint32_t mvi, uint32_t code) {
@@ -1302,11 +1368,11 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		}
 		else if (n)
 		{
-			if (nst + n > uint32_t(kFStage))
-				flush_stage(p, stage, nst);
 			if (out)
 				stage[nst + __popc(omask & lanemask_lt())] = code;
 			nst += n;
+			if (nst >= uint32_t(kFFlush))
+				flush_full();
 		}
 	};
 
@@ -1418,139 +1484,189 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clusterc
 		}
 		const uint32_t excl = incl - eff_count;
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		const uint32_t nz = __ballot_sync(0xffffffffu, eff_count != 0);
-		const bool nz_prefix = (nz & (nz + 1u)) == 0;
-		const uint32_t count0 = __shfl_sync(0xffffffffu, eff_count, 0);
-		const bool uniform = count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0);
-		const uint32_t recip = uniform ? 0xffffffffu / count0 + 1u : 0u;
-		// early pass: every command lane lists the positions of its set bits ONCE; its items then read one byte instead of
-		// selecting the rank-th set bit of the 64-bit window (25 instructions) per item
-		const bool use_table = alive_flatten && total <= kFItems;
-		if (use_table)
-		{
-			uint8_t* tbl = sh.items[warp] + excl;
-			for (uint32_t m = amask_lo; m; m &= m - 1u)
-				*tbl++ = uint8_t(__ffs(int(m)) - 1);
-			for (uint32_t m = amask_hi; m; m &= m - 1u)
-				*tbl++ = uint8_t(32 + __ffs(int(m)) - 1);
-		}
-		__syncwarp(); // records (and the item table) visible to the whole warp
 		stat_items += total;
 
-		// ---- item -> (command lane j, meshlet lane mgi) and the meshlet's loads, for the chunk starting at `b` ----
-		// Software pipeline (NVC_FILTER_PIPELINE): the loads of chunk k+1 are issued before chunk k is evaluated, so their DRAM
-		// latency (~1000 cycles under load: 23% of the stall samples of the unpipelined kernel, profiles/r2_*) overlaps ~260
-		// instructions of arithmetic.  Carried state: one packed word + the 12 loaded bytes.
-		auto fetch = [&](uint32_t b, uint32_t& jm, uint2& b0, uint32_t& b1) {
-			const uint32_t item = b + lane;
-			const bool active = item < total;
-			uint32_t j;
-			if (uniform)
-				j = __umulhi(item, recip);
-			else if (nz_prefix)
+		// ---- one run of flattened items [0, run_total): chunks of 32, software pipelined ----
+		// TABLE: item -> (command lane, meshlet lane) comes from sh.items (early pass, set bits only); otherwise it is derived
+		// from the scan (`run_excl`: exclusive offsets of this run's commands): multiply-high for uniform batches, head-bit
+		// popcount when the non-empty commands form a prefix, binary search over the scan else.
+		auto run = [&](auto table_tag, uint32_t run_total, uint32_t run_excl, uint32_t run_incl) {
+			constexpr bool TABLE = decltype(table_tag)::value;
+			uint32_t count0 = 0, recip = 0;
+			bool uniform = false, nz_prefix = false;
+			if (!TABLE)
 			{
-				uint32_t rel = excl - b;
-				uint32_t hbit = (eff_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
-				uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
-				uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && incl <= b));
-				j = first + __popc(heads & lanemask_le());
+				const uint32_t nz = __ballot_sync(0xffffffffu, eff_count != 0);
+				nz_prefix = (nz & (nz + 1u)) == 0;
+				count0 = __shfl_sync(0xffffffffu, eff_count, 0);
+				uniform = count0 >= 2 && __all_sync(0xffffffffu, eff_count == count0);
+				recip = uniform ? 0xffffffffu / count0 + 1u : 0u;
 			}
-			else
-			{
-				j = 0;
-#pragma unroll
-				for (int s = 16; s >= 1; s >>= 1)
+
+			// item -> (j, mgi) and the meshlet's loads for the chunk starting at `b`.  Software pipeline (NVC_FILTER_PIPELINE):
+			// the loads of chunk k+1 are issued before chunk k is evaluated, so their DRAM latency overlaps its arithmetic.
+			// Carried state: one packed word (j | mgi << 8 | old visibility bit << 30 | active << 31) + the 12 loaded bytes.
+			auto fetch = [&](uint32_t b, uint32_t& jm, uint2& b0, uint32_t& b1) {
+				const uint32_t item = b + lane;
+				const bool active = item < run_total;
+				uint32_t j, mgi;
+				if (TABLE)
 				{
-					uint32_t v = __shfl_sync(0xffffffffu, incl, (j + s - 1) & 31u);
-					if (v <= item)
-						j += s;
+					const uint32_t e = active ? uint32_t(sh.items[item]) : 0u;
+					j = e >> 6;
+					mgi = e & 63u;
 				}
-			}
-			j &= 31u;
-			uint32_t mgi = uniform ? item - j * count0 : item - __shfl_sync(0xffffffffu, excl, j);
-			if (!active)
-				j = 0u;
-			const CmdRecord& rec = recs[j];
-			if (alive_flatten) // the rank-th SET bit of the window is the meshlet's lane index
-				mgi = !active ? 0u : use_table ? uint32_t(sh.items[warp][item]) : select_bit64(rec.ids.z, rec.ids.w, mgi);
-			mgi &= 63u;
-			jm = j | (mgi << 8) | (active ? 0x80000000u : 0u);
-			b0 = make_uint2(0u, 0u);
-			b1 = 0u;
-			if (active)
+				else
+				{
+					if (uniform)
+						j = __umulhi(item, recip);
+					else if (nz_prefix)
+					{
+						uint32_t rel = run_excl - b;
+						uint32_t hbit = (eff_count != 0 && rel >= 1 && rel < 32) ? (1u << rel) : 0u;
+						uint32_t heads = __reduce_or_sync(0xffffffffu, hbit);
+						uint32_t first = __popc(__ballot_sync(0xffffffffu, eff_count != 0 && run_incl <= b));
+						j = first + __popc(heads & lanemask_le());
+					}
+					else
+					{
+						j = 0;
+#pragma unroll
+						for (int s = 16; s >= 1; s >>= 1)
+						{
+							uint32_t v = __shfl_sync(0xffffffffu, run_incl, (j + s - 1) & 31u);
+							if (v <= item)
+								j += s;
+						}
+					}
+					j &= 31u;
+					mgi = uniform ? item - j * count0 : item - __shfl_sync(0xffffffffu, run_excl, j);
+					if (!active)
+						j = 0u, mgi = 0u;
+					mgi &= 63u;
+				}
+				const uint4 ids = recs[j].ids;
+				uint32_t bit = 0u;
+				if (TABLE)
+					bit = 1u; // only set bits are listed
+				else if (track)
+					bit = ((mgi & 32u ? ids.w : ids.z) >> (mgi & 31u)) & 1u;
+				jm = j | (mgi << 8) | (bit << 30) | (active ? 0x80000000u : 0u);
+				b0 = make_uint2(0u, 0u);
+				b1 = 0u;
+				if (active)
+				{
+					const char* mp = reinterpret_cast<const char*>(p.meshlets + (ids.x + mgi));
+					b0 = ldg_stream_u2(mp, spol);
+					b1 = ldg_stream_u32(mp + 8, spol);
+				}
+			};
+
+			// NVC_FILTER_PIPELINE = prefetch distance in chunks (0: none).  Distance 2 keeps two chunks (2 x 768 bytes per warp) in
+			// flight: with one, a chunk's arithmetic (~0.6 us at 8 warps per scheduler) is shorter than the DRAM latency under load
+			uint32_t n_jm = 0, n_b1 = 0, m_jm = 0, m_b1 = 0;
+			uint2 n_b0 = make_uint2(0u, 0u), m_b0 = make_uint2(0u, 0u);
+#if NVC_FILTER_PIPELINE >= 1
+			if (run_total)
+				fetch(0u, n_jm, n_b0, n_b1);
+#endif
+#if NVC_FILTER_PIPELINE >= 2
+			if (run_total > 32u)
+				fetch(32u, m_jm, m_b0, m_b1);
+#endif
+			for (uint32_t base = 0; base < run_total; base += 32)
 			{
-				const char* mp = reinterpret_cast<const char*>(p.meshlets + (rec.ids.x + mgi));
-				b0 = ldg_stream_u2(mp, spol);
-				b1 = ldg_stream_u32(mp + 8, spol);
+#if NVC_FILTER_PIPELINE >= 2
+				const uint32_t jm = n_jm, b1 = n_b1;
+				const uint2 b0 = n_b0;
+				n_jm = m_jm, n_b0 = m_b0, n_b1 = m_b1;
+				if (base + 64u < run_total)
+					fetch(base + 64u, m_jm, m_b0, m_b1);
+#elif NVC_FILTER_PIPELINE == 1
+				const uint32_t jm = n_jm, b1 = n_b1;
+				const uint2 b0 = n_b0;
+				if (base + 32u < run_total)
+					fetch(base + 32u, n_jm, n_b0, n_b1);
+#else
+				fetch(base, n_jm, n_b0, n_b1);
+				const uint32_t jm = n_jm, b1 = n_b1;
+				const uint2 b0 = n_b0;
+				(void)m_jm, (void)m_b1, (void)m_b0;
+#endif
+				const bool active = (jm >> 31) != 0u;
+				const uint32_t j = jm & 31u;
+#if NVC_FILTER_BATCH_PREFETCH
+				if (base == 96u && batch_next < nbatch && cid_next < ncmd) // the commands have reached L2 by now: pull the draws
+					prefetch_l2(p.draws + __ldg(&p.task_commands[cid_next].drawId));
+#endif
+
+				// ---- the command's record, the meshlet's visibility bit ----
+				const CmdRecord& rec = recs[j];
+				const float4 row0 = rec.row0, row1 = rec.row1, row2 = rec.row2, aux = rec.aux;
+				const uint32_t flags = __float_as_uint(aux.w);
+				const bool bit = (jm & 0x40000000u) != 0u; // (false when the pass does not track bits)
+				const bool oldbit = bit;
+				const bool alive = (!LATE && track) ? (active && bit) : active; // :91-92
+				const bool skip = LATE && track && (flags & kRecLate) != 0u && bit; // :97-98
+
+				const FilterResult fr = filter_meshlet<LATE, FP>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
+				const bool undecided = alive && (!fr.decided || (flags & kRecExactOnly) != 0u);
+				const bool visible = alive && fr.visible;
+
+				// ---- nothing undecided, no visibility bit changes, nothing to append (the steady-state chunk of the late pass) ----
+				const bool work = active && !undecided && ((visible && !skip) || (track_late && (!bits_known || oldbit != visible)));
+				const uint32_t umask = __ballot_sync(0xffffffffu, undecided);
+				const bool any_work = __any_sync(0xffffffffu, work);
+				if (!(umask | uint32_t(any_work)))
+					continue;
+
+				const uint32_t mgi = (jm >> 8) & 63u;
+				const uint32_t code = (batch * 32u + j) | (mgi << 24); // :138
+				const uint32_t mvi = rec.ids.y + mgi;
+				// ---- undecided lanes -> queue (exact path on full warps) ----
+				if (umask)
+				{
+					if (undecided)
+						queue[nq + __popc(umask & lanemask_lt())] = make_uint4(0u, rec.ids.x + mgi, mvi, code | ((flags & kRecLate) << 31));
+					nq += __popc(umask);
+					stat_undecided += __popc(umask);
+				}
+				if (any_work)
+					commit(active && !undecided, visible, skip, oldbit, mvi, code);
+				if (nq >= 32u)
+					drain(32u);
 			}
 		};
 
-		uint32_t n_jm = 0, n_b1 = 0;
-		uint2 n_b0 = make_uint2(0u, 0u);
-#if NVC_FILTER_PIPELINE
-		if (total)
-			fetch(0u, n_jm, n_b0, n_b1);
-#endif
-		for (uint32_t base = 0; base < total; base += 32)
+		if (alive_flatten)
 		{
-#if NVC_FILTER_PIPELINE
-			const uint32_t jm = n_jm, b1 = n_b1;
-			const uint2 b0 = n_b0;
-			if (base + 32u < total)
-				fetch(base + 32u, n_jm, n_b0, n_b1);
-#else
-			fetch(base, n_jm, n_b0, n_b1);
-			const uint32_t jm = n_jm, b1 = n_b1;
-			const uint2 b0 = n_b0;
-#endif
-			const bool active = (jm >> 31) != 0u;
-			const uint32_t j = jm & 31u, mgi = (jm >> 8) & 63u;
-#if NVC_FILTER_BATCH_PREFETCH
-			if (base == 96u && batch_next < nbatch && cid_next < ncmd) // the commands have reached L2 by now: pull the draws
-				prefetch_l2(p.draws + __ldg(&p.task_commands[cid_next].drawId));
-#endif
-
-			// ---- the command's record, its visibility bit ----
-			const CmdRecord& rec = recs[j];
-			const uint4 ids = rec.ids;
-			const uint32_t mi = ids.x + mgi, mvi = ids.y + mgi;
-			const float4 row0 = rec.row0, row1 = rec.row1, row2 = rec.row2, aux = rec.aux;
-			const uint32_t flags = __float_as_uint(aux.w);
-
-			bool oldbit = false, skip = false, alive = active;
-			if (track)
+			// every command lane lists the positions of its set bits ONCE per (sub-)batch; items then read one 16-bit entry
+			// (command lane << 6 | meshlet lane) instead of searching the scan and selecting the rank-th set bit of the window
+			const uint32_t span = total <= kFItems ? 32u : 8u;
+			for (uint32_t lo = 0; lo < 32u; lo += span)
 			{
-				const bool bit = (((uint64_t(ids.w) << 32) | ids.z) >> mgi) & 1ull; // mgi < 64
-				oldbit = bit;
-				if (!LATE)
-					alive = alive && bit; // :91-92
-				else
-					skip = (flags & kRecLate) != 0u && bit; // :97-98
+				const uint32_t sub_base = __shfl_sync(0xffffffffu, excl, int(lo));
+				const uint32_t sub_end = lo + span < 32u ? __shfl_sync(0xffffffffu, excl, int((lo + span) & 31u)) : total;
+				if (sub_end == sub_base)
+					continue;
+				if (lane >= lo && lane < lo + span)
+				{
+					uint16_t* tbl = sh.items + (excl - sub_base);
+					const uint32_t tag = lane << 6;
+					for (uint32_t m = amask_lo; m; m &= m - 1u)
+						*tbl++ = uint16_t(tag | uint32_t(__ffs(int(m)) - 1));
+					for (uint32_t m = amask_hi; m; m &= m - 1u)
+						*tbl++ = uint16_t(tag | uint32_t(32 + __ffs(int(m)) - 1));
+				}
+				__syncwarp(); // records and the item table visible to the whole warp
+				run(std::true_type(), sub_end - sub_base, 0u, 0u);
+				__syncwarp(); // the table's readers are done
 			}
-
-			const FilterResult fr = filter_meshlet<LATE, FP>(fc, cd, p.hiz, row0, row1, row2, aux, b0, b1, backface, occlusion);
-			const bool decided = !alive || (fr.decided && (flags & kRecExactOnly) == 0u);
-			const bool visible = alive && fr.visible;
-
-			// ---- fast exit: nothing undecided, no visibility bit changes, nothing to append (the steady-state chunk) ----
-			const bool emits = visible && !skip;
-			const bool changes = track_late && (!bits_known || oldbit != visible);
-			if (!__any_sync(0xffffffffu, !decided || (active && (emits || changes))))
-				continue;
-
-			// ---- undecided lanes -> queue (exact path on full warps) ----
-			const uint32_t code = (batch * 32u + j) | (mgi << 24); // :138
-			const uint32_t umask = __ballot_sync(0xffffffffu, !decided);
-			if (umask)
-			{
-				if (!decided)
-					queue[nq + __popc(umask & lanemask_lt())] = make_uint4(0u, mi, mvi, code | ((flags & kRecLate) << 31));
-				nq += __popc(umask);
-				stat_undecided += __popc(umask);
-			}
-			commit(active && decided, visible, skip, oldbit, mvi, code);
-			if (nq >= 32u)
-				drain(32u);
+		}
+		else
+		{
+			__syncwarp(); // records visible to the whole warp
+			run(std::false_type(), total, excl, incl);
 		}
 #if NVC_FILTER_BATCH_PREFETCH
 		batch = batch_next;
@@ -2333,7 +2449,7 @@ __global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float*
 	NVC_GRID_DEPENDENCY_SYNC();
 	(void)total;
 	// block -> (level, row group): uniform walk over <= 16 levels
-	uint32_t l = 0, rg = blockIdx.x;
+	uint32_t l = hz.fp_first, rg = blockIdx.x;
 	for (;;)
 	{
 		const uint32_t n = footprint_row_groups(max(1u, hz.height >> l));
@@ -2376,7 +2492,7 @@ cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cuda
 	if (total == 0)
 		return cudaSuccess;
 	uint32_t blocks = 0;
-	for (uint32_t l = 0; l < hiz.levels; ++l)
+	for (uint32_t l = hiz.fp_first; l < hiz.levels; ++l)
 		blocks += footprint_row_groups(hiz.height >> l ? hiz.height >> l : 1u);
 #if NVC_PDL && !defined(NVC_EMU)
 	return launch_pdl(footprint_kernel, dim3(blocks), dim3(256), 0, stream, hiz, fp, total);
@@ -2386,11 +2502,14 @@ cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cuda
 #endif
 }
 
-cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
+cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, uint32_t max_blocks, cudaStream_t stream)
 {
+	// persistent grid: at most `max_blocks` CTAs (SMs x resident CTAs per SM, drawcull_occupancy) walk the tiles
 	uint32_t blocks = (p.cull.drawCount + kDrawBlock * kDPT - 1) / (kDrawBlock * kDPT);
 	if (blocks == 0)
 		blocks = 1;
+	if (max_blocks && blocks > max_blocks)
+		blocks = max_blocks;
 #if NVC_PDL && !defined(NVC_EMU)
 	void (*kernel)(DrawCullParams) = late ? (task ? drawcull_kernel<true, true> : drawcull_kernel<true, false>) : (task ? drawcull_kernel<false, true> : drawcull_kernel<false, false>);
 	return launch_pdl(kernel, dim3(blocks), dim3(kDrawBlock), 0, stream, p);
@@ -2412,9 +2531,31 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaS
 	return cudaGetLastError();
 }
 
+// resident CTAs per SM of the four drawcull specialisations: [late][task]
+cudaError_t drawcull_occupancy(int blocks_per_sm[2][2])
+{
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0][0], drawcull_kernel<false, false>, kDrawBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0][1], drawcull_kernel<false, true>, kDrawBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1][0], drawcull_kernel<true, false>, kDrawBlock, 0);
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1][1], drawcull_kernel<true, true>, kDrawBlock, 0);
+	return e;
+}
+
 uint32_t hiz_stage_bytes(const HiZDesc& hiz)
 {
 	return hiz.stage_level < hiz.levels ? ((hiz.stage_texels * 4u + 15u) & ~15u) : 0u;
+}
+
+// the main passes of a frame (TRACK) are specialised on the backface flag too; everything else reads its flags at run time
+template <bool LATE, bool FP, bool TASKOUT>
+static void (*pick_filter_kernel(bool track, bool bf))(ClusterParams)
+{
+	if (!track)
+		return clustercull_filter_kernel<LATE, FP, false, TASKOUT, -1>;
+	return bf ? clustercull_filter_kernel<LATE, FP, true, TASKOUT, 1> : clustercull_filter_kernel<LATE, FP, true, TASKOUT, 0>;
 }
 
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream)
@@ -2423,20 +2564,12 @@ cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t block
 	{
 		const bool track = p.cull.clusterOcclusionEnabled == 1 && p.cull.postPass == 0;
 		const bool taskout = p.payloads != nullptr;
+		const bool bf = p.cull.clusterBackfaceEnabled != 0;
 		void (*kernel)(ClusterParams);
 		if (taskout)
-		{
-			if (late)
-				kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true, true> : clustercull_filter_kernel<true, true, false, true>)
-				                  : (track ? clustercull_filter_kernel<true, false, true, true> : clustercull_filter_kernel<true, false, false, true>);
-			else
-				kernel = track ? clustercull_filter_kernel<false, false, true, true> : clustercull_filter_kernel<false, false, false, true>;
-		}
-		else if (late)
-			kernel = p.hiz.fp ? (track ? clustercull_filter_kernel<true, true, true, false> : clustercull_filter_kernel<true, true, false, false>)
-			                  : (track ? clustercull_filter_kernel<true, false, true, false> : clustercull_filter_kernel<true, false, false, false>);
+			kernel = late ? (p.hiz.fp ? pick_filter_kernel<true, true, true>(track, bf) : pick_filter_kernel<true, false, true>(track, bf)) : pick_filter_kernel<false, false, true>(track, bf);
 		else
-			kernel = track ? clustercull_filter_kernel<false, false, true, false> : clustercull_filter_kernel<false, false, false, false>;
+			kernel = late ? (p.hiz.fp ? pick_filter_kernel<true, true, false>(track, bf) : pick_filter_kernel<true, false, false>(track, bf)) : pick_filter_kernel<false, false, false>(track, bf);
 #if NVC_PDL && !defined(NVC_EMU)
 		return launch_pdl(kernel, dim3(blocks), dim3(kClusterBlock), 0, stream, p);
 #else
@@ -2504,9 +2637,9 @@ cudaError_t clustercull_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_l
 
 cudaError_t clustercull_filter_occupancy(int* blocks_per_sm_early, int* blocks_per_sm_late)
 {
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false, false, false>, kClusterBlock, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_early, clustercull_filter_kernel<false, false, true, false, 1>, kClusterBlock, 0);
 	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, false, false, false>, kClusterBlock, 0);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm_late, clustercull_filter_kernel<true, true, true, false, 1>, kClusterBlock, 0);
 	return e;
 }
 

@@ -200,6 +200,7 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 					}
 			}
 			hiz.fp = fp.data();
+			hiz.fp_first = uint32_t((done / 2000000) % 3); // the kernels take the four-texel path below this mip
 		}
 		FilterConsts fc = make_filter_consts(cd, hiz, true);
 
