@@ -609,39 +609,47 @@ def main():
     lib.nvc_filter_stats(path.ctx, filter_stats, 1)
     pass_ms, raster_ms = passes_of(ev)
 
-    # ---- the same K frames as ONE CUDA-graph launch each (graph replay; no per-launch host work, no timing
-    # events between the passes).  Calls of the C ABI only enqueue, so a frame captures as is.  Single GPU only: the peer
-    # exchange uses side streams and flags across processes. ----
+    # ---- the same frames as CUDA-graph launches (graph replay; no per-launch host work, no timing events between
+    # the passes).  Calls of the C ABI only enqueue, so a frame captures as is.  With the peer exchange (nvc_gather_*) a graph holds
+    # GF = 4 frames — the frame tags and the parity-selected receive buffers are baked into it — followed by the wait for its last
+    # push and nvc_gather_graph_advance, which moves the tags of the next replay on; three of the four exchanges still overlap the
+    # following frame's early passes. ----
     graph_ms = None
     graph_note = None
-    if world == 1 and os.environ.get("NVC_BENCH_GRAPH", "1") != "0":
+    GF = 4 if peer else 1
+    if os.environ.get("NVC_BENCH_GRAPH", "1") != "0" and K >= GF:
         try:
+            drain()
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                frame(cd)  # warm the side stream
-            torch.cuda.synchronize()
+                for _ in range(GF):
+                    frame(cd)  # warm the side stream
+                drain()
+            sync_all()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                frame(cd)
+                for _ in range(GF):
+                    frame(cd)
+                drain()
+                if peer:
+                    check(lib.nvc_gather_graph_advance(path.ctx, path._stream(), GF), path.ctx, "nvc_gather_graph_advance")
+            reps = K // GF
             for _ in range(3):
                 graph.replay()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             per = []
-            for rep in range(3):  # three regions of K replays: median and min reported
-                torch.cuda.synchronize()
-                g0.record()
-                for _ in range(K):
-                    graph.replay()
-                g1.record()
-                torch.cuda.synchronize()
-                per.append(g0.elapsed_time(g1))
+            for rep in range(3):  # three regions of K frames: median and min reported
+                per.append(timed(lambda k: graph.replay(), reps) * (K / float(reps * GF)))
             graph_ms = {"median": float(np.median(per)), "min": float(min(per))}
             del graph
         except Exception as e:
-            graph_note = str(e)[:160]
+            graph_note = str(e)[:200]
             torch.cuda.synchronize()
+        ok_t = torch.tensor([1 if graph_ms else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)  # a rank whose capture failed must not leave the others with a graph number
+        if not int(ok_t.item()):
+            graph_ms = None
     # headline = graph replay when it ran (that is how a host would drive the frame), eager otherwise
     max_ms = graph_ms["median"] if graph_ms else min(eager_ms, plain_ms)
 
@@ -856,7 +864,8 @@ def main():
         W, Hh = scene.screen
         hz = path.hiz
         pyr_texels = int(hz.total_texels)
-        fp_texels = sum((max(1, hz.width >> l) + 1) * (max(1, hz.height >> l) + 1) for l in range(hz.levels)) if has_fp else 0
+        fp_first = int(os.environ.get("NVC_FP_FIRST_LEVEL", "0"))
+        fp_texels = sum((max(1, hz.width >> l) + 1) * (max(1, hz.height >> l) + 1) for l in range(min(fp_first, hz.levels - 1), hz.levels)) if has_fp else 0
         alg = {
             # per draw: 48 (MeshDraw) + 4 (dvb) + 32 (cull head, drawn from the 208-byte Mesh once per geometry upload) + 20 per command written
             "drawcull_early": pr["early_reached"] * (48 + 4 + 32) + (D - pr["early_reached"]) * (16 + 4) + pr["cmds_early"] * 20,
@@ -918,7 +927,7 @@ def main():
             },
             "clocks": clocks,
             "timing": {
-                "headline": "CUDA-graph replay of the frame (median of 3 regions of %d replays)" % K if graph_ms else "eager launches from the host (%d frames; the faster of the regions with / without per-pass timing events)" % K,
+                "headline": ("CUDA-graph replay, %d frame(s) per graph (median of 3 regions of %d frames)" % (GF, K)) if graph_ms else "eager launches from the host (%d frames; the faster of the regions with / without per-pass timing events)" % K,
                 "graph_ms_per_step": ({k: v / K for k, v in graph_ms.items()} if graph_ms else None),
                 "eager_ms_per_step": eager_ms / K,
                 "eager_no_events_ms_per_step": plain_ms / K,

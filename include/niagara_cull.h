@@ -351,6 +351,11 @@ NVC_API int nvc_gather_connect(NvcContext* ctx, const void* all_tickets);
 NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_slab, const uint32_t* local_count4);
 NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream);
 NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t** gathered_count4);
+/* CUDA-graph replay of frames that contain the exchange: the calls above bake their frame tags (and the parity-selected buffer
+ * addresses) into a captured graph.  Enqueue this as the LAST operation of the captured sequence with `frames` = the number of
+ * nvc_gather_push calls captured (must be even); every replay then shifts the tags of the next one by `frames`.  Each captured push
+ * needs its nvc_gather_wait inside the same capture; all ranks replay the same graphs the same number of times. */
+NVC_API int nvc_gather_graph_advance(NvcContext* ctx, void* stream, uint32_t frames);
 /* transport of nvc_gather_push: 0 = copy engines (default), 2 / 3 = NVSwitch multicast (below), 1 = a 32-CTA kernel on a high-priority stream that writes only
  * the valid count x 20 bytes with 16-byte peer stores (also selectable with NVC_GATHER_MODE=sm) */
 NVC_API int nvc_gather_set_mode(NvcContext* ctx, int mode);

@@ -196,8 +196,6 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 	}
 	if (e == cudaSuccess)
 		e = nvc::clustercull_filter_occupancy(&ctx->cluster_filter_blocks_early, &ctx->cluster_filter_blocks_late);
-	if (e == cudaSuccess)
-		e = nvc::drawcull_occupancy(ctx->draw_blocks);
 	if (const char* env = getenv("NVC_CLUSTER_FILTER"))
 		ctx->cluster_filter = atoi(env) != 0;
 	if (const char* env = getenv("NVC_DRAW_FILTER"))
@@ -222,9 +220,6 @@ NVC_API int nvc_create(int device, const NvcLimits* limits, NvcContext** out_ctx
 		ctx->cluster_filter_blocks_early = 1;
 	if (ctx->cluster_filter_blocks_late < 1)
 		ctx->cluster_filter_blocks_late = 1;
-	for (int i = 0; i < 4; ++i)
-		if (ctx->draw_blocks[i >> 1][i & 1] < 1)
-			ctx->draw_blocks[i >> 1][i & 1] = 1;
 
 	*out_ctx = ctx;
 	return NVC_OK;
@@ -366,8 +361,7 @@ NVC_API int nvc_drawcull(NvcContext* ctx, void* stream, const NvcCullData* cull,
 		p.use_filter = (p.filter.enabled && p.filter.occ_ok) ? 1u : 0u;
 	}
 
-	const uint32_t max_blocks = uint32_t(ctx->sm_count) * uint32_t(ctx->draw_blocks[late != 0][task != 0]);
-	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, max_blocks, static_cast<cudaStream_t>(stream));
+	cudaError_t e = nvc::launch_drawcull(p, late != 0, task != 0, static_cast<cudaStream_t>(stream));
 	return e == cudaSuccess ? NVC_OK : cuda_fail(ctx, e, "nvc_drawcull");
 }
 
@@ -559,7 +553,7 @@ NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz)
 		h = h ? h : 1;
 		ctx->hiz_fp_offset[l] = uint32_t(total);
 		if (l >= ctx->hiz_fp_first)
-			total += uint64_t(w + 1) * (h + 1);
+			total += uint64_t(nvc::fp_pitch(w)) * (h + 1);
 	}
 	if (total >= (1ull << 31))
 		return NVC_ERROR_UNSUPPORTED;

@@ -292,7 +292,7 @@ __device__ __forceinline__ void filter_occlusion(const FilterConsts& fc, const N
 	{
 		// fract != 0 on both axes here, so all four texels of the footprint count: one load from the footprint image
 		const uint32_t ix = (uint32_t)(fminf(fmaxf(flx, -1.f), wmax) + 1.f), iy = (uint32_t)(fminf(fmaxf(fly, -1.f), hmax) + 1.f);
-		depth = __ldg(hiz.fp + (hiz.fp_offset[level] + iy * (wi + 1u) + ix));
+		depth = __ldg(hiz.fp + (hiz.fp_offset[level] + iy * fp_pitch(wi) + ix));
 	}
 	else
 	{

@@ -19,7 +19,6 @@ struct NvcContext
 	int sm_count = 0;
 	int cluster_blocks_early = 0, cluster_blocks_late = 0, cluster_blocks_late_staged = 0;
 	int cluster_filter_blocks_early = 0, cluster_filter_blocks_late = 0;
-	int draw_blocks[2][2] = { { 0, 0 }, { 0, 0 } }; // resident CTAs per SM of drawcull_kernel<late, task> (persistent grid)
 	bool draw_filter = false;   // env NVC_DRAW_FILTER=1: filtered occlusion stage of the late drawcull (measured: no gain on B200, the pass is not issue bound)
 	bool cluster_filter = true; // nvc_set_cluster_filter / env NVC_CLUSTER_FILTER: filtered cluster kernel (default) or the exact one
 	uint32_t hiz_stage_budget = 0; // texels (24 KB) of coarse Hi-Z mips staged per CTA; 0 = off (env NVC_HIZ_STAGE_TEXELS)
@@ -38,7 +37,7 @@ struct NvcContext
 	float* hiz_fp = nullptr;
 	const float* hiz_fp_key = nullptr;
 	uint32_t hiz_fp_width = 0, hiz_fp_height = 0, hiz_fp_levels = 0, hiz_fp_total = 0;
-	uint32_t hiz_fp_first = 2; // first mip with a footprint image (env NVC_FP_FIRST_LEVEL)
+	uint32_t hiz_fp_first = 0; // first mip with a footprint image (env NVC_FP_FIRST_LEVEL)
 	uint32_t hiz_fp_offset[NVC_MAX_HIZ_LEVELS] = {};
 	bool hiz_fp_valid = false; // set by nvc_depth_pyramid, cleared by nvc_prepare_hiz
 };
@@ -72,6 +71,15 @@ struct alignas(128) Scratch
 	uint32_t pad6[28];
 };
 
+// row pitch of a footprint-image level of width w (w + 1 entries per row, padded so that every row starts 16-byte aligned)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t fp_pitch(uint32_t w)
+{
+	return (w + 4u) & ~3u;
+}
+
 struct HiZDesc
 {
 	float* texels;
@@ -84,6 +92,7 @@ struct HiZDesc
 	// footprint whose lower corner is (i, j), i in [-1, w-1], j in [-1, h-1], indices clamped to the level — what the
 	// MIN-reduction sampler returns for any coordinate whose bilinear footprint starts there (resources.cpp:294-325).
 	// Level l: fp + fp_offset[l], pitch w + 1, entry (i + 1, j + 1).  fp == nullptr: not available.
+	// Level l: fp + fp_offset[l], row pitch fp_pitch(w) (a multiple of four entries: rows are 16-byte aligned), entry (i + 1, j + 1).
 	// Only mips >= fp_first have an image (the finest mips hold 15/16 of the texels and are sampled by sub-8-pixel spheres only;
 	// lookups into them take the four texel loads).
 	const float* fp;
@@ -172,8 +181,7 @@ struct PyramidParams
 	uint32_t vector_ok; // set by launch_pyramid: bases aligned for 16-byte loads
 };
 
-cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, uint32_t max_blocks, cudaStream_t stream);
-cudaError_t drawcull_occupancy(int blocks_per_sm[2][2]);
+cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream);
 cudaError_t launch_clustercull(const ClusterParams& p, bool late, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_taskcull(const ClusterParams& p, bool late, NvcMeshTaskPayload* payloads, uint32_t* emit_counts, uint32_t blocks, cudaStream_t stream);
 cudaError_t launch_pyramid(const PyramidParams& p, cudaStream_t stream);

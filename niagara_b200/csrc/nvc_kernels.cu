@@ -230,20 +230,8 @@ constexpr int kDPT = NVC_DRAW_PER_THREAD;
 constexpr uint32_t kDrawQueue = 128; // undecided draws per block that go through the shared queue (more: evaluated in place)
 constexpr uint32_t kDrawStage = 512 * kDPT > 1536 ? 1536 : 512 * kDPT; // commands staged per block before the coalesced write-out (static shared memory <= 48 KB)
 
-// Persistent grid (NVC_DRAW_MIN_BLOCKS CTAs per SM, launch_drawcull): a CTA walks tiles of 256 draws.  The pass is a chain of
-// dependent DRAM round trips (MeshDraw -> mesh head -> block atomic -> write-out), so the next tile's MeshDraw / dvb loads are
-// issued before the current tile is evaluated and its mesh heads as soon as the current tile's arithmetic is done: the loads
-// of tile k+1 travel while tile k computes, scans and writes (profiles/r2_variants.md: one tile per CTA = 29 / 34 us, latency bound
-// at 38 % of the HBM peak).
-#ifndef NVC_DRAW_MIN_BLOCKS
-#define NVC_DRAW_MIN_BLOCKS 4
-#endif
-#ifndef NVC_DRAW_PERSISTENT
-#define NVC_DRAW_PERSISTENT 1
-#endif
-
 template <bool LATE, bool TASK>
-__global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kernel(const DrawCullParams p)
+__global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullParams p)
 {
 	NVC_GRID_DEPENDENCY_SYNC(); // nothing of the previous pass (scratch counters, dvb, pyramid) is touched before this point
 	__shared__ uint32_t s_warp_total[kDrawBlock / 32];
@@ -259,60 +247,13 @@ __global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kern
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u, warp = tid >> 5;
 	const bool packed = p.mesh_heads != nullptr;
-	const uint32_t ntiles = (cd.drawCount + kDrawBlock * kDPT - 1) / (kDrawBlock * kDPT);
 	if (LATE && tid == 0)
 		s_qcount = 0;
 	if (LATE)
 		__syncthreads();
 
-	// ---- the prefetched tile: MeshDraw, draw visibility, mesh head of this thread's kDPT draws (draw k of the thread: tile base
-	// + k * 256 + tid, so that every load instruction of a warp covers 32 consecutive MeshDraws) ----
-	float4 n_d0[kDPT], n_d1[kDPT], n_m0[kDPT];
-	uint4 n_d2[kDPT], n_h1[kDPT];
-	uint32_t n_dv[kDPT];
-	bool n_reached[kDPT];
-	auto fetch_draws = [&](uint32_t tile) {
-#pragma unroll
-		for (int k = 0; k < kDPT; ++k)
-		{
-			const uint32_t di = (tile * kDPT + k) * kDrawBlock + tid;
-			n_d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-			n_d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
-			n_d2[k] = make_uint4(0u, 0u, ~cd.postPass, 0u);
-			n_dv[k] = 0u;
-			if (tile < ntiles && di < cd.drawCount)
-			{
-				const char* dp = reinterpret_cast<const char*>(p.draws + di);
-				n_d0[k] = ldg_f4(dp);      // position.xyz, scale
-				n_d1[k] = ldg_f4(dp + 16); // orientation
-				n_d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
-				n_dv[k] = p.draw_visibility[di]; // (read for every draw: independent of the MeshDraw loads, one round trip less)
-			}
-		}
-	};
-	auto fetch_heads = [&]() {
-#pragma unroll
-		for (int k = 0; k < kDPT; ++k)
-		{
-			n_reached[k] = n_d2[k].z == cd.postPass && (LATE || n_dv[k] != 0u); // :63, :67 (out-of-range lanes carry ~postPass)
-			n_m0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-			n_h1[k] = make_uint4(0u, 0u, 0u, 0u);
-			if (n_reached[k])
-			{
-				const char* mp = reinterpret_cast<const char*>(p.meshes + n_d2[k].x);
-				// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
-				const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + n_d2[k].x) : mp;
-				n_m0[k] = ldg_f4(hp); // center.xyz, radius
-				if (packed)
-					n_h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
-			}
-		}
-	};
-	fetch_draws(blockIdx.x);
-	fetch_heads();
-
-	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-	{
+	// per-draw state of this thread's kDPT draws (draw k of the thread: block base + k * 256 + tid, so that every load
+	// instruction of a warp still covers 32 consecutive MeshDraws)
 	uint32_t di[kDPT];
 	float4 d0[kDPT], d1[kDPT];
 	uint4 d2[kDPT];
@@ -321,18 +262,55 @@ __global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kern
 	bool emit[kDPT];
 	uint32_t units[kDPT]; // commands this draw appends: taskGroups (TASK) or 1
 	uint32_t lodIndex[kDPT], meshletOffset[kDPT], meshletCount[kDPT];
+
+	// ---- phase 1: all MeshDraw loads ----
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		di[k] = (blockIdx.x * kDPT + k) * kDrawBlock + tid;
+		d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
+		d2[k] = make_uint4(0u, 0u, 0u, 0u);
+		reached[k] = false;
+		if (di[k] < cd.drawCount)
+		{
+			const char* dp = reinterpret_cast<const char*>(p.draws + di[k]);
+			d0[k] = ldg_f4(dp);      // position.xyz, scale
+			d1[k] = ldg_f4(dp + 16); // orientation
+			d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
+			reached[k] = d2[k].z == cd.postPass; // :63
+		}
+	}
+	// ---- phase 2: draw visibility ----
+#pragma unroll
+	for (int k = 0; k < kDPT; ++k)
+	{
+		dv[k] = 0;
+		if (reached[k])
+		{
+			dv[k] = p.draw_visibility[di[k]];
+			if (!LATE && dv[k] == 0) // :67
+				reached[k] = false;
+		}
+	}
+	// ---- phase 3: mesh heads (dependent on meshIndex) ----
 	float4 m0[kDPT];
 	uint4 h1[kDPT];
 #pragma unroll
 	for (int k = 0; k < kDPT; ++k)
 	{
-		di[k] = (tile * kDPT + k) * kDrawBlock + tid;
-		d0[k] = n_d0[k], d1[k] = n_d1[k], d2[k] = n_d2[k], dv[k] = n_dv[k], m0[k] = n_m0[k], h1[k] = n_h1[k];
-		reached[k] = n_reached[k];
+		m0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		h1[k] = make_uint4(0u, 0u, 0u, 0u);
+		if (reached[k])
+		{
+			const char* mp = reinterpret_cast<const char*>(p.meshes + d2[k].x);
+			// packed: one 32-byte sector holds center, radius, lodCount and the LOD-0 meshlet range
+			const char* hp = packed ? reinterpret_cast<const char*>(p.mesh_heads + d2[k].x) : mp;
+			m0[k] = ldg_f4(hp); // center.xyz, radius
+			if (packed)
+				h1[k] = ldg_u4(hp + 16); // lodCount, lod0.meshletOffset, lod0.meshletCount, vertexOffset
+		}
 	}
-#if NVC_DRAW_PERSISTENT
-	fetch_draws(tile + gridDim.x); // in flight while this tile is evaluated
-#endif
 	// ---- phase 4a: view-space sphere, frustum, occlusion ----
 	f3 centers[kDPT];
 	float radii[kDPT];
@@ -475,9 +453,6 @@ __global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kern
 	if (lane == 31)
 		s_warp_total[warp] = incl;
 	__syncthreads();
-#if NVC_DRAW_PERSISTENT
-	fetch_heads(); // the next tile's MeshDraws have had this tile's arithmetic to arrive; its heads travel during the scan / write-out
-#endif
 	if (warp == 0)
 	{
 		uint32_t t = lane < kDrawBlock / 32 ? s_warp_total[lane] : 0;
@@ -566,15 +541,6 @@ __global__ void __launch_bounds__(kDrawBlock, NVC_DRAW_MIN_BLOCKS) drawcull_kern
 				mc[i] = s_stage[i];
 		}
 	}
-
-	if (LATE && tid == 0)
-		s_qcount = 0;
-	__syncthreads(); // the tile's shared state (scan totals, staged commands, queue) is free again
-#if !NVC_DRAW_PERSISTENT
-	fetch_draws(tile + gridDim.x);
-	fetch_heads();
-#endif
-	} // tiles
 
 	// ---- last-block epilogue: tasksubmit.comp.glsl:27-47 (TASK) / publish the count (draw path) ----
 	__threadfence();
@@ -2444,6 +2410,11 @@ __host__ __device__ __forceinline__ uint32_t footprint_row_groups(uint32_t h)
 	return (h + 1u + kFpRows - 1u) / kFpRows;
 }
 
+// A CTA owns kFpRows consecutive rows of one level's image; a thread produces 4 x kFpRows entries: per pyramid row one
+// 16-byte load (texels ix0 .. ix0+3) and one 4-byte load (texel ix0-1), the four horizontal minima, then the vertical
+// combination of adjacent rows and one 16-byte store per image row — 10 loads and ~70 instructions for 16 entries.
+// (Versions before: one thread per entry with a level search and an integer division, 24.5 us for a 2048^2 pyramid; one thread
+// per column with two scalar loads per row, 11-13 us at 66 % issue-active; profiles/r2_variants.md.)
 __global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float* __restrict__ fp, uint32_t total)
 {
 	NVC_GRID_DEPENDENCY_SYNC();
@@ -2459,7 +2430,7 @@ __global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float*
 		++l;
 	}
 	const uint32_t w = max(1u, hz.width >> l), h = max(1u, hz.height >> l);
-	const uint32_t pitch = w + 1u;
+	const uint32_t pitch = fp_pitch(w);
 	const uint32_t iy0 = rg * kFpRows;
 	if (iy0 > h)
 		return;
@@ -2473,7 +2444,32 @@ __global__ void __launch_bounds__(256) footprint_kernel(const HiZDesc hz, float*
 		const uint32_t iy = iy0 + k; // row iy - 1, clamped
 		rowoff[k] = min(iy ? iy - 1u : 0u, h - 1u) * w;
 	}
-	for (uint32_t ix = threadIdx.x; ix < pitch; ix += 256u)
+	// rows of the level start 16-byte aligned when w is a multiple of 4 and the level's base is (packed power-of-two pyramids)
+	const bool vec = (w & 3u) == 0 && ((reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(fp)) & 15u) == 0 && (hz.fp_offset[l] & 3u) == 0;
+	if (vec)
+	{
+		for (uint32_t ix0 = threadIdx.x * 4u; ix0 < pitch; ix0 += 1024u)
+		{
+			// entries ix0 .. ix0+3 use texels ix0-1 .. ix0+3 (clamped to [0, w-1]); ix0 == w: only entry w exists (texel w-1 twice)
+			float4 m[kFpRows + 1];
+#pragma unroll
+			for (uint32_t k = 0; k <= kFpRows; ++k)
+			{
+				const float* row = t + rowoff[k];
+				const float left = __ldg(row + (ix0 ? ix0 - 1u : 0u));
+				float4 b = make_float4(left, left, left, left);
+				if (ix0 < w)
+					b = __ldg(reinterpret_cast<const float4*>(row + ix0));
+				m[k] = make_float4(fminf(left, b.x), fminf(b.x, b.y), fminf(b.y, b.z), fminf(b.z, b.w));
+			}
+#pragma unroll
+			for (uint32_t k = 0; k < kFpRows; ++k)
+				if (iy0 + k <= h)
+					*reinterpret_cast<float4*>(out + k * pitch + ix0) = make_float4(fminf(m[k].x, m[k + 1].x), fminf(m[k].y, m[k + 1].y), fminf(m[k].z, m[k + 1].z), fminf(m[k].w, m[k + 1].w));
+		}
+		return;
+	}
+	for (uint32_t ix = threadIdx.x; ix <= w; ix += 256u)
 	{
 		const uint32_t x0 = ix ? ix - 1u : 0u, x1 = min(ix, w - 1u);
 		float m[kFpRows + 1];
@@ -2502,14 +2498,11 @@ cudaError_t launch_footprint(const HiZDesc& hiz, float* fp, uint32_t total, cuda
 #endif
 }
 
-cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, uint32_t max_blocks, cudaStream_t stream)
+cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, cudaStream_t stream)
 {
-	// persistent grid: at most `max_blocks` CTAs (SMs x resident CTAs per SM, drawcull_occupancy) walk the tiles
 	uint32_t blocks = (p.cull.drawCount + kDrawBlock * kDPT - 1) / (kDrawBlock * kDPT);
 	if (blocks == 0)
 		blocks = 1;
-	if (max_blocks && blocks > max_blocks)
-		blocks = max_blocks;
 #if NVC_PDL && !defined(NVC_EMU)
 	void (*kernel)(DrawCullParams) = late ? (task ? drawcull_kernel<true, true> : drawcull_kernel<true, false>) : (task ? drawcull_kernel<false, true> : drawcull_kernel<false, false>);
 	return launch_pdl(kernel, dim3(blocks), dim3(kDrawBlock), 0, stream, p);
@@ -2529,19 +2522,6 @@ cudaError_t launch_drawcull(const DrawCullParams& p, bool late, bool task, uint3
 			drawcull_kernel<false, false><<<blocks, kDrawBlock, 0, stream>>>(p);
 	}
 	return cudaGetLastError();
-}
-
-// resident CTAs per SM of the four drawcull specialisations: [late][task]
-cudaError_t drawcull_occupancy(int blocks_per_sm[2][2])
-{
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0][0], drawcull_kernel<false, false>, kDrawBlock, 0);
-	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0][1], drawcull_kernel<false, true>, kDrawBlock, 0);
-	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1][0], drawcull_kernel<true, false>, kDrawBlock, 0);
-	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1][1], drawcull_kernel<true, true>, kDrawBlock, 0);
-	return e;
 }
 
 uint32_t hiz_stage_bytes(const HiZDesc& hiz)

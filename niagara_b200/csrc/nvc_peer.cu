@@ -34,11 +34,14 @@ static_assert(sizeof(Ticket) == 192, "ticket is 3 x 64 bytes");
 // layout of the small `flags` allocation (uint32 words): [0, kMaxWorld) data flags, [kMaxWorld, 2 kMaxWorld) acks
 constexpr int kAckBase = 64;
 
-__global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag)
+// Every kernel of the protocol adds *epoch (a device word, 0 unless nvc_gather_graph_advance is used) to the tag it was launched
+// with: a captured CUDA graph holds its tags as launch arguments, and each replay must speak of later frames than the one before.
+__global__ void raise_flags_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag, const uint32_t* epoch)
 {
 	int p = threadIdx.x;
 	if (p < world)
 	{
+		tag += *epoch;
 		__threadfence_system();
 		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + rank) = tag; // P2P store over NVLink (or local)
 	}
@@ -74,11 +77,12 @@ __global__ void __launch_bounds__(256) push_kernel(const uint4* __restrict__ loc
 }
 
 // tells every peer that this rank is done with frame `tag`: acks[rank] = tag in the peer's memory
-__global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag)
+__global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag, const uint32_t* epoch)
 {
 	int p = threadIdx.x;
 	if (p < world)
 	{
+		tag += *epoch;
 		__threadfence_system();
 		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + kAckBase + rank) = tag;
 	}
@@ -107,16 +111,22 @@ __global__ void __launch_bounds__(256) mc_push_kernel(const uint4* __restrict__ 
 	__threadfence_system();
 }
 
-__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag)
+__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag, const uint32_t* epoch)
 {
 	int q = threadIdx.x;
 	if (q < world)
 	{
+		tag += *epoch;
 		// tags increase monotonically; signed distance handles wrap-around
 		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
 			__nanosleep(200);
 		__threadfence_system();
 	}
+}
+
+__global__ void advance_epoch_kernel(uint32_t* epoch, uint32_t frames)
+{
+	*epoch += frames;
 }
 
 } // namespace
@@ -143,7 +153,7 @@ struct NvcGather
 	bool fused_consumed = false; // the armed late drawcull has been launched
 	cudaStream_t side[kSideStreams] = {};
 	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
-	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity
+	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity; word 8: the graph epoch (see advance_epoch_kernel)
 	cudaEvent_t acked = nullptr;
 	uint32_t tag = 0, acked_tag = 0;
 	bool connected = false;
@@ -277,7 +287,9 @@ NVC_API int nvc_gather_create(NvcContext* ctx, size_t slab_bytes, int rank, int 
 	if (e == cudaSuccess)
 		e = cudaEventCreateWithFlags(&g->acked, cudaEventDisableTiming);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&g->count_stage, 32);
+		e = cudaMalloc(&g->count_stage, 48);
+	if (e == cudaSuccess)
+		e = cudaMemset(g->count_stage, 0, 48);
 	Ticket t;
 	memset(&t, 0, sizeof(t));
 	if (e == cudaSuccess)
@@ -411,7 +423,7 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	if (e == cudaSuccess && tag >= 3 && !fused)
 	{
 		// the parity buffers were last used by frame tag-2: every peer must have acknowledged it
-		wait_flags_kernel<<<1, kMaxWorld, 0, lead>>>(g->flags + kAckBase, g->world, tag - 2);
+		wait_flags_kernel<<<1, kMaxWorld, 0, lead>>>(g->flags + kAckBase, g->world, tag - 2, g->count_stage + 8);
 		e = cudaGetLastError();
 	}
 	if (g->mode >= 1 && e == cudaSuccess)
@@ -424,7 +436,7 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 		e = cudaGetLastError();
 		if (e == cudaSuccess)
 		{
-			raise_flags_kernel<<<1, kMaxWorld, 0, g->hi>>>(g->d_peer_flags, g->world, g->rank, tag);
+			raise_flags_kernel<<<1, kMaxWorld, 0, g->hi>>>(g->d_peer_flags, g->world, g->rank, tag, g->count_stage + 8);
 			e = cudaGetLastError();
 		}
 		if (e == cudaSuccess)
@@ -457,7 +469,7 @@ NVC_API int nvc_gather_push(NvcContext* ctx, void* stream, const void* local_sla
 	}
 	if (e == cudaSuccess)
 	{
-		raise_flags_kernel<<<1, kMaxWorld, 0, g->side[0]>>>(g->d_peer_flags, g->world, g->rank, tag);
+		raise_flags_kernel<<<1, kMaxWorld, 0, g->side[0]>>>(g->d_peer_flags, g->world, g->rank, tag, g->count_stage + 8);
 		e = cudaGetLastError();
 	}
 	if (e == cudaSuccess)
@@ -485,7 +497,7 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 	cudaError_t e = cudaSuccess;
 	if (g->tag >= 2 && g->acked_tag != g->tag - 1)
 	{
-		raise_acks_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->world, g->rank, g->tag - 1);
+		raise_acks_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->world, g->rank, g->tag - 1, g->count_stage + 8);
 		e = cudaGetLastError();
 		g->acked_tag = g->tag - 1;
 	}
@@ -493,7 +505,7 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 		e = cudaStreamWaitEvent(s, g->join[0], 0);
 	if (e == cudaSuccess)
 	{
-		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag);
+		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag, g->count_stage + 8);
 		e = cudaGetLastError();
 	}
 	if (e != cudaSuccess)
@@ -575,7 +587,9 @@ NVC_API int nvc_gather_attach(NvcContext* ctx, size_t slab_bytes, int rank, int 
 	if (e == cudaSuccess)
 		e = cudaMalloc(&g->d_peer_counts, sizeof(uint32_t*) * kMaxWorld);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&g->count_stage, 32);
+		e = cudaMalloc(&g->count_stage, 48);
+	if (e == cudaSuccess)
+		e = cudaMemset(g->count_stage, 0, 48);
 	if (e == cudaSuccess)
 	{
 		int lo = 0, hi = 0;
@@ -638,13 +652,35 @@ NVC_API int nvc_gather_fuse_next_drawcull(NvcContext* ctx, void* stream)
 	g->fused_consumed = false;
 	if (g->tag >= 3)
 	{
-		wait_flags_kernel<<<1, kMaxWorld, 0, static_cast<cudaStream_t>(stream)>>>(g->flags + kAckBase, g->world, g->tag - 2);
+		wait_flags_kernel<<<1, kMaxWorld, 0, static_cast<cudaStream_t>(stream)>>>(g->flags + kAckBase, g->world, g->tag - 2, g->count_stage + 8);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
 		{
 			ctx->last_error = std::string("nvc_gather_fuse_next_drawcull: ") + cudaGetErrorString(e);
 			return NVC_ERROR_CUDA;
 		}
+	}
+	return NVC_OK;
+}
+
+// CUDA-graph replay of frames that contain the exchange.  The calls above bake the frame tags they took at capture time into the
+// graph; enqueue this as the LAST operation of the captured sequence with `frames` = the number of nvc_gather_push calls captured
+// (even: the receive buffers alternate by tag parity and their addresses are baked too).  Every replay then advances all tags of
+// the next replay by `frames`.  Each captured push needs its nvc_gather_wait inside the same capture, and all ranks must replay
+// the same graphs the same number of times.
+NVC_API int nvc_gather_graph_advance(NvcContext* ctx, void* stream, uint32_t frames)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !g->connected || frames == 0 || (frames & 1u))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
+	advance_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(g->count_stage + 8, frames);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_graph_advance: ") + cudaGetErrorString(e);
+		return NVC_ERROR_CUDA;
 	}
 	return NVC_OK;
 }

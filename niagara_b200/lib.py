@@ -89,6 +89,7 @@ SIGNATURES = [
     ("nvc_gather_attach", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void_p), c_void_p]),
     ("nvc_gather_fuse_next_drawcull", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_buffers", ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    ("nvc_gather_graph_advance", ctypes.c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
 ]
 
 

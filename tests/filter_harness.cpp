@@ -185,7 +185,7 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 			{
 				uint32_t w = std::max(1u, hz.width >> l), h = std::max(1u, hz.height >> l);
 				hiz.fp_offset[l] = total;
-				total += (w + 1) * (h + 1);
+				total += fp_pitch(w) * (h + 1);
 			}
 			fp.resize(total);
 			for (uint32_t l = 0; l < hz.levels; ++l)
@@ -196,7 +196,7 @@ static void run(const Scenario& sc, uint64_t items, uint32_t seed, Stats& st)
 					for (uint32_t ix = 0; ix <= w; ++ix)
 					{
 						uint32_t x0 = ix ? ix - 1 : 0, x1 = std::min(ix, w - 1), y0 = iy ? iy - 1 : 0, y1 = std::min(iy, h - 1);
-						fp[hiz.fp_offset[l] + iy * (w + 1) + ix] = fminf(fminf(t[y0 * w + x0], t[y0 * w + x1]), fminf(t[y1 * w + x0], t[y1 * w + x1]));
+						fp[hiz.fp_offset[l] + iy * fp_pitch(w) + ix] = fminf(fminf(t[y0 * w + x0], t[y0 * w + x1]), fminf(t[y1 * w + x0], t[y1 * w + x1]));
 					}
 			}
 			hiz.fp = fp.data();

@@ -18,10 +18,6 @@ VARIANTS = {
     "pipe2": ["NVC_FILTER_PIPELINE=2"],
     "nohints": ["NVC_STREAM_HINTS=0"],
     "bpf": ["NVC_FILTER_BATCH_PREFETCH=1"],
-    "draw_np": ["NVC_DRAW_PERSISTENT=0"],  # drawcull: persistent grid without the cross-tile prefetch
-    "draw_mb5": ["NVC_DRAW_MIN_BLOCKS=5"],  # drawcull: resident CTAs per SM (register cap 64 / 51 / 42)
-    "draw_mb6": ["NVC_DRAW_MIN_BLOCKS=6"],
-    "draw_mb3": ["NVC_DRAW_MIN_BLOCKS=3"],
 }
 
 if __name__ == "__main__":
