@@ -435,6 +435,7 @@ def main():
     dcb_early = path.dcb
     dcb_late = torch.zeros_like(path.dcb) if peer else path.dcb
     pending = {"push": False}
+    xchg = {"on": True}  # the cull-only region (multi-GPU, reported beside the headline) switches the exchange off
 
     def frame(cull, events=None, task=None):
         """one frame; task = (payloads, emit_counts) runs meshlet.task.glsl's submission mode instead of the cluster passes"""
@@ -465,12 +466,12 @@ def main():
         path.pyramid(depth)
         mark(4)
         path.dcb = dcb_late
-        if peer and pending["push"]:
+        if peer and xchg["on"] and pending["push"]:
             # the previous frame's slab (and every peer's copy of it) must have landed before it is overwritten
             check(lib.nvc_gather_wait(path.ctx, path._stream()), path.ctx, "nvc_gather_wait")
             pending["push"] = False
             launches["n"] += 2
-        if gather == "fused":
+        if gather == "fused" and xchg["on"]:
             # fused compute + collective: the late drawcull stores its commands through the NVSwitch multicast mapping as it
             # writes them (this call takes the frame tag and waits for the peers' acknowledgements of that parity's buffers)
             check(lib.nvc_gather_fuse_next_drawcull(path.ctx, path._stream()), path.ctx, "nvc_gather_fuse_next_drawcull")
@@ -478,14 +479,14 @@ def main():
         path.cull(cull, late=True)
         mark(5)
         launches["n"] += 5 + (1 if has_fp else 0)
-        if peer:
+        if peer and xchg["on"]:
             # the late command slab is final once drawcull(late) is done: ce = push it to every peer with the copy engines,
             # mc = one multicast store kernel, fused = only counters + flags are left; all of it overlaps the late cluster
             # pass (and the next frame's early passes)
             check(lib.nvc_gather_push(path.ctx, path._stream(), ctypes.c_void_p(path.dcb.data_ptr()), ctypes.c_void_p(path.dccb.data_ptr())), path.ctx, "nvc_gather_push")
             pending["push"] = True
             launches["n"] += 1 if gather == "ce" else 2
-        elif gather == "nccl":
+        elif gather == "nccl" and xchg["on"]:
             done = torch.cuda.Event()
             done.record()
             comm_stream.wait_event(done)
@@ -500,7 +501,7 @@ def main():
             path.raster_depth(cull, produced["proj"], produced["vertices"], produced["meshletdata"], depth)
             launches["n"] += 1
         mark(7)
-        if gather == "nccl":
+        if gather == "nccl" and xchg["on"]:
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     NEV = 8  # timing marks per frame: start, cull e, clusters e, raster e, pyramid, cull l, clusters l, raster l
@@ -650,6 +651,34 @@ def main():
             dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)  # a rank whose capture failed must not leave the others with a graph number
         if not int(ok_t.item()):
             graph_ms = None
+    # ---- multi-GPU: the same frames WITHOUT the exchange (cull-only and cull + gather scaling are both reported) ----
+    cull_only_ms = None
+    if world > 1 and gather != "none":
+        try:
+            drain()
+            xchg["on"] = False
+            side2 = torch.cuda.Stream(dev)
+            side2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side2):
+                frame(cd)
+            sync_all()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=side2):
+                frame(cd)
+            for _ in range(3):
+                g2.replay()
+            cull_only_ms = timed(lambda k: g2.replay(), K)
+            del g2
+        except Exception as e:
+            graph_note = (graph_note or "") + " cull-only: " + str(e)[:120]
+            torch.cuda.synchronize()
+        xchg["on"] = True
+        if world > 1:
+            ok2 = torch.tensor([1 if cull_only_ms else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
+            if not int(ok2.item()):
+                cull_only_ms = None
+
     # headline = graph replay when it ran (that is how a host would drive the frame), eager otherwise
     max_ms = graph_ms["median"] if graph_ms else min(eager_ms, plain_ms)
 
@@ -933,6 +962,7 @@ def main():
                 "eager_no_events_ms_per_step": plain_ms / K,
                 **({"graph_unavailable": graph_note} if graph_note else {}),
             },
+            **({"without_exchange": {"value": tested_all * K / (cull_only_ms * 1e-3), "unit": "meshlets/s", "ms_per_step": cull_only_ms / K, "what": "the same frames with the all-gather switched off (--gather none), CUDA-graph replay, same process: cull-only scaling beside cull + gather (SURVEY 8(e))"}} if cull_only_ms else {}),
             "gpu_launches": gpu_launches,
             "gather_transport": transport if not gather_note else "ce",
             **({"gather_note": gather_note} if gather_note else {}),

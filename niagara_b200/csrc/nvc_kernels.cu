@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 		d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 		d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
 		d2[k] = make_uint4(0u, 0u, 0u, 0u);
+		dv[k] = 0;
 		reached[k] = false;
 		if (di[k] < cd.drawCount)
 		{
@@ -278,21 +279,17 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			d0[k] = ldg_f4(dp);      // position.xyz, scale
 			d1[k] = ldg_f4(dp + 16); // orientation
 			d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
+			// draw visibility: requested together with the MeshDraw (for every draw in range, also those of the other postPass), so
+			// that it is not one more dependent round trip in the life of the CTA
+			dv[k] = p.draw_visibility[di[k]];
 			reached[k] = d2[k].z == cd.postPass; // :63
 		}
 	}
 	// ---- phase 2: draw visibility ----
 #pragma unroll
 	for (int k = 0; k < kDPT; ++k)
-	{
-		dv[k] = 0;
-		if (reached[k])
-		{
-			dv[k] = p.draw_visibility[di[k]];
-			if (!LATE && dv[k] == 0) // :67
-				reached[k] = false;
-		}
-	}
+		if (reached[k] && !LATE && dv[k] == 0) // :67
+			reached[k] = false;
 	// ---- phase 3: mesh heads (dependent on meshIndex) ----
 	float4 m0[kDPT];
 	uint4 h1[kDPT];
@@ -1225,6 +1222,13 @@ __global__ void __launch_bounds__(kClusterBlock, NVC_CLUSTER_MIN_BLOCKS) cluster
 #ifndef NVC_FILTER_MIN_BLOCKS
 #define NVC_FILTER_MIN_BLOCKS 4
 #endif
+// resident CTAs per SM of the EARLY filtered kernel (no occlusion stage: fewer live registers; its shared-memory block is sized below)
+#ifndef NVC_FILTER_MIN_BLOCKS_EARLY
+#define NVC_FILTER_MIN_BLOCKS_EARLY 4
+#endif
+#ifndef NVC_FILTER_ITEMS
+#define NVC_FILTER_ITEMS 896
+#endif
 #ifndef NVC_FILTER_PIPELINE
 #define NVC_FILTER_PIPELINE 2
 #endif
@@ -1238,7 +1242,7 @@ constexpr int kFStage = kFFlush + 32;  // staged cluster indices per warp (a chu
 constexpr int kFQueue = 64;            // undecided items per warp (drained 32 at a time)
 // early pass: (command lane, meshlet lane) of every flattened item of one (sub-)batch; batches with more set bits are
 // processed as four sub-batches of 8 commands (<= 512 items)
-constexpr uint32_t kFItems = 896;
+constexpr uint32_t kFItems = NVC_FILTER_ITEMS;
 
 // One block of shared memory per warp: every field sits at a compile-time offset from the warp's base address.
 template <bool LATE>
@@ -1259,7 +1263,7 @@ static_assert(sizeof(FilterWarpShared<false>) * (256 / 32) + 16 <= 48 * 1024, "s
 // BF: clusterBackfaceEnabled as a compile-time fact (0 / 1; -1 = read at run time).  With it the cone arithmetic is
 // scheduled between the Hi-Z load and its use instead of behind a branch.
 template <bool LATE, bool FP, bool TRACK, bool TASKOUT, int BF>
-__global__ void __launch_bounds__(kClusterBlock, NVC_FILTER_MIN_BLOCKS) clustercull_filter_kernel(const ClusterParams p)
+__global__ void __launch_bounds__(kClusterBlock, LATE ? NVC_FILTER_MIN_BLOCKS : NVC_FILTER_MIN_BLOCKS_EARLY) clustercull_filter_kernel(const ClusterParams p)
 {
 	__shared__ FilterWarpShared<LATE> sh_all[kClusterWarps];
 	__shared__ uint32_t s_is_last;

@@ -76,18 +76,6 @@ __global__ void __launch_bounds__(256) push_kernel(const uint4* __restrict__ loc
 	__threadfence_system();
 }
 
-// tells every peer that this rank is done with frame `tag`: acks[rank] = tag in the peer's memory
-__global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag, const uint32_t* epoch)
-{
-	int p = threadIdx.x;
-	if (p < world)
-	{
-		tag += *epoch;
-		__threadfence_system();
-		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + kAckBase + rank) = tag;
-	}
-}
-
 // Multicast variant of the push: every 16-byte unit of the VALID part of the slab is stored ONCE, through the NVSwitch
 // multicast alias of this rank's slot — the switch replicates it into every rank's gathered buffer (egress 1x instead
 // of world x).  Same launch shape and placement as push_kernel.
@@ -118,6 +106,23 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag
 	{
 		tag += *epoch;
 		// tags increase monotonically; signed distance handles wrap-around
+		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
+			__nanosleep(200);
+		__threadfence_system();
+	}
+}
+
+// nvc_gather_wait in ONE launch: acknowledge frame `ack_tag` to every peer (0: nothing to acknowledge), then wait for `tag`
+__global__ void ack_and_wait_kernel(uint32_t* const* peer_flags, const uint32_t* flags, int world, int rank, uint32_t ack_tag, uint32_t tag, const uint32_t* epoch)
+{
+	int q = threadIdx.x;
+	if (q < world)
+	{
+		const uint32_t e = *epoch;
+		__threadfence_system();
+		if (ack_tag)
+			*reinterpret_cast<volatile uint32_t*>(peer_flags[q] + kAckBase + rank) = ack_tag + e;
+		tag += e;
 		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
 			__nanosleep(200);
 		__threadfence_system();
@@ -494,18 +499,18 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 	if (!on_context_device(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaError_t e = cudaSuccess;
+	// the acknowledgement of frame T-1 rides in the same launch as the wait for frame T (after this rank's own copies of frame T
+	// are done: acknowledgements only ever depend on earlier frames, so the order cannot deadlock)
+	uint32_t ack_tag = 0;
 	if (g->tag >= 2 && g->acked_tag != g->tag - 1)
 	{
-		raise_acks_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->world, g->rank, g->tag - 1, g->count_stage + 8);
-		e = cudaGetLastError();
+		ack_tag = g->tag - 1;
 		g->acked_tag = g->tag - 1;
 	}
-	if (e == cudaSuccess)
-		e = cudaStreamWaitEvent(s, g->join[0], 0);
+	cudaError_t e = cudaStreamWaitEvent(s, g->join[0], 0);
 	if (e == cudaSuccess)
 	{
-		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag, g->count_stage + 8);
+		ack_and_wait_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->flags, g->world, g->rank, ack_tag, g->tag, g->count_stage + 8);
 		e = cudaGetLastError();
 	}
 	if (e != cudaSuccess)

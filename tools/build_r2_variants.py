@@ -13,6 +13,9 @@ VARIANTS = {
     "fb6": ["NVC_FILTER_MIN_BLOCKS=6"],
     "pdl": ["NVC_PDL=1"],  # programmatic dependent launch of every frame kernel
     "smem_items": ["NVC_SMEM_ITEMS=1"],  # exact early cluster kernel: per-batch item table (round-1 experiment)
+    "f55": ["NVC_FILTER_MIN_BLOCKS=5", "NVC_FILTER_MIN_BLOCKS_EARLY=5", "NVC_FILTER_ITEMS=512"],
+    "fe5": ["NVC_FILTER_MIN_BLOCKS_EARLY=5", "NVC_FILTER_ITEMS=512"],  # early filtered kernel: 5 / 6 CTAs per SM (smaller item table)
+    "fe6": ["NVC_FILTER_MIN_BLOCKS_EARLY=6", "NVC_FILTER_ITEMS=512"],
     "pipe0": ["NVC_FILTER_PIPELINE=0"],  # meshlet prefetch distance of the filtered cluster kernels, in chunks
     "pipe1": ["NVC_FILTER_PIPELINE=1"],
     "pipe2": ["NVC_FILTER_PIPELINE=2"],
