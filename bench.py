@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the moving-camera and task-shading regions")
-    ap.add_argument("--gather", default="ce", choices=["ce", "sm", "mc", "fused", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), mc = one NVSwitch-multicast store kernel per rank (symmetric memory), fused = the late drawcull itself stores its commands through the multicast mapping, nccl = ncclAllGather, none = skip")
+    ap.add_argument("--gather", default="mc", choices=["ce", "sm", "mc", "fused", "nccl", "none"], help="multi-GPU exchange of the late MeshTaskCommand slabs + counters: ce = copy-engine peer pushes over NVLink (no SMs), mc = one NVSwitch-multicast store kernel per rank (symmetric memory), fused = the late drawcull itself stores its commands through the multicast mapping, nccl = ncclAllGather, none = skip")
     return ap.parse_args()
 
 
@@ -611,14 +611,18 @@ def main():
     pass_ms, raster_ms = passes_of(ev)
 
     # ---- the same frames as CUDA-graph launches (graph replay; no per-launch host work, no timing events between
-    # the passes).  Calls of the C ABI only enqueue, so a frame captures as is.  With the peer exchange (nvc_gather_*) a graph holds
-    # GF = 4 frames — the frame tags and the parity-selected receive buffers are baked into it — followed by the wait for its last
-    # push and nvc_gather_graph_advance, which moves the tags of the next replay on; three of the four exchanges still overlap the
-    # following frame's early passes. ----
+    # the passes).  Calls of the C ABI only enqueue, so a frame captures as is.
+    # Multi-GPU: frames WITHOUT an exchange (--gather none) are replayed the same way.  Frames with the peer exchange are replayable
+    # too (nvc_gather_graph_advance: GF = 4 frames per graph, verified at N = 2, profiles/r2_bench_n2_*.json) but that path is opt-in
+    # (NVC_BENCH_GRAPH_EXCHANGE=1): it has not been run on 8 GPUs, and a capture that fails on one rank only must not be able to
+    # take a scaling run down, so the default at N > 1 is the eager region above. ----
     graph_ms = None
     graph_note = None
-    GF = 4 if peer else 1
-    if os.environ.get("NVC_BENCH_GRAPH", "1") != "0" and K >= GF:
+    with_exchange = world > 1 and gather != "none"
+    GF = 4 if (peer and with_exchange) else 1
+    want_graph = os.environ.get("NVC_BENCH_GRAPH", "1") != "0" and K >= GF and (not with_exchange or (peer and os.environ.get("NVC_BENCH_GRAPH_EXCHANGE", "0") == "1"))
+    if want_graph:
+        graph = None
         try:
             drain()
             side = torch.cuda.Stream(dev)
@@ -629,12 +633,21 @@ def main():
                 drain()
             sync_all()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local" if world > 1 else "global"):  # (other threads of a multi-GPU process — the NCCL watchdog — must not invalidate the capture)
                 for _ in range(GF):
                     frame(cd)
                 drain()
-                if peer:
+                if with_exchange:
                     check(lib.nvc_gather_graph_advance(path.ctx, path._stream(), GF), path.ctx, "nvc_gather_graph_advance")
+        except Exception as e:
+            graph_note = str(e)[:200]
+            graph = None
+            torch.cuda.synchronize()
+        # every rank takes the same decision BEFORE anything rank-divergent happens (the regions below contain collectives)
+        ok_t = torch.tensor([1 if graph is not None else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        if int(ok_t.item()):
             reps = K // GF
             for _ in range(3):
                 graph.replay()
@@ -642,42 +655,20 @@ def main():
             for rep in range(3):  # three regions of K frames: median and min reported
                 per.append(timed(lambda k: graph.replay(), reps) * (K / float(reps * GF)))
             graph_ms = {"median": float(np.median(per)), "min": float(min(per))}
-            del graph
-        except Exception as e:
-            graph_note = str(e)[:200]
-            torch.cuda.synchronize()
-        ok_t = torch.tensor([1 if graph_ms else 0], dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)  # a rank whose capture failed must not leave the others with a graph number
-        if not int(ok_t.item()):
-            graph_ms = None
+        elif with_exchange:
+            # a failed capture has advanced this rank's frame tags without running the frames: the exchange cannot go on
+            raise SystemExit("bench.py: CUDA-graph capture of the exchange failed (%s); run without NVC_BENCH_GRAPH_EXCHANGE" % graph_note)
+        del graph
+
     # ---- multi-GPU: the same frames WITHOUT the exchange (cull-only and cull + gather scaling are both reported) ----
     cull_only_ms = None
-    if world > 1 and gather != "none":
-        try:
-            drain()
-            xchg["on"] = False
-            side2 = torch.cuda.Stream(dev)
-            side2.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side2):
-                frame(cd)
-            sync_all()
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, stream=side2):
-                frame(cd)
-            for _ in range(3):
-                g2.replay()
-            cull_only_ms = timed(lambda k: g2.replay(), K)
-            del g2
-        except Exception as e:
-            graph_note = (graph_note or "") + " cull-only: " + str(e)[:120]
-            torch.cuda.synchronize()
+    if with_exchange:
+        drain()
+        xchg["on"] = False
+        for _ in range(2):
+            frame(cd)
+        cull_only_ms = timed(lambda k: frame(cd), K)
         xchg["on"] = True
-        if world > 1:
-            ok2 = torch.tensor([1 if cull_only_ms else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
-            if not int(ok2.item()):
-                cull_only_ms = None
 
     # headline = graph replay when it ran (that is how a host would drive the frame), eager otherwise
     max_ms = graph_ms["median"] if graph_ms else min(eager_ms, plain_ms)
@@ -728,6 +719,14 @@ def main():
           multi_gpu_verified = bool(flag.item())
       except Exception as e:  # the verification must never take the measurement down (ranks may then disagree: report, do not hang)
         multi_gpu_note = str(e)[:160]
+
+    exchange_timed_out = None
+    if world > 1 and peer:
+        flag = ctypes.c_int(0)
+        if lib.nvc_gather_status(path.ctx, ctypes.byref(flag)) == 0:
+            t = torch.tensor([flag.value], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exchange_timed_out = bool(t.item())
 
     def run_moving_camera():
         """yaw 0.2 degrees per step: the late pass now emits clusters and flips visibility bits"""
@@ -962,7 +961,7 @@ def main():
                 "eager_no_events_ms_per_step": plain_ms / K,
                 **({"graph_unavailable": graph_note} if graph_note else {}),
             },
-            **({"without_exchange": {"value": tested_all * K / (cull_only_ms * 1e-3), "unit": "meshlets/s", "ms_per_step": cull_only_ms / K, "what": "the same frames with the all-gather switched off (--gather none), CUDA-graph replay, same process: cull-only scaling beside cull + gather (SURVEY 8(e))"}} if cull_only_ms else {}),
+            **({"without_exchange": {"value": tested_all * K / (cull_only_ms * 1e-3), "unit": "meshlets/s", "ms_per_step": cull_only_ms / K, "what": "the same frames with the all-gather switched off (--gather none), eager launches like the headline region at N > 1, same process: cull-only scaling beside cull + gather (SURVEY 8(e))"}} if cull_only_ms else {}),
             "gpu_launches": gpu_launches,
             "gather_transport": transport if not gather_note else "ce",
             **({"gather_note": gather_note} if gather_note else {}),
@@ -980,14 +979,16 @@ def main():
             peak_i = 148 * 4 * mhz * 1e6
             line["issue_roofline"] = {"kernel": KERNEL_OF_PASS["clustercull_late"], "warp_instructions_per_launch": inst, "achieved_ginst_s": inst / (mean_ms[4] * 1e-3) / 1e9, "peak_ginst_s": peak_i / 1e9, "frac": inst / (mean_ms[4] * 1e-3) / peak_i}
         if multi_gpu_verified is not None:
-            line["multi_gpu_verified"] = multi_gpu_verified
+            line["multi_gpu_verified"] = multi_gpu_verified and not exchange_timed_out
+        if exchange_timed_out:
+            line["exchange_timed_out"] = True  # a device-side wait of the protocol gave up (nvc_gather_status): the gathered data are void
         if multi_gpu_note:
             line["multi_gpu_verified_error"] = multi_gpu_note
         line.update(extras)
         if e2e:
             line["e2e"] = e2e
             line["e2e_incremental"] = e2e_inc
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, scene, cpu_threads())
         print(json.dumps(line))
     if world > 1:

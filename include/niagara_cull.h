@@ -356,6 +356,9 @@ NVC_API int nvc_gather_buffers(NvcContext* ctx, void** gathered_slabs, uint32_t*
  * nvc_gather_push calls captured (must be even); every replay then shifts the tags of the next one by `frames`.  Each captured push
  * needs its nvc_gather_wait inside the same capture; all ranks replay the same graphs the same number of times. */
 NVC_API int nvc_gather_graph_advance(NvcContext* ctx, void* stream, uint32_t frames);
+/* The device-side waits of the protocol give up after ~20 s (a peer that crashed or disagrees about the frame) instead of hanging the
+ * GPU; *timed_out = 1 from then on (the gathered data are undefined, later waits return at once).  Synchronises the device. */
+NVC_API int nvc_gather_status(NvcContext* ctx, int* timed_out);
 /* transport of nvc_gather_push: 0 = copy engines (default), 2 / 3 = NVSwitch multicast (below), 1 = a 32-CTA kernel on a high-priority stream that writes only
  * the valid count x 20 bytes with 16-byte peer stores (also selectable with NVC_GATHER_MODE=sm) */
 NVC_API int nvc_gather_set_mode(NvcContext* ctx, int mode);

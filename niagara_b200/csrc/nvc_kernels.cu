@@ -271,7 +271,6 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 		d0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 		d1[k] = make_float4(0.f, 0.f, 0.f, 1.f);
 		d2[k] = make_uint4(0u, 0u, 0u, 0u);
-		dv[k] = 0;
 		reached[k] = false;
 		if (di[k] < cd.drawCount)
 		{
@@ -279,17 +278,21 @@ __global__ void __launch_bounds__(kDrawBlock) drawcull_kernel(const DrawCullPara
 			d0[k] = ldg_f4(dp);      // position.xyz, scale
 			d1[k] = ldg_f4(dp + 16); // orientation
 			d2[k] = ldg_u4(dp + 32); // meshIndex, meshletVisibilityOffset, postPass, materialIndex
-			// draw visibility: requested together with the MeshDraw (for every draw in range, also those of the other postPass), so
-			// that it is not one more dependent round trip in the life of the CTA
-			dv[k] = p.draw_visibility[di[k]];
 			reached[k] = d2[k].z == cd.postPass; // :63
 		}
 	}
 	// ---- phase 2: draw visibility ----
 #pragma unroll
 	for (int k = 0; k < kDPT; ++k)
-		if (reached[k] && !LATE && dv[k] == 0) // :67
-			reached[k] = false;
+	{
+		dv[k] = 0;
+		if (reached[k])
+		{
+			dv[k] = p.draw_visibility[di[k]];
+			if (!LATE && dv[k] == 0) // :67
+				reached[k] = false;
+		}
+	}
 	// ---- phase 3: mesh heads (dependent on meshIndex) ----
 	float4 m0[kDPT];
 	uint4 h1[kDPT];

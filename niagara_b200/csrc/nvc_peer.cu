@@ -76,6 +76,18 @@ __global__ void __launch_bounds__(256) push_kernel(const uint4* __restrict__ loc
 	__threadfence_system();
 }
 
+// tells every peer that this rank is done with frame `tag`: acks[rank] = tag in the peer's memory
+__global__ void raise_acks_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t tag, const uint32_t* epoch)
+{
+	int p = threadIdx.x;
+	if (p < world)
+	{
+		tag += *epoch;
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t*>(peer_flags[p] + kAckBase + rank) = tag;
+	}
+}
+
 // Multicast variant of the push: every 16-byte unit of the VALID part of the slab is stored ONCE, through the NVSwitch
 // multicast alias of this rank's slot — the switch replicates it into every rank's gathered buffer (egress 1x instead
 // of world x).  Same launch shape and placement as push_kernel.
@@ -99,32 +111,29 @@ __global__ void __launch_bounds__(256) mc_push_kernel(const uint4* __restrict__ 
 	__threadfence_system();
 }
 
-__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag, const uint32_t* epoch)
+// A peer that never answers (a crashed process, ranks that disagree about the frame they are in) must not hang this GPU for ever:
+// after ~20 s (SM cycles) a wait gives up and marks the exchange DEAD (word 1 of `epoch`); every later wait returns at once and
+// nvc_gather_status reports it.  The gathered data are then undefined; the caller decides what to do.
+constexpr long long kSpinLimitCycles = 40000000000ll;
+
+__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t tag, uint32_t* epoch)
 {
 	int q = threadIdx.x;
 	if (q < world)
 	{
-		tag += *epoch;
+		tag += epoch[0];
+		volatile uint32_t* dead = epoch + 1;
+		const long long t0 = clock64();
 		// tags increase monotonically; signed distance handles wrap-around
 		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
+		{
+			if (*dead != 0u || clock64() - t0 > kSpinLimitCycles)
+			{
+				*dead = 1u;
+				break;
+			}
 			__nanosleep(200);
-		__threadfence_system();
-	}
-}
-
-// nvc_gather_wait in ONE launch: acknowledge frame `ack_tag` to every peer (0: nothing to acknowledge), then wait for `tag`
-__global__ void ack_and_wait_kernel(uint32_t* const* peer_flags, const uint32_t* flags, int world, int rank, uint32_t ack_tag, uint32_t tag, const uint32_t* epoch)
-{
-	int q = threadIdx.x;
-	if (q < world)
-	{
-		const uint32_t e = *epoch;
-		__threadfence_system();
-		if (ack_tag)
-			*reinterpret_cast<volatile uint32_t*>(peer_flags[q] + kAckBase + rank) = ack_tag + e;
-		tag += e;
-		while (int32_t(*reinterpret_cast<const volatile uint32_t*>(flags + q) - tag) < 0)
-			__nanosleep(200);
+		}
 		__threadfence_system();
 	}
 }
@@ -158,7 +167,7 @@ struct NvcGather
 	bool fused_consumed = false; // the armed late drawcull has been launched
 	cudaStream_t side[kSideStreams] = {};
 	cudaEvent_t fork = nullptr, join[kSideStreams] = {};
-	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity; word 8: the graph epoch (see advance_epoch_kernel)
+	uint32_t* count_stage = nullptr; // [2][4] snapshot of the local counters, by tag parity; word 8: the graph epoch (see advance_epoch_kernel), word 9: the "exchange dead" mark
 	cudaEvent_t acked = nullptr;
 	uint32_t tag = 0, acked_tag = 0;
 	bool connected = false;
@@ -499,18 +508,18 @@ NVC_API int nvc_gather_wait(NvcContext* ctx, void* stream)
 	if (!on_context_device(ctx))
 		return NVC_ERROR_INVALID_ARGUMENT;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	// the acknowledgement of frame T-1 rides in the same launch as the wait for frame T (after this rank's own copies of frame T
-	// are done: acknowledgements only ever depend on earlier frames, so the order cannot deadlock)
-	uint32_t ack_tag = 0;
+	cudaError_t e = cudaSuccess;
 	if (g->tag >= 2 && g->acked_tag != g->tag - 1)
 	{
-		ack_tag = g->tag - 1;
+		raise_acks_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->world, g->rank, g->tag - 1, g->count_stage + 8);
+		e = cudaGetLastError();
 		g->acked_tag = g->tag - 1;
 	}
-	cudaError_t e = cudaStreamWaitEvent(s, g->join[0], 0);
+	if (e == cudaSuccess)
+		e = cudaStreamWaitEvent(s, g->join[0], 0);
 	if (e == cudaSuccess)
 	{
-		ack_and_wait_kernel<<<1, kMaxWorld, 0, s>>>(g->d_peer_flags, g->flags, g->world, g->rank, ack_tag, g->tag, g->count_stage + 8);
+		wait_flags_kernel<<<1, kMaxWorld, 0, s>>>(g->flags, g->world, g->tag, g->count_stage + 8);
 		e = cudaGetLastError();
 	}
 	if (e != cudaSuccess)
@@ -687,6 +696,23 @@ NVC_API int nvc_gather_graph_advance(NvcContext* ctx, void* stream, uint32_t fra
 		ctx->last_error = std::string("nvc_gather_graph_advance: ") + cudaGetErrorString(e);
 		return NVC_ERROR_CUDA;
 	}
+	return NVC_OK;
+}
+
+// 1 in *timed_out when a wait of this context has given up (see wait_flags_kernel); synchronises the device.
+NVC_API int nvc_gather_status(NvcContext* ctx, int* timed_out)
+{
+	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
+	if (!g || !timed_out)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	uint32_t v = 0;
+	cudaError_t e = cudaMemcpy(&v, g->count_stage + 9, sizeof(v), cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess)
+	{
+		ctx->last_error = std::string("nvc_gather_status: ") + cudaGetErrorString(e);
+		return NVC_ERROR_CUDA;
+	}
+	*timed_out = v != 0u;
 	return NVC_OK;
 }
 

@@ -90,6 +90,7 @@ SIGNATURES = [
     ("nvc_gather_fuse_next_drawcull", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_buffers", ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     ("nvc_gather_graph_advance", ctypes.c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
+    ("nvc_gather_status", ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int)]),
 ]
 
 
