@@ -781,7 +781,7 @@ def main():
         }
 
     extras = {}
-    if not args.no_extras and args.workload == "C4":
+    if not args.no_extras and args.workload == "C4" and world == 1:  # single-GPU diagnostics (write path, task-shading mode)
         for key, fn in (("moving_camera", run_moving_camera), ("task_shading", run_task_shading)):
             try:
                 extras[key] = fn()
@@ -852,39 +852,40 @@ def main():
         path.db = db_orig
         depth = depth_sets[0]
 
-        # incremental: what the reference's frame loop moves per frame (niagara.cpp:1362-1411, 1487-1516): the CullData push
-        # constants and the MeshDraws the animation touched go up (one packed {index, MeshDraw} copy + nvc_update_draws
-        # scatter), the two indirect-count words come back; depth and the visible slabs never leave the device.
-        n_anim = max(1, D // 100)
-        anim_idx = np.linspace(0, D - 1, n_anim).astype(np.uint32)
-        idx_host = torch.from_numpy(anim_idx.view(np.int32).copy()).pin_memory()
-        val_host = torch.from_numpy(np.ascontiguousarray(scene.draws[anim_idx]).view(np.uint8).reshape(-1).copy()).pin_memory()
-        idx_dev = torch.empty_like(idx_host, device=dev)
-        val_dev = torch.empty_like(val_host, device=dev)
-        cd_host = torch.from_numpy(np.frombuffer(bytes(cd), dtype=np.uint8).copy()).pin_memory()
-        cd_dev = torch.empty(cd_host.numel(), dtype=torch.uint8, device=dev)
+        if world == 1:
+            # incremental: what the reference's frame loop moves per frame (niagara.cpp:1362-1411, 1487-1516): the CullData push
+            # constants and the MeshDraws the animation touched go up (one packed {index, MeshDraw} copy + nvc_update_draws
+            # scatter), the two indirect-count words come back; depth and the visible slabs never leave the device.
+            n_anim = max(1, D // 100)
+            anim_idx = np.linspace(0, D - 1, n_anim).astype(np.uint32)
+            idx_host = torch.from_numpy(anim_idx.view(np.int32).copy()).pin_memory()
+            val_host = torch.from_numpy(np.ascontiguousarray(scene.draws[anim_idx]).view(np.uint8).reshape(-1).copy()).pin_memory()
+            idx_dev = torch.empty_like(idx_host, device=dev)
+            val_dev = torch.empty_like(val_host, device=dev)
+            cd_host = torch.from_numpy(np.frombuffer(bytes(cd), dtype=np.uint8).copy()).pin_memory()
+            cd_dev = torch.empty(cd_host.numel(), dtype=torch.uint8, device=dev)
 
-        def inc_frame(k):
-            idx_dev.copy_(idx_host, non_blocking=True)
-            val_dev.copy_(val_host, non_blocking=True)
-            cd_dev.copy_(cd_host, non_blocking=True)  # the push constants' bytes (the C ABI takes them by value from the host)
-            check(lib.nvc_update_draws(path.ctx, path._stream(), ctypes.c_void_p(path.db.data_ptr()), D, ctypes.c_void_p(idx_dev.data_ptr()), ctypes.c_void_p(val_dev.data_ptr()), n_anim), path.ctx, "nvc_update_draws")
-            frame(cd)
-            count_host[:4].copy_(path.dccb, non_blocking=True)
-            count_host[4:].copy_(path.ccb, non_blocking=True)
-            main_stream.synchronize()
+            def inc_frame(k):
+                idx_dev.copy_(idx_host, non_blocking=True)
+                val_dev.copy_(val_host, non_blocking=True)
+                cd_dev.copy_(cd_host, non_blocking=True)  # the push constants' bytes (the C ABI takes them by value from the host)
+                check(lib.nvc_update_draws(path.ctx, path._stream(), ctypes.c_void_p(path.db.data_ptr()), D, ctypes.c_void_p(idx_dev.data_ptr()), ctypes.c_void_p(val_dev.data_ptr()), n_anim), path.ctx, "nvc_update_draws")
+                frame(cd)
+                count_host[:4].copy_(path.dccb, non_blocking=True)
+                count_host[4:].copy_(path.ccb, non_blocking=True)
+                main_stream.synchronize()
 
-        for k in range(2):
-            inc_frame(k)
-        i_ms = timed(inc_frame, K)
-        e2e_inc = {
-            "value": tested_all * K / (i_ms * 1e-3),
-            "unit": "meshlets/s",
-            "h2d_bytes_per_step": int(idx_host.numel() * 4 + val_host.numel() + cd_host.numel()),
-            "d2h_bytes_per_step": 32,
-            "ms_per_step": i_ms / K,
-            "what": "per step: H2D CullData + %d animated MeshDraws (1%% of the scene, packed {index, MeshDraw} + nvc_update_draws scatter), the frame, D2H of the two indirect-count blocks, host waits for them" % n_anim,
-        }
+            for k in range(2):
+                inc_frame(k)
+            i_ms = timed(inc_frame, K)
+            e2e_inc = {
+                "value": tested_all * K / (i_ms * 1e-3),
+                "unit": "meshlets/s",
+                "h2d_bytes_per_step": int(idx_host.numel() * 4 + val_host.numel() + cd_host.numel()),
+                "d2h_bytes_per_step": 32,
+                "ms_per_step": i_ms / K,
+                "what": "per step: H2D CullData + %d animated MeshDraws (1%% of the scene, packed {index, MeshDraw} + nvc_update_draws scatter), the frame, D2H of the two indirect-count blocks, host waits for them" % n_anim,
+            }
 
     clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
     if rank == 0:
@@ -987,7 +988,8 @@ def main():
         line.update(extras)
         if e2e:
             line["e2e"] = e2e
-            line["e2e_incremental"] = e2e_inc
+            if e2e_inc:
+                line["e2e_incremental"] = e2e_inc
         if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, scene, cpu_threads())
         print(json.dumps(line))

@@ -1,4 +1,4 @@
-"""GPU variants of two CPU checks and the CUDA-graph capture of a frame (parked in round 1, part of the -m gpu suite since round 2).
+"""PARKED (see README.md here): GPU variants of two CPU checks and the CUDA-graph capture of a frame.
 
 1. end-to-end on rasterised depth with the CUDA path as culler (tests/test_end_to_end_raster.py with VisibilityPath):
    device buffers are mirrored into an OraclePath used only as a buffer holder for the reference's mesh shader +
@@ -34,7 +34,7 @@ def _mirror(torch, g, o):
     o.dvb[:] = g.dvb.cpu().numpy().astype(np.uint32)[: len(o.dvb)]
 
 
-def test_cuda_two_phase_frames_on_rasterised_depth(golden_dir):
+def pending_test_cuda_two_phase_frames_on_rasterised_depth(golden_dir):
     import torch
 
     from niagara_b200.path import VisibilityPath
@@ -87,7 +87,7 @@ def test_cuda_two_phase_frames_on_rasterised_depth(golden_dir):
     assert owners_total > 5000
 
 
-def test_hostile_inputs_culling_off(golden_dir):
+def pending_test_hostile_inputs_culling_off(golden_dir):
     import warnings
 
     import hostile
@@ -99,7 +99,7 @@ def test_hostile_inputs_culling_off(golden_dir):
         _run_frames(s, frames=2, toggles=dict(culling=False))
 
 
-def test_frame_in_cuda_graph(golden_dir):
+def pending_test_frame_in_cuda_graph(golden_dir):
     """include/niagara_cull.h promises that pass calls only enqueue (no allocation, no synchronisation) and can be captured into a
     CUDA graph: capture one frame, replay it over two frames of state, compare with the oracle."""
     import torch
