@@ -212,6 +212,11 @@ NVC_API int nvc_set_hiz_staging(NvcContext* ctx, uint32_t texels);
  * scattered texels.  The image is valid only for pyramids written by nvc_depth_pyramid: a caller that stores texels itself must
  * not prepare (or must pass NULL here to release).  Allocates / frees: call outside stream capture.  hiz == NULL releases. */
 NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz);
+/* Diagnostics / tests: the device pointer of the footprint image, its first mip (mips below it have no image), the entry offset of
+ * every mip (offset_out[NVC_MAX_HIZ_LEVELS], floats) and the total entry count.  Mip l of width w, height h: rows of pitch
+ * (w + 4) & ~3 entries, entry (i + 1, j + 1) = min of texels (i..i+1, j..j+1) clamped to the mip, i in [-1, w-1], j in [-1, h-1].
+ * Valid after the nvc_depth_pyramid call that wrote it; *image_out = NULL when no image is prepared. */
+NVC_API int nvc_hiz_footprints(NvcContext* ctx, const float** image_out, uint32_t* first_level_out, uint32_t* offset_out, uint32_t* total_out);
 
 /* The cluster pass runs by default as a conservative FILTER (fused arithmetic with an error margin on every comparison,
  * per-command transforms) whose undecided meshlets are re-evaluated by the exact strict-IEEE path: results are identical,

@@ -571,6 +571,21 @@ NVC_API int nvc_prepare_hiz(NvcContext* ctx, const NvcHiZ* hiz)
 	return NVC_OK;
 }
 
+NVC_API int nvc_hiz_footprints(NvcContext* ctx, const float** image_out, uint32_t* first_level_out, uint32_t* offset_out, uint32_t* total_out)
+{
+	if (!ctx || !image_out)
+		return NVC_ERROR_INVALID_ARGUMENT;
+	const bool have = ctx->hiz_fp && ctx->hiz_fp_valid;
+	*image_out = have ? ctx->hiz_fp : nullptr;
+	if (first_level_out)
+		*first_level_out = ctx->hiz_fp_first;
+	if (offset_out)
+		memcpy(offset_out, ctx->hiz_fp_offset, sizeof(ctx->hiz_fp_offset));
+	if (total_out)
+		*total_out = have ? ctx->hiz_fp_total : 0u;
+	return NVC_OK;
+}
+
 NVC_API int nvc_update_draws(NvcContext* ctx, void* stream, NvcMeshDraw* draws, uint32_t draw_count, const uint32_t* update_indices,
     const NvcMeshDraw* update_values, uint32_t count)
 {

@@ -80,6 +80,7 @@ SIGNATURES = [
     ("nvc_nccl_unique_id", ctypes.c_int, [c_void_p]),
     ("nvc_nccl_init", ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int]),
     ("nvc_allgather_visible", ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p]),
+    ("nvc_hiz_footprints", ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     ("nvc_gather_create", ctypes.c_int, [c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, c_void_p]),
     ("nvc_gather_connect", ctypes.c_int, [c_void_p, c_void_p]),
     ("nvc_gather_push", ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

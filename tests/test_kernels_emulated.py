@@ -128,6 +128,34 @@ def test_pyramid_sizes(size):
     assert np.array_equal(o.pyramid_texels.view(np.uint32), e.pyramid_texels.view(np.uint32))
 
 
+@pytest.mark.parametrize("size", [(64, 64), (100, 60), (30, 17), (129, 257), (2, 2), (1, 1), (256, 8), (1920, 1080), (1000, 3), (4096, 16)])
+def test_footprint_image(size):
+    """the derived footprint image (nvc_prepare_hiz): every entry of every mip = min of the clamped 2 x 2 texel footprint, for
+    pyramids whose rows take the 16-byte path of footprint_kernel and for shapes that do not (widths 1, 2, 3 mod 4, tiny mips)"""
+    import ctypes
+
+    w, h = size
+    depth = np.random.default_rng(w * 11 + h).random((h, w), dtype=np.float32)
+    blank = (np.zeros(1, layout.MESH_DTYPE), np.zeros(1, layout.MESHLET_DTYPE), np.zeros(1, layout.MESHDRAW_DTYPE))
+    e = emu_lib.EmuPath(*blank, w, h, prepare_meshes=False)
+    e.pyramid(depth)
+    image, first, total = ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_uint32()
+    offsets = (ctypes.c_uint32 * 16)()
+    assert e.emu.nvc_hiz_footprints(e.ctx, ctypes.byref(image), ctypes.byref(first), offsets, ctypes.byref(total)) == 0
+    assert image.value and total.value > 0
+    fp = np.ctypeslib.as_array(ctypes.cast(image.value, ctypes.POINTER(ctypes.c_float)), shape=(total.value,))  # emulated device memory is host memory
+    hz = e.hiz
+    for l in range(first.value, hz.levels):
+        lw, lh = max(1, hz.width >> l), max(1, hz.height >> l)
+        t = e.pyramid_texels[hz.level_offset[l] : hz.level_offset[l] + lw * lh].reshape(lh, lw)
+        pad = np.pad(t, 1, mode="edge")  # texel (-1) = texel 0, texel w = texel w - 1
+        want = np.minimum(np.minimum(pad[:-1, :-1], pad[:-1, 1:]), np.minimum(pad[1:, :-1], pad[1:, 1:]))  # (lh + 1, lw + 1)
+        pitch = (lw + 4) & ~3
+        got = fp[offsets[l] : offsets[l] + pitch * (lh + 1)].reshape(lh + 1, pitch)[:, : lw + 1]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (size, l)
+    e.close()
+
+
 def test_tiny_and_empty_inputs(golden_dir):
     _frames(_kp(golden_dir, 1))
     s = _kp(golden_dir, 3)
