@@ -705,6 +705,8 @@ NVC_API int nvc_gather_status(NvcContext* ctx, int* timed_out)
 	NvcGather* g = ctx ? static_cast<NvcGather*>(ctx->gather) : nullptr;
 	if (!g || !timed_out)
 		return NVC_ERROR_INVALID_ARGUMENT;
+	if (!on_context_device(ctx))
+		return NVC_ERROR_INVALID_ARGUMENT;
 	uint32_t v = 0;
 	cudaError_t e = cudaMemcpy(&v, g->count_stage + 9, sizeof(v), cudaMemcpyDeviceToHost);
 	if (e != cudaSuccess)
