@@ -926,7 +926,8 @@ def main():
             "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": workload_label(args) + "; per GPU",
+                "workload": workload_label(args),  # (per GPU: weak scaling; identical string in the reference arm)
+                "per": "GPU (weak scaling: every rank culls its own scene of this size)",
                 "step": "one frame: early drawcull+tasksubmit, early clustercull+clustersubmit, depth pyramid%s, late drawcull+tasksubmit, late clustercull+clustersubmit (%d launches)%s" % (" + footprint image" if has_fp else "", 6 if has_fp else 5, {"ce": "; + all-gather of the late MeshTaskCommand slabs+counters by copy-engine peer pushes over NVLink (nvc_gather_*), every frame, pipelined one frame deep: the exchange of frame k must complete before drawcull(late) of frame k+1 overwrites the slab, and the last one before the clock stops", "sm": "; + all-gather of the late MeshTaskCommand slabs+counters by a unicast peer-store kernel (nvc_gather_*), every frame, one frame deep", "mc": "; + all-gather of the late MeshTaskCommand slabs+counters by ONE NVSwitch-multicast store kernel per rank (nvc_gather_*, symmetric memory), every frame, one frame deep", "fused": "; + all-gather of the late MeshTaskCommand slabs FUSED into drawcull(late): its command write-out also goes through the NVSwitch multicast mapping (counters + flags follow), every frame, one frame deep", "nccl": "; + ncclAllGather of the late MeshTaskCommand slabs+counters on a high-priority side stream", "none": ""}[gather]),
                 "counting": "value = meshlet instances TESTED by the two cluster passes per second (early %d + late %d per step per GPU); draws_per_s likewise (early %d + late %d)" % (pr["tested_early"], pr["tested_late"], pr["early_reached"], D),
                 "l2": "inputs larger than L2 (Meshlet[] %d MB + MeshDraw[] %d MB + Mesh[] %d MB + depth %d MB per step vs 126 MB L2), no flush" % (scene.meshlets.nbytes >> 20, scene.draws.nbytes >> 20, scene.meshes.nbytes >> 20, scene.depth.nbytes >> 20),
