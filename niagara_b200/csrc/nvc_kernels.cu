@@ -1246,6 +1246,7 @@ constexpr int kFQueue = 64;            // undecided items per warp (drained 32 a
 // early pass: (command lane, meshlet lane) of every flattened item of one (sub-)batch; batches with more set bits are
 // processed as four sub-batches of 8 commands (<= 512 items)
 constexpr uint32_t kFItems = NVC_FILTER_ITEMS;
+static_assert(kFItems >= 8u * 64u, "a sub-batch of 8 commands (<= 64 meshlets each) must fit the item table");
 
 // One block of shared memory per warp: every field sits at a compile-time offset from the warp's base address.
 template <bool LATE>

@@ -233,9 +233,13 @@ def test_hostile_inputs(golden_dir):
         _frames(s, frames=2, toggles=dict(culling=False))
 
 
-@pytest.mark.parametrize("defines", [("NVC_PACKED=1",), ("NVC_ALIVE_FLATTEN=0",), ("NVC_UNIFORM_FLATTEN=0",), ("NVC_ALIVE_FLATTEN=0", "NVC_UNIFORM_FLATTEN=0"), ("NVC_SMEM_ITEMS=1",)])
+@pytest.mark.parametrize(
+    "defines",
+    [("NVC_PACKED=1",), ("NVC_ALIVE_FLATTEN=0",), ("NVC_UNIFORM_FLATTEN=0",), ("NVC_ALIVE_FLATTEN=0", "NVC_UNIFORM_FLATTEN=0"), ("NVC_SMEM_ITEMS=1",), ("NVC_FILTER_ITEMS=512",), ("NVC_FILTER_PIPELINE=1",), ("NVC_FILTER_PIPELINE=0",)],
+)
 def test_build_time_variants(golden_dir, defines):
-    """the compile-time variants of the cluster kernels (packed FP32x2 arithmetic, the flatten strategies)"""
+    """the compile-time variants of the cluster kernels (packed FP32x2 arithmetic, the flatten strategies; filtered kernel: the smallest
+    item table (512 entries), so that the dense batches of the kitten scenes take the 8-command sub-batch path, and the meshlet prefetch distances 1 and 0)"""
     assert _frames(_kp(golden_dir, 3000), defines=defines) > 300
     assert _frames(scenes.config4_scene(draw_count=6000, screen=(512, 512)), defines=defines, cmd_capacity=12000) > 3000
     # several frames with a moving camera: the early pass sees sparse, changing visibility masks
